@@ -1,0 +1,159 @@
+// CUDA-core kernels around the tensor-core convolution:
+//   * conv_first_kernel : CNN1 (cin = 1, K = 9 - no GEMM shape to speak of), DCSCN.py:240-253 first iteration
+//   * conv_last_kernel  : R-CNN1 (cout = 1, no bias / activation) fused with  tf.add(H[-1], x2, "output")
+//                         (DCSCN.py:318-325)
+//   * conv_ref_kernel   : plain fp32 FMA restatement of the tensor-core layer on the same buffers; used only by
+//                         the on-GPU validation tests (option conv_impl = 1), never by default
+//   * small layout helpers for the debug / parity interface
+#pragma once
+#include "common.h"
+#include "epilogue.cuh"
+
+namespace dcscn {
+
+// ------------------------------------------------------------------ CNN1 -----------------------------------
+struct ConvFirstParams {
+  ConvGeom g;            // only n_img, H, W used
+  int ksz;
+  int n_pad;             // padded cout (multiple of 16)
+  const float* x;        // [N, H, W] fp32 (channels == 1)
+  const float* w;        // [k*k][n_pad] fp32, zero padded
+  EpiParams epi;         // EPI_PLANES, out_scale 1
+};
+
+__global__ void __launch_bounds__(256) conv_first_kernel(const ConvFirstParams p) {
+  extern __shared__ float s_w[];  // [taps][n_pad]
+  const int taps = p.ksz * p.ksz;
+  for (int i = threadIdx.x; i < taps * p.n_pad; i += blockDim.x) s_w[i] = p.w[i];
+  __syncthreads();
+  const int groups = p.n_pad >> 4;
+  const int half = p.ksz >> 1;
+  const long long total = (long long)p.g.n_img * p.g.H * p.g.W * groups;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int grp = (int)(idx % groups);
+    const long long pix = idx / groups;
+    const int x = (int)(pix % p.g.W);
+    const int y = (int)((pix / p.g.W) % p.g.H);
+    const int img = (int)(pix / ((long long)p.g.W * p.g.H));
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+    const float* xi = p.x + (size_t)img * p.g.H * p.g.W;
+    for (int t = 0; t < taps; ++t) {
+      const int yy = y + t / p.ksz - half, xx = x + t % p.ksz - half;
+      if (yy < 0 || yy >= p.g.H || xx < 0 || xx >= p.g.W) continue;
+      const float v = __ldg(xi + (size_t)yy * p.g.W + xx);
+      const float* wr = s_w + t * p.n_pad + grp * 16;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[i] = fmaf(v, wr[i], acc[i]);
+    }
+    epilogue_store16(p.epi, p.g, p.n_pad, img, y, x, grp * 16, acc);
+  }
+}
+
+// ---------------------------------------------------------------- R-CNN1 -----------------------------------
+struct ConvLastParams {
+  int n_img, H, W;       // HR resolution
+  int ksz;               // 3
+  int C;                 // input channels
+  int pitch;             // channel pitch of src
+  const float* src;      // [N, H, W, pitch] fp32
+  const float* w;        // [k*k][C] fp32  (cout == 1)
+  float bias;            // 0 for the reference graph
+  const float* x2;       // [N, H, W] bicubic
+  float* y;              // [N, H, W]
+};
+
+constexpr int kLastTW = 32, kLastTH = 8, kLastCC = 8;
+
+__global__ void __launch_bounds__(256) conv_last_kernel(const ConvLastParams p) {
+  extern __shared__ float s_mem[];
+  const int half = p.ksz >> 1;
+  const int PW = kLastTW + 2 * half, PH = kLastTH + 2 * half;
+  float* s_w = s_mem;                                  // [taps][C]
+  float* s_in = s_mem + p.ksz * p.ksz * p.C;           // [PH][PW][kLastCC]
+  const int taps = p.ksz * p.ksz;
+  for (int i = threadIdx.x; i < taps * p.C; i += blockDim.x) s_w[i] = p.w[i];
+
+  const int tiles_x = (p.W + kLastTW - 1) / kLastTW, tiles_y = (p.H + kLastTH - 1) / kLastTH;
+  const int tile = blockIdx.x;
+  const int img = tile / (tiles_x * tiles_y);
+  const int t2 = tile - img * tiles_x * tiles_y;
+  const int ty = t2 / tiles_x, tx = t2 - ty * tiles_x;
+  const int lx = threadIdx.x % kLastTW, ly = threadIdx.x / kLastTW;
+  const int ox = tx * kLastTW + lx, oy = ty * kLastTH + ly;
+  const float* src = p.src + (size_t)img * p.H * p.W * p.pitch;
+
+  float acc = p.bias;
+  for (int c0 = 0; c0 < p.C; c0 += kLastCC) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < PH * PW * kLastCC; i += blockDim.x) {
+      const int c = i % kLastCC;
+      const int pp = i / kLastCC;
+      const int sx = pp % PW, sy = pp / PW;
+      const int gx = tx * kLastTW + sx - half, gy = ty * kLastTH + sy - half;
+      float v = 0.f;
+      if (gx >= 0 && gx < p.W && gy >= 0 && gy < p.H && (c0 + c) < p.C)
+        v = __ldg(src + ((size_t)gy * p.W + gx) * p.pitch + c0 + c);
+      s_in[i] = v;
+    }
+    __syncthreads();
+    const int cc = (p.C - c0) < kLastCC ? (p.C - c0) : kLastCC;
+    for (int t = 0; t < taps; ++t) {
+      const float* si = s_in + ((ly + t / p.ksz) * PW + (lx + t % p.ksz)) * kLastCC;
+      const float* wr = s_w + t * p.C + c0;
+      for (int c = 0; c < cc; ++c) acc = fmaf(si[c], wr[c], acc);
+    }
+  }
+  if (ox < p.W && oy < p.H) {
+    const size_t o = ((size_t)img * p.H + oy) * p.W + ox;
+    p.y[o] = acc + __ldg(p.x2 + o);
+  }
+}
+
+// ---------------------------------------------------- validation conv (CUDA cores, fp32) -------------------
+__global__ void __launch_bounds__(128) conv_ref_kernel(const ConvRefParams p) {
+  const int groups = p.n_total_pad >> 4;
+  const int half = p.ksz >> 1;
+  const long long total = (long long)p.g.n_img * p.g.H * p.g.W * groups;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int grp = (int)(idx % groups);
+    const long long pix = idx / groups;
+    const int x = (int)(pix % p.g.W);
+    const int y = (int)((pix / p.g.W) % p.g.H);
+    const int img = (int)(pix / ((long long)p.g.W * p.g.H));
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+    for (int t = 0; t < p.ksz * p.ksz; ++t) {
+      const int yy = y + t / p.ksz - half, xx = x + t % p.ksz - half;
+      if (yy < 0 || yy >= p.g.H || xx < 0 || xx >= p.g.W) continue;
+      const size_t base = (((size_t)img * p.g.H + yy) * p.g.W + xx) * p.src_pitch;
+      for (int c = 0; c < p.cin; ++c) {
+        const int q = p.in_map[c];
+        float a = __half2float(p.src_hi[base + q]);
+        if (p.src_lo != nullptr) a += __half2float(p.src_lo[base + q]);
+        const float* wr = p.w + ((size_t)t * p.cin + c) * p.cout;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int n = grp * 16 + i;
+          if (n < p.cout) acc[i] = fmaf(a, __ldg(wr + n), acc[i]);
+        }
+      }
+    }
+    epilogue_store16(p.epi, p.g, p.n_total_pad, img, y, x, grp * 16, acc);
+  }
+}
+
+// ---------------------------------------------------------------- helpers ----------------------------------
+__global__ void planes_to_f32_kernel(const __half* hi, const __half* lo, float* out, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float v = __half2float(hi[i]);
+    if (lo != nullptr) v += __half2float(lo[i]);
+    out[i] = v;
+  }
+}
+
+}  // namespace dcscn

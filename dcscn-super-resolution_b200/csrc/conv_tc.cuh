@@ -1,0 +1,220 @@
+// Implicit-GEMM convolution on tcgen05 tensor cores (sm_100a).
+//
+// Replaces  tf.nn.conv2d(SAME, stride 1, NHWC, HWIO) + bias + PReLU  of the reference
+// (helper/tf_graph.py:104-153 conv2d / build_conv; :238-249 build_pixel_shuffler_layer).
+//
+// GEMM view:  D[M = 128 pixels (TH x TW patch), N = cout (padded to 16)]
+//             = sum over taps (ky,kx) and input-channel chunks of  A_tap[128 x KC] * W_tap[KC x N]
+//   * A tiles are fetched by TMA (4-D tiled tensor map over the NHWC fp16 plane, box {KC, TW, TH, 1});
+//     the box origin is shifted by the tap offset and TMA zero-fills out-of-image pixels, which IS
+//     TF's SAME padding - no halo handling in the kernel.
+//   * fp32-equivalent precision from fp16 tensor cores:  a = a_hi + a_lo,  w*2^s = w_hi + w_lo
+//     (each 11-bit significands), D += a_hi*w_hi + a_lo*w_hi + a_hi*w_lo   (3 x kind::f16 UMMA,
+//     fp32 accumulation in TMEM).  NPLANES == 1 is the single-pass fp16 "fast" mode.
+//   * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..5 = epilogue
+//     (TMEM -> registers -> bias/PReLU/split -> global), double-buffered TMEM accumulators, persistent
+//     CTAs striding over (pixel-tile, column-tile) work items.
+#pragma once
+#include "common.h"
+#include "epilogue.cuh"
+#include "ptx.cuh"
+
+namespace dcscn {
+
+constexpr int kTcThreads = 192;
+constexpr int kMaxStages = 8;
+constexpr int kAccStages = 2;
+constexpr int kAccStride = 256;  // TMEM columns per accumulator stage
+
+template <int KC>
+struct TcSmem {
+  static constexpr int kRowBytes = KC * 2;                  // 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
+  static constexpr int kABytes = kTileM * kRowBytes;        // one A plane tile
+  static constexpr int kSbo = 8 * kRowBytes;                // 8-row core-matrix group stride
+  static constexpr uint64_t kLayout = (KC == 64) ? 2ull : 4ull;  // UMMA LayoutType: SW128 = 2, SW64 = 4
+};
+
+// Shared-memory matrix descriptor for a K-major swizzled operand tile (cute::UMMA::SmemDescriptor).
+template <int KC>
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);              // start address  [0,14)
+  d |= (uint64_t)1 << 16;                                // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(TcSmem<KC>::kSbo >> 4) << 32;          // stride byte offset [32,46)
+  d |= (uint64_t)1 << 46;                                // descriptor version (Blackwell)
+  d |= TcSmem<KC>::kLayout << 61;                        // swizzle mode
+  return d;
+}
+
+// kind::f16 instruction descriptor: fp16 x fp16 -> fp32, A and B K-major, M = 128, N = n_pad.
+__device__ __forceinline__ uint32_t make_idesc_f16(int n_pad) {
+  return (1u << 4) | ((uint32_t)(n_pad >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+}
+
+__host__ __device__ inline size_t tc_stage_bytes(int KC, int nplanes, int n_pad) {
+  return (size_t)nplanes * ((size_t)kTileM * KC * 2 + (size_t)n_pad * KC * 2);
+}
+
+template <int KC, int NPLANES>
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
+               const ConvTCParams p, const int num_stages) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages x (A_hi, A_lo, B_hi, B_lo)] then barriers
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int A_BYTES = TcSmem<KC>::kABytes;
+  const int B_BYTES = p.n_pad * KC * 2;
+  const int STAGE_BYTES = NPLANES * (A_BYTES + B_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)num_stages * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* acc_full = empty_bar + kMaxStages;
+  uint64_t* acc_empty = acc_full + kAccStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kAccStages);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < num_stages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < kAccStages; ++s) {
+      ptx::mbar_init(&acc_full[s], 1);
+      ptx::mbar_init(&acc_empty[s], 4);  // one arrive per epilogue warp
+    }
+    ptx::fence_barrier_init();
+    ptx::fence_proxy_async();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, kAccStages * kAccStride);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const ConvGeom& g = p.g;
+  const int tiles_per_img = g.tiles_x * g.tiles_y;
+  const int num_work = g.n_img * tiles_per_img * p.n_tiles;
+  const int taps = p.ksz * p.ksz;
+  const int half = p.ksz >> 1;
+
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      ptx::prefetch_tensormap(&tm_hi);
+      if (NPLANES == 2) ptx::prefetch_tensormap(&tm_lo);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+        const int n_tile = work % p.n_tiles;
+        const int tile = work / p.n_tiles;
+        const int img = tile / tiles_per_img;
+        const int t2 = tile - img * tiles_per_img;
+        const int ty = t2 / g.tiles_x, tx = t2 - ty * g.tiles_x;
+        const __half* wsrc = p.wpack + (size_t)n_tile * taps * p.chunks * (size_t)(NPLANES * p.n_pad * KC);
+        for (int tap = 0; tap < taps; ++tap) {
+          const int dy = tap / p.ksz - half, dx = tap % p.ksz - half;
+          for (int ch = 0; ch < p.chunks; ++ch) {
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)STAGE_BYTES);
+            ptx::tma_load_4d(st, &tm_hi, &full_bar[stage], ch * KC, tx * g.TW + dx, ty * g.TH + dy, img);
+            if (NPLANES == 2)
+              ptx::tma_load_4d(st + A_BYTES, &tm_lo, &full_bar[stage], ch * KC, tx * g.TW + dx, ty * g.TH + dy, img);
+            ptx::bulk_load(st + NPLANES * A_BYTES, wsrc + (size_t)(tap * p.chunks + ch) * (NPLANES * p.n_pad * KC),
+                           (uint32_t)(NPLANES * B_BYTES), &full_bar[stage]);
+            if (++stage == num_stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer ================================
+    const uint32_t idesc = make_idesc_f16(p.n_pad);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+      ptx::mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kAccStride);
+      uint32_t accumulate = 0;
+      for (int tap = 0; tap < taps; ++tap) {
+        for (int ch = 0; ch < p.chunks; ++ch) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          if (lane == 0) {
+            const uint32_t a_hi = ptx::smem_u32(smem + (size_t)stage * STAGE_BYTES);
+            const uint32_t a_lo = a_hi + A_BYTES;
+            const uint32_t b_hi = a_hi + NPLANES * A_BYTES;
+            const uint32_t b_lo = b_hi + B_BYTES;
+            int ksteps = (p.cin_pad - ch * KC);
+            ksteps = (ksteps > KC ? KC : ksteps) >> 4;
+            for (int ks = 0; ks < ksteps; ++ks) {
+              const uint32_t koff = ks * 32;  // 16 fp16 along K inside the swizzled row
+              const uint64_t da_hi = make_smem_desc<KC>(a_hi + koff);
+              const uint64_t db_hi = make_smem_desc<KC>(b_hi + koff);
+              ptx::mma_f16_ss(tmem_d, da_hi, db_hi, idesc, accumulate);
+              accumulate = 1;
+              if (NPLANES == 2) {
+                const uint64_t da_lo = make_smem_desc<KC>(a_lo + koff);
+                const uint64_t db_lo = make_smem_desc<KC>(b_lo + koff);
+                ptx::mma_f16_ss(tmem_d, da_lo, db_hi, idesc, 1);
+                ptx::mma_f16_ss(tmem_d, da_hi, db_lo, idesc, 1);
+              }
+            }
+            ptx::mma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs have read it
+          }
+          __syncwarp();
+          if (++stage == num_stages) { stage = 0; phase ^= 1; }
+        }
+      }
+      if (lane == 0) ptx::mma_commit(&acc_full[acc]);  // accumulator complete -> epilogue
+      __syncwarp();
+      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // ============================== epilogue ==================================
+    const int quad = warp & 3;               // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;        // pixel index inside the TH x TW patch
+    const int py = row / g.TW, px = row - py * g.TW;
+    const int n_total = p.n_tiles * p.n_pad;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+      const int n_tile = work % p.n_tiles;
+      const int tile = work / p.n_tiles;
+      const int img = tile / tiles_per_img;
+      const int t2 = tile - img * tiles_per_img;
+      const int ty = t2 / g.tiles_x, tx = t2 - ty * g.tiles_x;
+      const int y = ty * g.TH + py, x = tx * g.TW + px;
+      const bool valid = (y < g.H) && (x < g.W);
+
+      ptx::mbar_wait(&acc_full[acc], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kAccStride);
+      for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
+        float v[16];
+        ptx::tmem_ld16(taddr + c0, v);
+        if (valid) epilogue_store16(p.epi, g, n_total, img, y, x, n_tile * p.n_pad + c0, v);
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&acc_empty[acc]);
+      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, kAccStages * kAccStride);
+  }
+}
+
+}  // namespace dcscn

@@ -1,0 +1,914 @@
+// DCSCN engine: graph plan, parameter storage / packing, workspace, launch orchestration and the C-ABI
+// declared in include/dcscn_b200.h.  Stands in for what `sess.run(self.y_)` executed in the reference
+// (DCSCN.py:565; graph built by DCSCN.py:222-332 and helper/tf_graph.py:104-249).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/dcscn_b200.h"
+#include "common.h"
+#include "conv_aux.cuh"
+#include "conv_tc.cuh"
+
+using namespace dcscn;
+
+// ----------------------------------------------------------------------------------------- errors ----
+static thread_local std::string g_last_error;
+
+static int fail(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return 1;
+}
+
+#define CUDA_TRY(expr)                                                                         \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess)                                                                     \
+      return fail("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__, cudaGetErrorString(_e)); \
+  } while (0)
+
+static inline int pad16(int v) { return (v + 15) & ~15; }
+
+// ------------------------------------------------------------------------------------- graph plan ----
+struct LayerDef {
+  std::string scope;  // TF variable scope, e.g. "CNN3", "Up-PS/Up-PS_CNN"
+  int k, cin, cout;
+  bool bias, prelu;
+};
+
+struct ParamDef {
+  std::string name;
+  std::vector<int64_t> shape;
+  std::vector<float> host;
+  int64_t numel() const {
+    int64_t n = 1;
+    for (auto d : shape) n *= d;
+    return n;
+  }
+};
+
+// device-side packed form of one tensor-core layer (possibly a fusion of several TF layers)
+struct TcLayer {
+  std::string name;
+  int ksz = 3;
+  int cin_pad = 0;              // channel extent of the source region
+  int n_tiles = 1, n_pad = 16;  // column tiling
+  int n_valid = 0;
+  std::vector<int> in_map;      // logical cin -> channel position in the source region
+  std::vector<float> w_host;    // fused HWIO fp32 [taps][cin][cout]
+  std::vector<float> bias_host, alpha_host;  // [n_tiles*n_pad]
+  int cin = 0, cout = 0;
+  float wscale = 1.f;
+  __half* d_wpack = nullptr;
+  float* d_bias = nullptr;
+  float* d_alpha = nullptr;
+  float* d_wref = nullptr;      // fp32 HWIO for the validation kernel
+  int* d_in_map = nullptr;
+  int packed_kc = 0, packed_planes = 0;
+};
+
+struct TcLaunch {
+  CUtensorMap tm_hi, tm_lo;
+  ConvTCParams p;
+  ConvRefParams ref;
+  int grid = 0;
+  int stages = 0;
+  size_t smem = 0;
+};
+
+struct Plan {
+  int n = 0, h = 0, w = 0;
+  ConvFirstParams first;
+  std::vector<TcLaunch> tc;      // in execution order
+  ConvLastParams last;
+};
+
+struct dcscn_handle {
+  dcscn_config cfg;
+  int sm_count = 148;
+  std::vector<int> filters;          // feature-extraction filter schedule
+  std::vector<LayerDef> layers;      // graph-construction order (self.Weights order)
+  std::vector<ParamDef> params;
+  std::map<std::string, int> param_index;
+  bool params_dirty = true;
+
+  // layout
+  std::vector<int> feat_off, feat_w;
+  int feat_pitch = 0;
+  int a1_w = 0, b1_w = 0, nin_pitch = 0;
+  int ps_out = 0;                    // channels after the last depth_to_space
+  int mid_pitch = 0;                 // x4: channels after the first depth_to_space (padded)
+
+  // packed layers
+  std::vector<TcLayer> tcl;          // CNN2..CNNL, A1+B1, B2, Up-PS [, Up-PS2]
+  float* d_first_w = nullptr;        // CNN1 [taps][n_pad]
+  float* d_first_bias = nullptr;
+  float* d_first_alpha = nullptr;
+  float* d_last_w = nullptr;         // R-CNN1 [taps][C]
+
+  // workspace (grow-only)
+  size_t cap_px = 0;                 // LR pixels the buffers can hold
+  __half *feat_hi = nullptr, *feat_lo = nullptr;
+  __half *b1_hi = nullptr, *b1_lo = nullptr;
+  __half *nin_hi = nullptr, *nin_lo = nullptr;
+  __half *mid_hi = nullptr, *mid_lo = nullptr;
+  float* hr = nullptr;
+  float *io_x = nullptr, *io_x2 = nullptr, *io_y = nullptr;  // staging for forward_host
+  size_t io_cap = 0;
+  int64_t device_bytes = 0;
+
+  std::vector<std::unique_ptr<Plan>> plans;
+  Plan* last_plan = nullptr;
+
+  int conv_impl = 0;
+  int kc = 64;
+  int64_t launches = 0;
+  PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+};
+
+static int planes(const dcscn_handle* h) { return h->cfg.precision == DCSCN_PRECISION_F16X1 ? 1 : 2; }
+
+// Filter-count schedule of the feature-extraction stack (DCSCN.py:240-244).
+static std::vector<int> feature_filters(const dcscn_config& c) {
+  std::vector<int> out;
+  const int minf = std::min(c.filters, c.min_filters);  // DCSCN.py:37
+  int n = c.filters;
+  for (int i = 0; i < c.layers; ++i) {
+    if (minf != 0 && i > 0) {
+      double x1 = (double)i / (double)(c.layers - 1);
+      double y1 = std::pow(x1, 1.0 / (double)c.filters_decay_gamma);
+      n = (int)((c.filters - minf) * (1 - y1) + minf);
+    }
+    out.push_back(n);
+  }
+  return out;
+}
+
+static void add_param(dcscn_handle* h, const std::string& name, std::vector<int64_t> shape, float fill) {
+  ParamDef p;
+  p.name = name;
+  p.shape = shape;
+  p.host.assign((size_t)p.numel(), fill);
+  h->param_index[name] = (int)h->params.size();
+  h->params.push_back(std::move(p));
+}
+
+static int build_graph(dcscn_handle* h) {
+  const dcscn_config& c = h->cfg;
+  if (!c.use_nin) return fail("use_nin=false is not supported (no shipped checkpoint uses it)");
+  if (c.depthwise_separable) return fail("depthwise_separable graphs are not built by this engine version");
+  if (c.channels != 1) return fail("channels must be 1 (helper/args.py: 'Now it should be 1')");
+  if (std::max(c.reconstruct_layers, 1) != 1) return fail("reconstruct_layers > 1 is not supported");
+  if (c.scale < 2 || c.scale > 4) return fail("scale must be 2, 3 or 4");
+  if (c.cnn_size != 3 && c.cnn_size != 1 && c.cnn_size != 5) return fail("cnn_size %d is not supported", c.cnn_size);
+  if (c.layers < 2) return fail("layers must be >= 2");
+
+  h->filters = feature_filters(c);
+  int cin = c.channels, total = 0;
+  for (int i = 0; i < c.layers; ++i) {
+    h->layers.push_back({"CNN" + std::to_string(i + 1), c.cnn_size, cin, h->filters[i], true, true});
+    cin = h->filters[i];
+    total += cin;
+  }
+  h->layers.push_back({"A1", 1, total, c.nin_filters, true, true});
+  h->layers.push_back({"B1", 1, total, c.nin_filters2, true, true});
+  h->layers.push_back({"B2", 3, c.nin_filters2, c.nin_filters2, true, true});
+  cin = c.nin_filters + c.nin_filters2;
+  h->ps_out = c.pixel_shuffler_filters != 0 ? c.pixel_shuffler_filters : cin;
+  if (c.scale == 4) {  // DCSCN.py:298-304
+    h->layers.push_back({"Up-PS/Up-PS_CNN", c.cnn_size, cin, 4 * cin, true, false});
+    h->layers.push_back({"Up-PS2/Up-PS2_CNN", c.cnn_size, cin, 4 * h->ps_out, true, false});
+  } else {
+    h->layers.push_back({"Up-PS/Up-PS_CNN", c.cnn_size, cin, c.scale * c.scale * h->ps_out, true, false});
+  }
+  h->layers.push_back({"R-CNN1", c.cnn_size, h->ps_out, 1, false, false});
+
+  for (const LayerDef& l : h->layers) {
+    std::string base = l.scope.substr(l.scope.find_last_of('/') == std::string::npos ? 0 : l.scope.find_last_of('/') + 1);
+    add_param(h, l.scope + "/conv_W", {l.k, l.k, l.cin, l.cout}, 0.f);
+    if (l.bias) add_param(h, l.scope + "/conv_B", {l.cout}, 0.f);                 // util.bias: zeros
+    if (l.prelu) add_param(h, l.scope + "/prelu/" + base + "_prelu", {l.cout}, 0.1f);  // tf_graph.py:91
+  }
+
+  // channel layout of the shared feature ("concat") buffer: 16-aligned slot per CNN layer
+  int off = 0;
+  for (int f : h->filters) {
+    h->feat_off.push_back(off);
+    h->feat_w.push_back(pad16(f));
+    off += pad16(f);
+  }
+  h->feat_pitch = off;
+  h->b1_w = pad16(c.nin_filters2);
+  h->a1_w = pad16(c.nin_filters);
+  h->nin_pitch = h->b1_w + h->a1_w;  // [B2 | A1]  (Concat2 order, DCSCN.py:281)
+  h->mid_pitch = pad16(cin);
+  return 0;
+}
+
+static const LayerDef* find_layer(const dcscn_handle* h, const std::string& scope) {
+  for (const LayerDef& l : h->layers)
+    if (l.scope == scope) return &l;
+  return nullptr;
+}
+static const std::vector<float>& P(const dcscn_handle* h, const std::string& name) {
+  return h->params[h->param_index.at(name)].host;
+}
+
+// ------------------------------------------------------------------------------ weight packing ----
+template <typename T>
+static int upload(T** dptr, const std::vector<T>& host, dcscn_handle* h) {
+  if (*dptr) {
+    cudaFree(*dptr);
+    *dptr = nullptr;
+  }
+  if (host.empty()) return 0;
+  CUDA_TRY(cudaMalloc((void**)dptr, host.size() * sizeof(T)));
+  CUDA_TRY(cudaMemcpy(*dptr, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// Appends the TF layer `scope` as columns [col0, col0+cout) of a fused tensor-core layer.
+static void fuse_columns(const dcscn_handle* h, TcLayer& t, const std::string& scope, int col0, int n_total_pad) {
+  const LayerDef* l = find_layer(h, scope);
+  const std::vector<float>& W = P(h, scope + "/conv_W");
+  const int taps = l->k * l->k;
+  for (int tp = 0; tp < taps; ++tp)
+    for (int ci = 0; ci < l->cin; ++ci)
+      for (int co = 0; co < l->cout; ++co)
+        t.w_host[((size_t)tp * t.cin + ci) * t.cout + col0 + co] = W[((size_t)tp * l->cin + ci) * l->cout + co];
+  std::string base = scope.substr(scope.find_last_of('/') == std::string::npos ? 0 : scope.find_last_of('/') + 1);
+  (void)n_total_pad;
+  if (l->bias) {
+    const std::vector<float>& B = P(h, scope + "/conv_B");
+    for (int co = 0; co < l->cout; ++co) t.bias_host[col0 + co] = B[co];
+  }
+  if (l->prelu) {
+    const std::vector<float>& A = P(h, scope + "/prelu/" + base + "_prelu");
+    for (int co = 0; co < l->cout; ++co) t.alpha_host[col0 + co] = A[co];
+  }
+}
+
+static void choose_tiling(int n_total_pad16, int* n_tiles, int* n_pad) {
+  int nt = (n_total_pad16 + 255) / 256;
+  int np = pad16((n_total_pad16 + nt - 1) / nt);
+  *n_tiles = nt;
+  *n_pad = np;
+}
+
+static int pack_tc_layer(dcscn_handle* h, TcLayer& t) {
+  const int KC = h->kc;
+  const int NPL = planes(h);
+  const int taps = t.ksz * t.ksz;
+  const int chunks = (t.cin_pad + KC - 1) / KC;
+  const int n_total = t.n_tiles * t.n_pad;
+
+  float maxw = 0.f;
+  for (float v : t.w_host) maxw = std::max(maxw, std::fabs(v));
+  t.wscale = 1.f;
+  if (maxw > 0.f) t.wscale = std::ldexp(1.0f, (int)std::floor(std::log2(16384.0 / (double)maxw)));
+
+  // dense, channel-position-indexed weights  Wq[tap][q][n]
+  std::vector<float> wq((size_t)taps * t.cin_pad * n_total, 0.f);
+  for (int tp = 0; tp < taps; ++tp)
+    for (int ci = 0; ci < t.cin; ++ci) {
+      const int q = t.in_map[ci];
+      for (int co = 0; co < t.cout; ++co)
+        wq[((size_t)tp * t.cin_pad + q) * n_total + co] = t.w_host[((size_t)tp * t.cin + ci) * t.cout + co] * t.wscale;
+    }
+
+  // tiles in the shared-memory image of a K-major swizzled UMMA operand: row = output channel, KC halves per row,
+  // 16-byte chunk j of row r lands at chunk j ^ f(r)  (SW128: f = r & 7, SW64: f = (r >> 1) & 3)
+  const int row_chunks = KC / 8;
+  const size_t tile_elems = (size_t)t.n_pad * KC;
+  std::vector<__half> pack((size_t)t.n_tiles * taps * chunks * NPL * tile_elems);
+  for (int nt = 0; nt < t.n_tiles; ++nt)
+    for (int tp = 0; tp < taps; ++tp)
+      for (int ch = 0; ch < chunks; ++ch) {
+        __half* base = pack.data() + (((size_t)nt * taps + tp) * chunks + ch) * NPL * tile_elems;
+        for (int r = 0; r < t.n_pad; ++r) {
+          const int n = nt * t.n_pad + r;
+          const int sw = (KC == 64) ? (r & 7) : ((r >> 1) & 3);
+          for (int kk = 0; kk < KC; ++kk) {
+            const int q = ch * KC + kk;
+            float v = (q < t.cin_pad) ? wq[((size_t)tp * t.cin_pad + q) * n_total + n] : 0.f;
+            __half hi = __float2half_rn(v);
+            __half lo = __float2half_rn(v - __half2float(hi));
+            const int j = kk / 8, e = kk % 8;
+            const size_t pos = (size_t)r * KC + (size_t)((j ^ sw) % row_chunks) * 8 + e;
+            base[pos] = hi;
+            if (NPL == 2) base[tile_elems + pos] = lo;
+          }
+        }
+      }
+  if (upload(&t.d_wpack, pack, h)) return 1;
+  if (upload(&t.d_bias, t.bias_host, h)) return 1;
+  if (upload(&t.d_alpha, t.alpha_host, h)) return 1;
+  if (upload(&t.d_wref, t.w_host, h)) return 1;
+  if (upload(&t.d_in_map, t.in_map, h)) return 1;
+  t.packed_kc = KC;
+  t.packed_planes = NPL;
+  return 0;
+}
+
+static TcLayer make_tc(const std::string& name, int ksz, int cin, int cout_cols, int cin_pad) {
+  TcLayer t;
+  t.name = name;
+  t.ksz = ksz;
+  t.cin = cin;
+  t.cout = cout_cols;
+  t.cin_pad = cin_pad;
+  choose_tiling(pad16(cout_cols), &t.n_tiles, &t.n_pad);
+  t.n_valid = cout_cols;
+  t.w_host.assign((size_t)ksz * ksz * cin * cout_cols, 0.f);
+  t.bias_host.assign((size_t)t.n_tiles * t.n_pad, 0.f);
+  t.alpha_host.assign((size_t)t.n_tiles * t.n_pad, 1.f);
+  return t;
+}
+
+static void free_tc(TcLayer& t) {
+  cudaFree(t.d_wpack);
+  cudaFree(t.d_bias);
+  cudaFree(t.d_alpha);
+  cudaFree(t.d_wref);
+  cudaFree(t.d_in_map);
+  t.d_wpack = nullptr;
+  t.d_bias = t.d_alpha = t.d_wref = nullptr;
+  t.d_in_map = nullptr;
+}
+
+// (Re)builds every device-side weight image from the host fp32 parameters.
+static int finalize_params(dcscn_handle* h) {
+  const dcscn_config& c = h->cfg;
+  for (TcLayer& t : h->tcl) free_tc(t);
+  h->tcl.clear();
+  h->plans.clear();
+  h->last_plan = nullptr;
+  const int L = c.layers;
+
+  // CNN1 (CUDA cores)
+  {
+    const LayerDef* l = find_layer(h, "CNN1");
+    const int taps = l->k * l->k, np = h->feat_w[0];
+    std::vector<float> w((size_t)taps * np, 0.f), b(np, 0.f), a(np, 1.f);
+    const auto& W = P(h, "CNN1/conv_W");
+    for (int tp = 0; tp < taps; ++tp)
+      for (int co = 0; co < l->cout; ++co) w[(size_t)tp * np + co] = W[(size_t)tp * l->cout + co];
+    const auto& B = P(h, "CNN1/conv_B");
+    const auto& A = P(h, "CNN1/prelu/CNN1_prelu");
+    for (int co = 0; co < l->cout; ++co) {
+      b[co] = B[co];
+      a[co] = A[co];
+    }
+    if (upload(&h->d_first_w, w, h) || upload(&h->d_first_bias, b, h) || upload(&h->d_first_alpha, a, h)) return 1;
+  }
+  // CNN2..CNNL
+  for (int i = 1; i < L; ++i) {
+    const std::string scope = "CNN" + std::to_string(i + 1);
+    const LayerDef* l = find_layer(h, scope);
+    TcLayer t = make_tc(scope, l->k, l->cin, l->cout, h->feat_w[i - 1]);
+    for (int ci = 0; ci < l->cin; ++ci) t.in_map.push_back(ci);
+    fuse_columns(h, t, scope, 0, 0);
+    h->tcl.push_back(std::move(t));
+  }
+  // A1 || B1 fused 1x1 over the whole concat buffer: columns [A1 (padded to 16) | B1]
+  {
+    const LayerDef* a1 = find_layer(h, "A1");
+    const LayerDef* b1 = find_layer(h, "B1");
+    TcLayer t = make_tc("A1+B1", 1, a1->cin, h->a1_w + b1->cout, h->feat_pitch);
+    for (int li = 0; li < L; ++li)
+      for (int ci = 0; ci < h->filters[li]; ++ci) t.in_map.push_back(h->feat_off[li] + ci);
+    fuse_columns(h, t, "A1", 0, 0);
+    fuse_columns(h, t, "B1", h->a1_w, 0);
+    h->tcl.push_back(std::move(t));
+  }
+  // B2
+  {
+    const LayerDef* l = find_layer(h, "B2");
+    TcLayer t = make_tc("B2", l->k, l->cin, l->cout, h->b1_w);
+    for (int ci = 0; ci < l->cin; ++ci) t.in_map.push_back(ci);
+    fuse_columns(h, t, "B2", 0, 0);
+    h->tcl.push_back(std::move(t));
+  }
+  // Up-PS (+ Up-PS2): input = Concat2 = [B2 | A1]
+  {
+    const LayerDef* l = find_layer(h, "Up-PS/Up-PS_CNN");
+    TcLayer t = make_tc("Up-PS", l->k, l->cin, l->cout, h->nin_pitch);
+    for (int ci = 0; ci < c.nin_filters2; ++ci) t.in_map.push_back(ci);
+    for (int ci = 0; ci < c.nin_filters; ++ci) t.in_map.push_back(h->b1_w + ci);
+    fuse_columns(h, t, "Up-PS/Up-PS_CNN", 0, 0);
+    h->tcl.push_back(std::move(t));
+    if (c.scale == 4) {
+      const LayerDef* l2 = find_layer(h, "Up-PS2/Up-PS2_CNN");
+      TcLayer t2 = make_tc("Up-PS2", l2->k, l2->cin, l2->cout, h->mid_pitch);
+      for (int ci = 0; ci < l2->cin; ++ci) t2.in_map.push_back(ci);
+      fuse_columns(h, t2, "Up-PS2/Up-PS2_CNN", 0, 0);
+      h->tcl.push_back(std::move(t2));
+    }
+  }
+  for (TcLayer& t : h->tcl)
+    if (pack_tc_layer(h, t)) return 1;
+  // R-CNN1 (CUDA cores): [taps][C]
+  {
+    const LayerDef* l = find_layer(h, "R-CNN1");
+    const auto& W = P(h, "R-CNN1/conv_W");  // [k,k,C,1]
+    std::vector<float> w(W.begin(), W.end());
+    (void)l;
+    if (upload(&h->d_last_w, w, h)) return 1;
+  }
+  h->params_dirty = false;
+  return 0;
+}
+
+// ----------------------------------------------------------------------------------- workspace ----
+template <typename T>
+static int dev_alloc(dcscn_handle* h, T** p, size_t count, bool zero) {
+  if (*p) {
+    cudaFree(*p);
+    *p = nullptr;
+  }
+  if (count == 0) return 0;
+  CUDA_TRY(cudaMalloc((void**)p, count * sizeof(T)));
+  if (zero) CUDA_TRY(cudaMemset(*p, 0, count * sizeof(T)));
+  h->device_bytes += (int64_t)(count * sizeof(T));
+  return 0;
+}
+
+static int ensure_workspace(dcscn_handle* h, size_t lr_px) {
+  if (lr_px <= h->cap_px) return 0;
+  const dcscn_config& c = h->cfg;
+  h->plans.clear();
+  h->last_plan = nullptr;
+  h->device_bytes = 0;
+  const bool two = planes(h) == 2;
+  const size_t s2 = (size_t)c.scale * c.scale;
+  if (dev_alloc(h, &h->feat_hi, lr_px * h->feat_pitch, true)) return 1;
+  if (dev_alloc(h, &h->feat_lo, two ? lr_px * h->feat_pitch : 0, true)) return 1;
+  if (dev_alloc(h, &h->b1_hi, lr_px * h->b1_w, true)) return 1;
+  if (dev_alloc(h, &h->b1_lo, two ? lr_px * h->b1_w : 0, true)) return 1;
+  if (dev_alloc(h, &h->nin_hi, lr_px * h->nin_pitch, true)) return 1;
+  if (dev_alloc(h, &h->nin_lo, two ? lr_px * h->nin_pitch : 0, true)) return 1;
+  if (c.scale == 4) {
+    if (dev_alloc(h, &h->mid_hi, lr_px * 4 * h->mid_pitch, true)) return 1;
+    if (dev_alloc(h, &h->mid_lo, two ? lr_px * 4 * h->mid_pitch : 0, true)) return 1;
+  }
+  if (dev_alloc(h, &h->hr, lr_px * s2 * h->ps_out, true)) return 1;
+  h->cap_px = lr_px;
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------- plans ----
+static void choose_patch(int H, int W, int* TH, int* TW) {
+  // 128-pixel rectangular patches; minimise padded area, prefer wide patches (contiguous TMA rows)
+  static const int cand[][2] = {{8, 16}, {4, 32}, {16, 8}, {2, 64}, {32, 4}, {1, 128}, {64, 2}, {128, 1}};
+  long long best = -1;
+  for (auto& c : cand) {
+    const int th = c[0], tw = c[1];
+    long long area = (long long)((H + th - 1) / th) * th * ((W + tw - 1) / tw) * tw;
+    if (best < 0 || area < best) {
+      best = area;
+      *TH = th;
+      *TW = tw;
+    }
+  }
+}
+
+static int encode_map(dcscn_handle* h, CUtensorMap* tm, const __half* base, int cin_pad, int pitch, int n, int H,
+                      int W, int TH, int TW) {
+  const int KC = h->kc;
+  cuuint64_t dims[4] = {(cuuint64_t)cin_pad, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)pitch * 2, (cuuint64_t)W * pitch * 2, (cuuint64_t)H * W * pitch * 2};
+  cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)TW, (cuuint32_t)TH, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = h->encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)base, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail("cuTensorMapEncodeTiled failed (%d) cin_pad=%d pitch=%d n=%d H=%d W=%d box=%dx%d", (int)r, cin_pad,
+                pitch, n, H, W, TH, TW);
+  return 0;
+}
+
+static int add_tc_launch(dcscn_handle* h, Plan* pl, const TcLayer& t, const __half* src_hi, const __half* src_lo,
+                         int src_pitch, int n, int H, int W, const EpiParams& epi) {
+  TcLaunch L;
+  memset(&L, 0, sizeof(L));
+  int TH, TW;
+  choose_patch(H, W, &TH, &TW);
+  ConvGeom g{n, H, W, (W + TW - 1) / TW, (H + TH - 1) / TH, TW, TH};
+  if (encode_map(h, &L.tm_hi, src_hi, t.cin_pad, src_pitch, n, H, W, TH, TW)) return 1;
+  if (planes(h) == 2) {
+    if (encode_map(h, &L.tm_lo, src_lo, t.cin_pad, src_pitch, n, H, W, TH, TW)) return 1;
+  } else {
+    L.tm_lo = L.tm_hi;
+  }
+  L.p.g = g;
+  L.p.ksz = t.ksz;
+  L.p.cin_pad = t.cin_pad;
+  L.p.chunks = (t.cin_pad + h->kc - 1) / h->kc;
+  L.p.n_tiles = t.n_tiles;
+  L.p.n_pad = t.n_pad;
+  L.p.wpack = t.d_wpack;
+  L.p.epi = epi;
+  L.p.epi.bias = t.d_bias;
+  L.p.epi.alpha = t.d_alpha;
+  L.p.epi.out_scale = 1.0f / t.wscale;
+  L.p.epi.n_valid = t.n_valid;
+
+  const size_t stage = tc_stage_bytes(h->kc, planes(h), t.n_pad);
+  const size_t budget = 227 * 1024 - 2048;
+  int stages = (int)std::min<size_t>(kMaxStages, budget / stage);
+  if (stages < 2) return fail("layer %s: pipeline stage of %zu bytes does not fit twice in shared memory", t.name.c_str(), stage);
+  L.stages = stages;
+  L.smem = stages * stage + 1024 + 256;
+  const long long work = (long long)n * g.tiles_x * g.tiles_y * t.n_tiles;
+  L.grid = (int)std::min<long long>(work, h->sm_count);
+
+  // validation twin
+  L.ref.g = g;
+  L.ref.ksz = t.ksz;
+  L.ref.cin = t.cin;
+  L.ref.cout = t.cout;
+  L.ref.src_hi = src_hi;
+  L.ref.src_lo = planes(h) == 2 ? src_lo : nullptr;
+  L.ref.src_pitch = src_pitch;
+  L.ref.in_map = t.d_in_map;
+  L.ref.w = t.d_wref;
+  L.ref.n_total_pad = t.n_tiles * t.n_pad;
+  L.ref.epi = L.p.epi;
+  L.ref.epi.out_scale = 1.0f;
+  pl->tc.push_back(L);
+  return 0;
+}
+
+static EpiParams epi_planes(__half* hi, __half* lo, int pitch, int col_begin, int col_end) {
+  EpiParams e;
+  memset(&e, 0, sizeof(e));
+  e.mode = EPI_PLANES;
+  e.num_seg = 1;
+  e.seg[0] = {col_begin, col_end, hi, lo, pitch};
+  e.keep_prob = 1.0f;
+  e.out_scale = 1.0f;
+  return e;
+}
+
+static Plan* get_plan(dcscn_handle* h, int n, int H, int W) {
+  for (auto& p : h->plans)
+    if (p->n == n && p->h == H && p->w == W) return p.get();
+  const dcscn_config& c = h->cfg;
+  std::unique_ptr<Plan> pl(new Plan());
+  pl->n = n;
+  pl->h = H;
+  pl->w = W;
+  const bool two = planes(h) == 2;
+  auto lo = [&](__half* p, size_t off) -> __half* { return two ? p + off : nullptr; };
+
+  // CNN1
+  memset(&pl->first, 0, sizeof(pl->first));
+  pl->first.g = ConvGeom{n, H, W, 1, 1, 1, 1};
+  pl->first.ksz = find_layer(h, "CNN1")->k;
+  pl->first.n_pad = h->feat_w[0];
+  pl->first.w = h->d_first_w;
+  pl->first.epi = epi_planes(h->feat_hi, lo(h->feat_lo, 0), h->feat_pitch, 0, h->feat_w[0]);
+  pl->first.epi.bias = h->d_first_bias;
+  pl->first.epi.alpha = h->d_first_alpha;
+  pl->first.epi.n_valid = h->filters[0];
+
+  size_t ti = 0;
+  for (int i = 1; i < c.layers; ++i, ++ti) {
+    EpiParams e = epi_planes(h->feat_hi + h->feat_off[i], lo(h->feat_lo, h->feat_off[i]), h->feat_pitch, 0, h->feat_w[i]);
+    if (add_tc_launch(h, pl.get(), h->tcl[ti], h->feat_hi + h->feat_off[i - 1], lo(h->feat_lo, h->feat_off[i - 1]),
+                      h->feat_pitch, n, H, W, e))
+      return nullptr;
+  }
+  {  // A1+B1: columns [0,a1_w) -> nin[:, b1_w:], columns [a1_w, a1_w+b1_w) -> b1
+    EpiParams e = epi_planes(h->nin_hi + h->b1_w, lo(h->nin_lo, h->b1_w), h->nin_pitch, 0, h->a1_w);
+    e.num_seg = 2;
+    e.seg[1] = {h->a1_w, h->a1_w + h->b1_w, h->b1_hi, two ? h->b1_lo : nullptr, h->b1_w};
+    if (add_tc_launch(h, pl.get(), h->tcl[ti++], h->feat_hi, lo(h->feat_lo, 0), h->feat_pitch, n, H, W, e)) return nullptr;
+  }
+  {  // B2 -> nin[:, 0:b1_w]
+    EpiParams e = epi_planes(h->nin_hi, lo(h->nin_lo, 0), h->nin_pitch, 0, h->b1_w);
+    if (add_tc_launch(h, pl.get(), h->tcl[ti++], h->b1_hi, two ? h->b1_lo : nullptr, h->b1_w, n, H, W, e)) return nullptr;
+  }
+  int HR_H = H, HR_W = W;
+  {  // Up-PS
+    EpiParams e;
+    memset(&e, 0, sizeof(e));
+    e.keep_prob = 1.0f;
+    if (c.scale == 4) {
+      e.mode = EPI_D2S_PLANES;
+      e.d2s_r = 2;
+      e.d2s_cout = c.nin_filters + c.nin_filters2;
+      e.num_seg = 1;
+      e.seg[0] = {0, 0, h->mid_hi, two ? h->mid_lo : nullptr, h->mid_pitch};
+    } else {
+      e.mode = EPI_D2S_F32;
+      e.d2s_r = c.scale;
+      e.d2s_cout = h->ps_out;
+      e.dst_f32 = h->hr;
+      e.d2s_pitch = h->ps_out;
+    }
+    if (add_tc_launch(h, pl.get(), h->tcl[ti++], h->nin_hi, two ? h->nin_lo : nullptr, h->nin_pitch, n, H, W, e)) return nullptr;
+    HR_H = H * (c.scale == 4 ? 2 : c.scale);
+    HR_W = W * (c.scale == 4 ? 2 : c.scale);
+  }
+  if (c.scale == 4) {  // Up-PS2 at 2x resolution
+    EpiParams e;
+    memset(&e, 0, sizeof(e));
+    e.keep_prob = 1.0f;
+    e.mode = EPI_D2S_F32;
+    e.d2s_r = 2;
+    e.d2s_cout = h->ps_out;
+    e.dst_f32 = h->hr;
+    e.d2s_pitch = h->ps_out;
+    if (add_tc_launch(h, pl.get(), h->tcl[ti++], h->mid_hi, two ? h->mid_lo : nullptr, h->mid_pitch, n, HR_H, HR_W, e))
+      return nullptr;
+    HR_H *= 2;
+    HR_W *= 2;
+  }
+  memset(&pl->last, 0, sizeof(pl->last));
+  pl->last.n_img = n;
+  pl->last.H = HR_H;
+  pl->last.W = HR_W;
+  pl->last.ksz = find_layer(h, "R-CNN1")->k;
+  pl->last.C = h->ps_out;
+  pl->last.pitch = h->ps_out;
+  pl->last.src = h->hr;
+  pl->last.w = h->d_last_w;
+  pl->last.bias = 0.f;
+  if (h->plans.size() >= 64) h->plans.erase(h->plans.begin());
+  h->plans.push_back(std::move(pl));
+  return h->plans.back().get();
+}
+
+// ------------------------------------------------------------------------------------- forward ----
+template <int KC, int NPL>
+static int launch_tc_inst(dcscn_handle* h, const TcLaunch& L, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<KC, NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  conv_tc_kernel<KC, NPL><<<L.grid, kTcThreads, L.smem, st>>>(L.tm_hi, L.tm_lo, L.p, L.stages);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+static int launch_tc(dcscn_handle* h, const TcLaunch& L, cudaStream_t st) {
+  h->launches++;
+  if (h->conv_impl == 1) {
+    const long long total = (long long)L.ref.g.n_img * L.ref.g.H * L.ref.g.W * (L.ref.n_total_pad >> 4);
+    const int grid = (int)std::min<long long>((total + 127) / 128, (long long)h->sm_count * 16);
+    conv_ref_kernel<<<grid, 128, 0, st>>>(L.ref);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+  }
+  const int npl = planes(h);
+  if (h->kc == 64) return npl == 2 ? launch_tc_inst<64, 2>(h, L, st) : launch_tc_inst<64, 1>(h, L, st);
+  return npl == 2 ? launch_tc_inst<32, 2>(h, L, st) : launch_tc_inst<32, 1>(h, L, st);
+}
+
+static int forward_impl(dcscn_handle* h, const float* x, const float* x2, float* y, int n, int H, int W,
+                        cudaStream_t st) {
+  if (n <= 0 || H <= 0 || W <= 0) return fail("forward: bad shape n=%d h=%d w=%d", n, H, W);
+  CUDA_TRY(cudaSetDevice(h->cfg.device_id));
+  if (h->params_dirty && finalize_params(h)) return 1;
+  if (ensure_workspace(h, (size_t)n * H * W)) return 1;
+  Plan* pl = get_plan(h, n, H, W);
+  if (!pl) return 1;
+  h->last_plan = pl;
+
+  {  // CNN1
+    ConvFirstParams p = pl->first;
+    p.x = x;
+    const long long total = (long long)n * H * W * (p.n_pad >> 4);
+    const int grid = (int)std::min<long long>((total + 255) / 256, (long long)h->sm_count * 8);
+    const size_t smem = (size_t)p.ksz * p.ksz * p.n_pad * sizeof(float);
+    conv_first_kernel<<<grid, 256, smem, st>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+  }
+  for (const TcLaunch& L : pl->tc)
+    if (launch_tc(h, L, st)) return 1;
+  {  // R-CNN1 + x2
+    ConvLastParams p = pl->last;
+    p.x2 = x2;
+    p.y = y;
+    const int half = p.ksz >> 1;
+    const int tiles = ((p.W + kLastTW - 1) / kLastTW) * ((p.H + kLastTH - 1) / kLastTH) * p.n_img;
+    const size_t smem = ((size_t)p.ksz * p.ksz * p.C + (size_t)(kLastTH + 2 * half) * (kLastTW + 2 * half) * kLastCC) * sizeof(float);
+    conv_last_kernel<<<tiles, 256, smem, st>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+  }
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------- C ABI ----
+extern "C" {
+
+const char* dcscn_last_error(void) { return g_last_error.c_str(); }
+
+int dcscn_create(const dcscn_config* cfg, dcscn_handle** out) {
+  if (!cfg || !out) return fail("dcscn_create: null argument");
+  if (cfg->struct_size != (int32_t)sizeof(dcscn_config))
+    return fail("dcscn_create: dcscn_config size mismatch (got %d, expected %d)", cfg->struct_size, (int)sizeof(dcscn_config));
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail("dcscn_create: no CUDA device available (%s); this library has no CPU path", cudaGetErrorString(e));
+  if (cfg->device_id < 0 || cfg->device_id >= ndev) return fail("dcscn_create: device %d out of range (%d devices)", cfg->device_id, ndev);
+  CUDA_TRY(cudaSetDevice(cfg->device_id));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device_id));
+  if (prop.major != 10) return fail("dcscn_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", cfg->device_id, prop.major, prop.minor);
+
+  std::unique_ptr<dcscn_handle> h(new dcscn_handle());
+  h->cfg = *cfg;
+  h->sm_count = prop.multiProcessorCount;
+  if (build_graph(h.get())) return 1;
+
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (qres != cudaDriverEntryPointSuccess || fn == nullptr) return fail("cuTensorMapEncodeTiled is not available in this driver");
+  h->encode = (PFN_cuTensorMapEncodeTiled_v12000)fn;
+  *out = h.release();
+  return 0;
+}
+
+int dcscn_destroy(dcscn_handle* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->cfg.device_id);
+  cudaDeviceSynchronize();
+  for (TcLayer& t : h->tcl) free_tc(t);
+  cudaFree(h->d_first_w);
+  cudaFree(h->d_first_bias);
+  cudaFree(h->d_first_alpha);
+  cudaFree(h->d_last_w);
+  cudaFree(h->feat_hi);
+  cudaFree(h->feat_lo);
+  cudaFree(h->b1_hi);
+  cudaFree(h->b1_lo);
+  cudaFree(h->nin_hi);
+  cudaFree(h->nin_lo);
+  cudaFree(h->mid_hi);
+  cudaFree(h->mid_lo);
+  cudaFree(h->hr);
+  cudaFree(h->io_x);
+  cudaFree(h->io_x2);
+  cudaFree(h->io_y);
+  delete h;
+  return 0;
+}
+
+int dcscn_num_params(dcscn_handle* h) { return h ? (int)h->params.size() : 0; }
+
+int dcscn_param_info(dcscn_handle* h, int index, char* name_buf, int name_buf_len, int64_t* dims4, int* ndim) {
+  if (!h || index < 0 || index >= (int)h->params.size()) return fail("dcscn_param_info: bad index %d", index);
+  const ParamDef& p = h->params[index];
+  if (name_buf && name_buf_len > 0) snprintf(name_buf, name_buf_len, "%s", p.name.c_str());
+  if (ndim) *ndim = (int)p.shape.size();
+  if (dims4)
+    for (size_t i = 0; i < p.shape.size() && i < 4; ++i) dims4[i] = p.shape[i];
+  return 0;
+}
+
+int dcscn_set_param(dcscn_handle* h, const char* name, const float* host_data, int64_t numel) {
+  if (!h || !name || !host_data) return fail("dcscn_set_param: null argument");
+  auto it = h->param_index.find(name);
+  if (it == h->param_index.end()) return fail("dcscn_set_param: unknown variable '%s'", name);
+  ParamDef& p = h->params[it->second];
+  if (numel != p.numel()) return fail("dcscn_set_param: '%s' has %lld elements, got %lld", name, (long long)p.numel(), (long long)numel);
+  memcpy(p.host.data(), host_data, (size_t)numel * sizeof(float));
+  h->params_dirty = true;
+  return 0;
+}
+
+int dcscn_get_param(dcscn_handle* h, const char* name, float* host_data, int64_t numel) {
+  if (!h || !name || !host_data) return fail("dcscn_get_param: null argument");
+  auto it = h->param_index.find(name);
+  if (it == h->param_index.end()) return fail("dcscn_get_param: unknown variable '%s'", name);
+  const ParamDef& p = h->params[it->second];
+  if (numel != p.numel()) return fail("dcscn_get_param: '%s' has %lld elements, got %lld", name, (long long)p.numel(), (long long)numel);
+  memcpy(host_data, p.host.data(), (size_t)numel * sizeof(float));
+  return 0;
+}
+
+int dcscn_forward(dcscn_handle* h, const float* x_dev, const float* x2_dev, float* y_dev, int n, int height, int width,
+                  void* stream) {
+  if (!h || !x_dev || !x2_dev || !y_dev) return fail("dcscn_forward: null argument");
+  return forward_impl(h, x_dev, x2_dev, y_dev, n, height, width, (cudaStream_t)stream);
+}
+
+int dcscn_forward_host(dcscn_handle* h, const float* x, const float* x2, float* y, int n, int height, int width) {
+  if (!h || !x || !x2 || !y) return fail("dcscn_forward_host: null argument");
+  CUDA_TRY(cudaSetDevice(h->cfg.device_id));
+  const size_t lr = (size_t)n * height * width;
+  const size_t hr = lr * h->cfg.scale * h->cfg.scale;
+  if (hr > h->io_cap) {
+    cudaFree(h->io_x);
+    cudaFree(h->io_x2);
+    cudaFree(h->io_y);
+    h->io_x = h->io_x2 = h->io_y = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&h->io_x, lr * sizeof(float)));
+    CUDA_TRY(cudaMalloc((void**)&h->io_x2, hr * sizeof(float)));
+    CUDA_TRY(cudaMalloc((void**)&h->io_y, hr * sizeof(float)));
+    h->io_cap = hr;
+  }
+  cudaStream_t st = 0;
+  CUDA_TRY(cudaMemcpyAsync(h->io_x, x, lr * sizeof(float), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(h->io_x2, x2, hr * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (forward_impl(h, h->io_x, h->io_x2, h->io_y, n, height, width, st)) return 1;
+  CUDA_TRY(cudaMemcpyAsync(y, h->io_y, hr * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int dcscn_get_activation(dcscn_handle* h, const char* tensor, float* host_data, int64_t numel) {
+  if (!h || !tensor || !host_data) return fail("dcscn_get_activation: null argument");
+  Plan* pl = h->last_plan;
+  if (!pl) return fail("dcscn_get_activation: no forward has run yet");
+  CUDA_TRY(cudaSetDevice(h->cfg.device_id));
+  CUDA_TRY(cudaDeviceSynchronize());
+  const dcscn_config& c = h->cfg;
+  const std::string t(tensor);
+  const __half *hi = nullptr, *lo = nullptr;
+  const float* f32 = nullptr;
+  int pitch = 0, off = 0, ch = 0;
+  size_t px = (size_t)pl->n * pl->h * pl->w;
+  if (t.rfind("CNN", 0) == 0) {
+    int i = atoi(t.c_str() + 3) - 1;
+    if (i < 0 || i >= c.layers) return fail("dcscn_get_activation: no tensor '%s'", tensor);
+    hi = h->feat_hi; lo = h->feat_lo; pitch = h->feat_pitch; off = h->feat_off[i]; ch = h->filters[i];
+  } else if (t == "A1") {
+    hi = h->nin_hi; lo = h->nin_lo; pitch = h->nin_pitch; off = h->b1_w; ch = c.nin_filters;
+  } else if (t == "B2") {
+    hi = h->nin_hi; lo = h->nin_lo; pitch = h->nin_pitch; off = 0; ch = c.nin_filters2;
+  } else if (t == "B1") {
+    hi = h->b1_hi; lo = h->b1_lo; pitch = h->b1_w; off = 0; ch = c.nin_filters2;
+  } else if (t == "Up-PS" && c.scale == 4) {
+    hi = h->mid_hi; lo = h->mid_lo; pitch = h->mid_pitch; off = 0; ch = c.nin_filters + c.nin_filters2; px *= 4;
+  } else if ((t == "Up-PS" && c.scale != 4) || (t == "Up-PS2" && c.scale == 4)) {
+    f32 = h->hr; pitch = h->ps_out; ch = h->ps_out; px *= (size_t)c.scale * c.scale;
+  } else {
+    return fail("dcscn_get_activation: no tensor '%s'", tensor);
+  }
+  if (numel != (int64_t)(px * ch)) return fail("dcscn_get_activation: '%s' has %lld elements, got %lld", tensor, (long long)(px * ch), (long long)numel);
+  std::vector<float> full(px * pitch);
+  if (f32) {
+    CUDA_TRY(cudaMemcpy(full.data(), f32, full.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  } else {
+    float* tmp = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&tmp, full.size() * sizeof(float)));
+    planes_to_f32_kernel<<<1024, 256>>>(hi, planes(h) == 2 ? lo : nullptr, tmp, full.size());
+    cudaError_t e = cudaMemcpy(full.data(), tmp, full.size() * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(tmp);
+    if (e != cudaSuccess) return fail("dcscn_get_activation: copy failed: %s", cudaGetErrorString(e));
+  }
+  for (size_t p = 0; p < px; ++p)
+    for (int k = 0; k < ch; ++k) host_data[p * ch + k] = full[p * pitch + off + k];
+  return 0;
+}
+
+int dcscn_set_option(dcscn_handle* h, const char* key, int64_t value) {
+  if (!h || !key) return fail("dcscn_set_option: null argument");
+  const std::string k(key);
+  if (k == "conv_impl") {
+    if (value != 0 && value != 1) return fail("conv_impl must be 0 (tcgen05) or 1 (CUDA-core validation)");
+    h->conv_impl = (int)value;
+  } else if (k == "kc") {
+    if (value != 64 && value != 32) return fail("kc must be 64 or 32");
+    if (h->kc != (int)value) {
+      h->kc = (int)value;
+      h->params_dirty = true;  // weight tiles depend on KC
+      h->plans.clear();
+      h->last_plan = nullptr;
+    }
+  } else {
+    return fail("dcscn_set_option: unknown option '%s'", key);
+  }
+  return 0;
+}
+
+int64_t dcscn_launch_count(dcscn_handle* h) { return h ? h->launches : 0; }
+int64_t dcscn_device_bytes(dcscn_handle* h) { return h ? h->device_bytes : 0; }
+
+}  // extern "C"

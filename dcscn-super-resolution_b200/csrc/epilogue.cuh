@@ -1,0 +1,120 @@
+// Fused convolution epilogue shared by the tcgen05 kernel and the CUDA-core validation kernel:
+//   acc * out_scale + bias  -> PReLU -> [inverted dropout] -> store
+// replacing the reference's un-fused  tf.add(bias) / PReLU / tf.nn.dropout / tf.concat /
+// tf.depth_to_space  ops (helper/tf_graph.py:109, :89-94, :130, :248; DCSCN.py:259,281).
+#pragma once
+#include "common.h"
+
+namespace dcscn {
+
+__device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
+  // fp16 saturates at 65504; DCSCN activations live in 0..~1e3 (inputs are 0..255 luma).
+  v = fminf(fmaxf(v, -65504.f), 65504.f);
+  hi = __float2half_rn(v);
+  lo = __float2half_rn(v - __half2float(hi));
+}
+
+// Counter-based keep mask for inverted dropout (tf.nn.dropout, tf_graph.py:130).
+__host__ __device__ __forceinline__ uint32_t dropout_hash(uint32_t seed, uint32_t layer, uint64_t idx) {
+  uint64_t z = idx + 0x9E3779B97F4A7C15ull * (uint64_t)(seed + 1) + ((uint64_t)layer << 40);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return (uint32_t)(z >> 32);
+}
+__host__ __device__ __forceinline__ bool dropout_keep(uint32_t seed, uint32_t layer, uint64_t idx, float keep_prob) {
+  // 24-bit uniform in [0,1)
+  return (float)(dropout_hash(seed, layer, idx) >> 8) * (1.0f / 16777216.0f) < keep_prob;
+}
+
+__device__ __forceinline__ void store_planes16(__half* dst_hi, __half* dst_lo, size_t off, const float (&v)[16]) {
+  __align__(16) __half hi[16];
+  __align__(16) __half lo[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) split_f16(v[i], hi[i], lo[i]);
+  uint4* ph = reinterpret_cast<uint4*>(dst_hi + off);
+  ph[0] = reinterpret_cast<const uint4*>(hi)[0];
+  ph[1] = reinterpret_cast<const uint4*>(hi)[1];
+  if (dst_lo != nullptr) {
+    uint4* pl = reinterpret_cast<uint4*>(dst_lo + off);
+    pl[0] = reinterpret_cast<const uint4*>(lo)[0];
+    pl[1] = reinterpret_cast<const uint4*>(lo)[1];
+  }
+}
+
+// One output pixel (img, y, x) of the LR grid, 16 consecutive GEMM columns starting at `cg`.
+__device__ __forceinline__ void epilogue_store16(const EpiParams& e, const ConvGeom& g, int n_total, int img, int y,
+                                                 int x, int cg, const float (&acc)[16]) {
+  float v[16];
+  const float4* b4 = reinterpret_cast<const float4*>(e.bias + cg);
+  const float4* a4 = reinterpret_cast<const float4*>(e.alpha + cg);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float4 b = __ldg(b4 + q);
+    float4 a = __ldg(a4 + q);
+    float t0 = fmaf(acc[4 * q + 0], e.out_scale, b.x);
+    float t1 = fmaf(acc[4 * q + 1], e.out_scale, b.y);
+    float t2 = fmaf(acc[4 * q + 2], e.out_scale, b.z);
+    float t3 = fmaf(acc[4 * q + 3], e.out_scale, b.w);
+    v[4 * q + 0] = t0 > 0.f ? t0 : a.x * t0;
+    v[4 * q + 1] = t1 > 0.f ? t1 : a.y * t1;
+    v[4 * q + 2] = t2 > 0.f ? t2 : a.z * t2;
+    v[4 * q + 3] = t3 > 0.f ? t3 : a.w * t3;
+  }
+  if (e.keep_prob < 1.0f) {
+    const float inv_keep = 1.0f / e.keep_prob;
+    const uint64_t base = ((uint64_t)((size_t)img * g.H + y) * g.W + x) * (uint64_t)n_total + cg;
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      v[i] = dropout_keep(e.drop_seed, e.drop_layer, base + i, e.keep_prob) ? v[i] * inv_keep : 0.f;
+  }
+
+  if (e.mode == EPI_PLANES) {
+#pragma unroll
+    for (int s = 0; s < kMaxSegments; ++s) {
+      if (s < e.num_seg && cg >= e.seg[s].col_begin && cg < e.seg[s].col_end) {
+        size_t off = ((size_t)((size_t)img * g.H + y) * g.W + x) * e.seg[s].pitch + (cg - e.seg[s].col_begin);
+        store_planes16(e.seg[s].dst_hi, e.seg[s].dst_lo, off, v);
+      }
+    }
+    return;
+  }
+
+  // depth_to_space, DCR order: column = (i*r + j)*cout + c  ->  (y*r + i, x*r + j, c)   (tf_graph.py:248)
+  const int r = e.d2s_r;
+  const int co = e.d2s_cout;
+  const int HR_H = g.H * r, HR_W = g.W * r;
+  if ((co & 15) == 0) {
+    if (cg >= e.n_valid) return;
+    const int ij = cg / co, c = cg - ij * co;
+    const int i = ij / r, j = ij - i * r;
+    const size_t pix = (size_t)((size_t)img * HR_H + (y * r + i)) * HR_W + (x * r + j);
+    if (e.mode == EPI_D2S_F32) {
+      float4* d = reinterpret_cast<float4*>(e.dst_f32 + pix * e.d2s_pitch + c);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) d[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    } else {
+      store_planes16(e.seg[0].dst_hi, e.seg[0].dst_lo, pix * e.seg[0].pitch + c, v);
+    }
+  } else {
+    // narrow pixel-shuffler outputs (c-DCSCN: pixel_shuffler_filters = 1): element-wise scatter
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+      const int col = cg + t;
+      if (col >= e.n_valid) break;
+      const int ij = col / co, c = col - ij * co;
+      const int i = ij / r, j = ij - i * r;
+      const size_t pix = (size_t)((size_t)img * HR_H + (y * r + i)) * HR_W + (x * r + j);
+      if (e.mode == EPI_D2S_F32) {
+        e.dst_f32[pix * e.d2s_pitch + c] = v[t];
+      } else {
+        __half hi, lo;
+        split_f16(v[t], hi, lo);
+        e.seg[0].dst_hi[pix * e.seg[0].pitch + c] = hi;
+        if (e.seg[0].dst_lo != nullptr) e.seg[0].dst_lo[pix * e.seg[0].pitch + c] = lo;
+      }
+    }
+  }
+}
+
+}  // namespace dcscn

@@ -1,0 +1,221 @@
+"""
+ctypes binding of the C-ABI in include/dcscn_b200.h (libdcscn_b200.so, built from csrc/).
+
+This is what stands where `self.sess.run(...)` stood in the reference
+(DCSCN.py:420, :565, :575): PyTorch tensors are only the device containers whose
+raw pointers are handed to the library.  There is NO CPU fallback: if the shared
+library is missing or no B200 is present, construction raises.
+"""
+
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "csrc", "libdcscn_b200.so")
+
+PRECISION_F16X3 = 0
+PRECISION_F16X1 = 1
+
+
+class DcscnConfig(ctypes.Structure):
+    """Mirror of `struct dcscn_config` (include/dcscn_b200.h)."""
+    _fields_ = [
+        ("struct_size", ctypes.c_int32),
+        ("scale", ctypes.c_int32),
+        ("layers", ctypes.c_int32),
+        ("filters", ctypes.c_int32),
+        ("min_filters", ctypes.c_int32),
+        ("filters_decay_gamma", ctypes.c_float),
+        ("use_nin", ctypes.c_int32),
+        ("nin_filters", ctypes.c_int32),
+        ("nin_filters2", ctypes.c_int32),
+        ("cnn_size", ctypes.c_int32),
+        ("reconstruct_layers", ctypes.c_int32),
+        ("reconstruct_filters", ctypes.c_int32),
+        ("pixel_shuffler_filters", ctypes.c_int32),
+        ("depthwise_separable", ctypes.c_int32),
+        ("channels", ctypes.c_int32),
+        ("dropout_keep", ctypes.c_float),
+        ("l2_decay", ctypes.c_float),
+        ("clipping_norm", ctypes.c_float),
+        ("beta1", ctypes.c_float),
+        ("beta2", ctypes.c_float),
+        ("epsilon", ctypes.c_float),
+        ("device_id", ctypes.c_int32),
+        ("precision", ctypes.c_int32),
+    ]
+
+
+EXPORTED_SYMBOLS = [
+    "dcscn_create", "dcscn_destroy", "dcscn_last_error", "dcscn_num_params", "dcscn_param_info",
+    "dcscn_set_param", "dcscn_get_param", "dcscn_forward", "dcscn_forward_host", "dcscn_get_activation",
+    "dcscn_set_option", "dcscn_launch_count", "dcscn_device_bytes",
+]
+
+_lib = None
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def load_library(path=None):
+    """dlopen the C-ABI library; raises EngineError (never falls back) when it is missing."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.isfile(path):
+        raise EngineError("CUDA extension %s not found - build it with `python __graft_entry__.py` "
+                          "(or `make -C dcscn-super-resolution_b200/csrc`); there is no CPU fallback" % path)
+    lib = ctypes.CDLL(path)
+    vp, ci, c64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
+    fp = ctypes.POINTER(ctypes.c_float)
+    lib.dcscn_last_error.restype = ctypes.c_char_p
+    lib.dcscn_create.argtypes = [ctypes.POINTER(DcscnConfig), ctypes.POINTER(vp)]
+    lib.dcscn_destroy.argtypes = [vp]
+    lib.dcscn_num_params.argtypes = [vp]
+    lib.dcscn_param_info.argtypes = [vp, ci, ctypes.c_char_p, ci, ctypes.POINTER(c64), ctypes.POINTER(ci)]
+    lib.dcscn_set_param.argtypes = [vp, ctypes.c_char_p, fp, c64]
+    lib.dcscn_get_param.argtypes = [vp, ctypes.c_char_p, fp, c64]
+    lib.dcscn_forward.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp]
+    lib.dcscn_forward_host.argtypes = [vp, vp, vp, vp, ci, ci, ci]
+    lib.dcscn_get_activation.argtypes = [vp, ctypes.c_char_p, fp, c64]
+    lib.dcscn_set_option.argtypes = [vp, ctypes.c_char_p, c64]
+    lib.dcscn_launch_count.argtypes = [vp]
+    lib.dcscn_launch_count.restype = c64
+    lib.dcscn_device_bytes.argtypes = [vp]
+    lib.dcscn_device_bytes.restype = c64
+    _lib = lib
+    return lib
+
+
+def make_config(scale=2, layers=12, filters=196, min_filters=48, filters_decay_gamma=1.5, use_nin=True,
+                nin_filters=64, nin_filters2=32, cnn_size=3, reconstruct_layers=1, reconstruct_filters=32,
+                pixel_shuffler_filters=0, depthwise_separable=False, channels=1, dropout_keep=0.8,
+                l2_decay=0.0001, clipping_norm=5.0, beta1=0.9, beta2=0.999, epsilon=1e-8, device_id=0,
+                precision=PRECISION_F16X3):
+    c = DcscnConfig()
+    c.struct_size = ctypes.sizeof(DcscnConfig)
+    c.scale, c.layers, c.filters, c.min_filters = scale, layers, filters, min_filters
+    c.filters_decay_gamma = filters_decay_gamma
+    c.use_nin, c.nin_filters, c.nin_filters2, c.cnn_size = int(use_nin), nin_filters, nin_filters2, cnn_size
+    c.reconstruct_layers, c.reconstruct_filters = reconstruct_layers, reconstruct_filters
+    c.pixel_shuffler_filters, c.depthwise_separable, c.channels = pixel_shuffler_filters, int(depthwise_separable), channels
+    c.dropout_keep, c.l2_decay, c.clipping_norm = dropout_keep, l2_decay, clipping_norm
+    c.beta1, c.beta2, c.epsilon = beta1, beta2, epsilon
+    c.device_id, c.precision = device_id, precision
+    return c
+
+
+class Engine:
+    """One DCSCN graph instance on one GPU."""
+
+    def __init__(self, config):
+        self.lib = load_library()
+        self.config = config
+        self.handle = ctypes.c_void_p()
+        self._check(self.lib.dcscn_create(ctypes.byref(config), ctypes.byref(self.handle)))
+
+    def _check(self, rc):
+        if rc != 0:
+            raise EngineError(self.lib.dcscn_last_error().decode("utf-8", "replace"))
+
+    def close(self):
+        if self.handle:
+            self.lib.dcscn_destroy(self.handle)
+            self.handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- variables ----
+    def param_shapes(self):
+        out = {}
+        buf = ctypes.create_string_buffer(256)
+        dims = (ctypes.c_int64 * 4)()
+        nd = ctypes.c_int()
+        for i in range(self.lib.dcscn_num_params(self.handle)):
+            self._check(self.lib.dcscn_param_info(self.handle, i, buf, 256, dims, ctypes.byref(nd)))
+            out[buf.value.decode()] = tuple(int(dims[k]) for k in range(nd.value))
+        return out
+
+    def set_param(self, name, array):
+        a = np.ascontiguousarray(array, dtype=np.float32)
+        self._check(self.lib.dcscn_set_param(self.handle, name.encode(), a.ctypes.data_as(ctypes.POINTER(ctypes.c_float)),
+                                             a.size))
+
+    def get_param(self, name):
+        shape = self.param_shapes()[name]
+        a = np.empty(shape, dtype=np.float32)
+        self._check(self.lib.dcscn_get_param(self.handle, name.encode(), a.ctypes.data_as(ctypes.POINTER(ctypes.c_float)),
+                                             a.size))
+        return a
+
+    def set_params(self, weights):
+        shapes = self.param_shapes()
+        for name, shape in shapes.items():
+            if name not in weights:
+                raise EngineError("checkpoint has no variable '%s'" % name)
+            w = np.asarray(weights[name])
+            if tuple(w.shape) != tuple(shape):
+                raise EngineError("variable '%s': checkpoint shape %s != graph shape %s" % (name, w.shape, shape))
+            self.set_param(name, w)
+
+    # ---- compute ----
+    def forward(self, x, x2, y=None, stream=None):
+        """x [n,h,w,1], x2 [n,s*h,s*w,1]: contiguous fp32 CUDA torch tensors.  Asynchronous."""
+        import torch
+        n, h, w = int(x.shape[0]), int(x.shape[1]), int(x.shape[2])
+        s = self.config.scale
+        assert x.is_cuda and x2.is_cuda and x.dtype == torch.float32 and x2.dtype == torch.float32
+        assert x.is_contiguous() and x2.is_contiguous()
+        assert tuple(x2.shape[:3]) == (n, s * h, s * w), "x2 must be [n, scale*h, scale*w, 1]"
+        if y is None:
+            y = torch.empty((n, s * h, s * w, 1), dtype=torch.float32, device=x.device)
+        st = stream if stream is not None else torch.cuda.current_stream(x.device).cuda_stream
+        self._check(self.lib.dcscn_forward(self.handle, x.data_ptr(), x2.data_ptr(), y.data_ptr(), n, h, w,
+                                           ctypes.c_void_p(st)))
+        return y
+
+    def forward_host(self, x, x2, y=None):
+        """numpy (or pinned torch CPU) fp32 arrays in, numpy out; H2D + forward + D2H, synchronous."""
+        xa, x2a = _host_array(x), _host_array(x2)
+        n, h, w = xa.shape[0], xa.shape[1], xa.shape[2]
+        s = self.config.scale
+        assert tuple(x2a.shape[:3]) == (n, s * h, s * w)
+        if y is None:
+            y = np.empty((n, s * h, s * w, 1), dtype=np.float32)
+        ya = _host_array(y)
+        self._check(self.lib.dcscn_forward_host(self.handle, xa.ctypes.data, x2a.ctypes.data, ya.ctypes.data, n, h, w))
+        return y
+
+    def get_activation(self, tensor, shape):
+        a = np.empty(shape, dtype=np.float32)
+        self._check(self.lib.dcscn_get_activation(self.handle, tensor.encode(),
+                                                  a.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), a.size))
+        return a
+
+    def set_option(self, key, value):
+        self._check(self.lib.dcscn_set_option(self.handle, key.encode(), int(value)))
+
+    @property
+    def launch_count(self):
+        return int(self.lib.dcscn_launch_count(self.handle))
+
+    @property
+    def device_bytes(self):
+        return int(self.lib.dcscn_device_bytes(self.handle))
+
+
+def _host_array(a):
+    if isinstance(a, np.ndarray):
+        assert a.dtype == np.float32 and a.flags["C_CONTIGUOUS"]
+        return a
+    # torch CPU tensor (possibly pinned): share memory
+    return a.numpy()

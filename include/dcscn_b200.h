@@ -1,0 +1,102 @@
+/*
+ * dcscn_b200.h - C-ABI of the B200-native DCSCN forward / backward hot path.
+ *
+ * The reference (jiny2001/dcscn-super-resolution) has no FFI: its seam is the Python class
+ * DCSCN.SuperResolution and the four `sess.run` call sites.  Each entry point below names the
+ * reference interface it stands in for (paths relative to the reference checkout).
+ *
+ * All tensors are contiguous fp32 NHWC with C == 1 at the boundary (TF placeholders
+ * x / x2 / y, DCSCN.py:224-226).  Functions return 0 on success, non-zero on error;
+ * dcscn_last_error() returns the message of the last failure on the calling thread.
+ * A handle is not re-entrant; use one handle per GPU / host thread.
+ */
+#ifndef DCSCN_B200_H_
+#define DCSCN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dcscn_handle dcscn_handle;
+
+/* Arithmetic of the tensor-core layers. */
+enum {
+  DCSCN_PRECISION_F16X3 = 0, /* fp32-equivalent: fp16 hi/lo split operands, 3 UMMA passes, fp32 accumulate */
+  DCSCN_PRECISION_F16X1 = 1  /* single-pass fp16 operands (PSNR-neutral, not 1e-3-pixel exact) */
+};
+
+/*
+ * Graph hyper-parameters: the subset of helper/args.py:16-98 flags that shape the graph built by
+ * DCSCN.SuperResolution.__init__ (DCSCN.py:29-106) and build_graph (DCSCN.py:222-332).
+ */
+typedef struct dcscn_config {
+  int32_t struct_size;            /* sizeof(dcscn_config), for ABI checking */
+  int32_t scale;                  /* --scale (2, 3 or 4) */
+  int32_t layers;                 /* --layers */
+  int32_t filters;                /* --filters */
+  int32_t min_filters;            /* --min_filters */
+  float filters_decay_gamma;      /* --filters_decay_gamma */
+  int32_t use_nin;                /* --use_nin (only 1 is supported) */
+  int32_t nin_filters;            /* --nin_filters  (A1) */
+  int32_t nin_filters2;           /* --nin_filters2 (B1, B2) */
+  int32_t cnn_size;               /* --cnn_size (3) */
+  int32_t reconstruct_layers;     /* --reconstruct_layers (max(flag,1) == 1 supported) */
+  int32_t reconstruct_filters;    /* --reconstruct_filters */
+  int32_t pixel_shuffler_filters; /* --pixel_shuffler_filters (0 = same as input) */
+  int32_t depthwise_separable;    /* --depthwise_separable */
+  int32_t channels;               /* --channels (1) */
+  float dropout_keep;             /* --dropout_rate (keep probability, training only) */
+  float l2_decay;                 /* --l2_decay */
+  float clipping_norm;            /* --clipping_norm */
+  float beta1, beta2, epsilon;    /* --beta1 --beta2 --epsilon (Adam) */
+  int32_t device_id;              /* --gpu_device_id */
+  int32_t precision;              /* DCSCN_PRECISION_* */
+} dcscn_config;
+
+/* SuperResolution(flags) + build_graph() + init_session (DCSCN.py:29, :222; tf_graph.py:65). */
+int dcscn_create(const dcscn_config* cfg, dcscn_handle** out);
+/* sess.close() */
+int dcscn_destroy(dcscn_handle* h);
+const char* dcscn_last_error(void);
+
+/*
+ * Variables of the graph, named exactly like the TF variables in the reference's checkpoints
+ * (tf.train.Saver, tf_graph.py:263-296): "CNN1/conv_W" [k,k,cin,cout] HWIO, "CNN1/conv_B",
+ * "CNN1/prelu/CNN1_prelu", "A1/...", "B1/...", "B2/...", "Up-PS/Up-PS_CNN/conv_W", "R-CNN1/conv_W" ...
+ */
+int dcscn_num_params(dcscn_handle* h);
+int dcscn_param_info(dcscn_handle* h, int index, char* name_buf, int name_buf_len, int64_t* dims4, int* ndim);
+/* saver.restore (tf_graph.py:276): host fp32 -> engine.  numel must match the variable. */
+int dcscn_set_param(dcscn_handle* h, const char* name, const float* host_data, int64_t numel);
+/* saver.save (tf_graph.py:291): engine -> host fp32. */
+int dcscn_get_param(dcscn_handle* h, const char* name, float* host_data, int64_t numel);
+
+/*
+ * sess.run(self.y_, {x, x2, dropout: 1.0, is_training: 0})  (DCSCN.py:565, :575).
+ * x [n,h,w,1], x2 and y [n,scale*h,scale*w,1]: DEVICE pointers; asynchronous on `stream` (cudaStream_t).
+ */
+int dcscn_forward(dcscn_handle* h, const float* x_dev, const float* x2_dev, float* y_dev, int n, int height,
+                  int width, void* stream);
+/* Same call with HOST buffers (pinned or pageable): H2D, forward, D2H, synchronises before returning. */
+int dcscn_forward_host(dcscn_handle* h, const float* x, const float* x2, float* y, int n, int height, int width);
+
+/*
+ * Parity / debug: output of one layer of the LAST forward as fp32 NHWC [n, H_l, W_l, cout_l]
+ * (`tensor` is the reference's self.H entry: "CNN1".."CNNL", "A1", "B1", "B2", "Up-PS", "Up-PS2").
+ */
+int dcscn_get_activation(dcscn_handle* h, const char* tensor, float* host_data, int64_t numel);
+
+/* Options: "conv_impl" 0 = tcgen05 (default), 1 = CUDA-core fp32 validation kernels;
+ *          "kc" 64 | 32 = K-chunk (channels per pipeline stage) of the tensor-core kernel. */
+int dcscn_set_option(dcscn_handle* h, const char* key, int64_t value);
+/* Number of kernels this handle has launched so far (bench.py "gpu_launches"). */
+int64_t dcscn_launch_count(dcscn_handle* h);
+/* Bytes of device memory currently held by the handle. */
+int64_t dcscn_device_bytes(dcscn_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCSCN_B200_H_ */

@@ -62,6 +62,7 @@ struct ConvTCParams {
   int chunks;            // ceil(cin_pad / KC)
   int n_tiles;           // column tiles (N > 256 is split)
   int n_pad;             // columns per tile, multiple of 16, <= 256
+  int seg_chunks;        // pipeline stages per accumulation segment (fp32 promotion period)
   const __half* wpack;   // packed weights [n_tile][tap][chunk][plane][n_pad x KC] (pre-swizzled)
   EpiParams epi;
 };

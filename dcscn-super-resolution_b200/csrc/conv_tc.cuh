@@ -11,9 +11,14 @@
 //   * fp32-equivalent precision from fp16 tensor cores:  a = a_hi + a_lo,  w*2^s = w_hi + w_lo
 //     (each 11-bit significands), D += a_hi*w_hi + a_lo*w_hi + a_hi*w_lo   (3 x kind::f16 UMMA,
 //     fp32 accumulation in TMEM).  NPLANES == 1 is the single-pass fp16 "fast" mode.
-//   * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..5 = epilogue
-//     (TMEM -> registers -> bias/PReLU/split -> global), double-buffered TMEM accumulators, persistent
-//     CTAs striding over (pixel-tile, column-tile) work items.
+//   * The tensor core's fp32 accumulator update truncates (round-toward-zero) on every UMMA, a bias that grows
+//     linearly with the number of accumulation steps (measured: ~0.5 ulp per UMMA, 3e-3 absolute after the
+//     333 UMMAs of CNN2).  K is therefore cut into short segments (`seg_chunks` pipeline stages): each segment
+//     accumulates in TMEM from zero, and the epilogue warps add the segment sums into fp32 registers with
+//     round-to-nearest ("promotion"), double-buffered against the next segment's UMMAs.
+//   * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 4..11 = epilogue (registers re-balanced with setmaxnreg)
+//     (TMEM -> registers, running fp32 sums, then bias/PReLU/split -> global), persistent CTAs striding
+//     over (pixel-tile, column-tile) work items.
 #pragma once
 #include "common.h"
 #include "epilogue.cuh"
@@ -21,10 +26,15 @@
 
 namespace dcscn {
 
-constexpr int kTcThreads = 192;
+constexpr int kEpiWarps = 8;                       // two warps per TMEM lane quadrant, each owning half of the columns
+constexpr int kEpiWarp0 = 4;                       // warpgroup 0 = {TMA, MMA, 2 idle}; warpgroups 1.. = epilogue
+constexpr int kTcThreads = (kEpiWarp0 + kEpiWarps) * 32;
+constexpr int kRegsIssue = 40, kRegsEpilogue = 232;  // setmaxnreg budgets (128*56 + 256*224 <= 64K)
 constexpr int kMaxStages = 8;
 constexpr int kAccStages = 2;
 constexpr int kAccStride = 256;  // TMEM columns per accumulator stage
+constexpr int kColSplit = kEpiWarps / 4;           // column groups
+constexpr int kMaxColChunks = 16 / kColSplit;      // 16-column chunks one epilogue thread accumulates (256 columns total)
 
 template <int KC>
 struct TcSmem {
@@ -81,7 +91,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     }
     for (int s = 0; s < kAccStages; ++s) {
       ptx::mbar_init(&acc_full[s], 1);
-      ptx::mbar_init(&acc_empty[s], 4);  // one arrive per epilogue warp
+      ptx::mbar_init(&acc_empty[s], kEpiWarps);  // one arrive per epilogue warp
     }
     ptx::fence_barrier_init();
     ptx::fence_proxy_async();
@@ -101,6 +111,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
   const int taps = p.ksz * p.ksz;
   const int half = p.ksz >> 1;
 
+  if (warp < kEpiWarp0) {
+  ptx::setmaxnreg_dec<kRegsIssue>();
   if (warp == 0) {
     // ============================== TMA producer ==============================
     if (lane == 0) {
@@ -134,17 +146,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
   } else if (warp == 1) {
     // ============================== MMA issuer ================================
     const uint32_t idesc = make_idesc_f16(p.n_pad);
+    const int total_chunks = taps * p.chunks;
     int stage = 0;
     uint32_t phase = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
+    uint32_t seg_count = 0;
     for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
-      ptx::mbar_wait(&acc_empty[acc], acc_phase ^ 1);
-      ptx::tc_fence_after();
-      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kAccStride);
-      uint32_t accumulate = 0;
-      for (int tap = 0; tap < taps; ++tap) {
-        for (int ch = 0; ch < p.chunks; ++ch) {
+      for (int c0 = 0; c0 < total_chunks; c0 += p.seg_chunks) {
+        const int acc = seg_count & 1;
+        ptx::mbar_wait(&acc_empty[acc], ((seg_count >> 1) & 1) ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kAccStride);
+        uint32_t accumulate = 0;  // every segment starts from zero
+        const int c1 = (c0 + p.seg_chunks < total_chunks) ? c0 + p.seg_chunks : total_chunks;
+        for (int c = c0; c < c1; ++c) {
+          const int ch = c % p.chunks;
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
           if (lane == 0) {
@@ -158,33 +173,45 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
               const uint32_t koff = ks * 32;  // 16 fp16 along K inside the swizzled row
               const uint64_t da_hi = make_smem_desc<KC>(a_hi + koff);
               const uint64_t db_hi = make_smem_desc<KC>(b_hi + koff);
-              ptx::mma_f16_ss(tmem_d, da_hi, db_hi, idesc, accumulate);
-              accumulate = 1;
               if (NPLANES == 2) {
+                // small correction terms first, the dominant hi*hi product last
                 const uint64_t da_lo = make_smem_desc<KC>(a_lo + koff);
                 const uint64_t db_lo = make_smem_desc<KC>(b_lo + koff);
-                ptx::mma_f16_ss(tmem_d, da_lo, db_hi, idesc, 1);
+                ptx::mma_f16_ss(tmem_d, da_lo, db_hi, idesc, accumulate);
                 ptx::mma_f16_ss(tmem_d, da_hi, db_lo, idesc, 1);
+                accumulate = 1;
               }
+              ptx::mma_f16_ss(tmem_d, da_hi, db_hi, idesc, accumulate);
+              accumulate = 1;
             }
             ptx::mma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs have read it
           }
           __syncwarp();
           if (++stage == num_stages) { stage = 0; phase ^= 1; }
         }
+        if (lane == 0) ptx::mma_commit(&acc_full[acc]);  // segment complete -> epilogue promotes it
+        __syncwarp();
+        ++seg_count;
       }
-      if (lane == 0) ptx::mma_commit(&acc_full[acc]);  // accumulator complete -> epilogue
-      __syncwarp();
-      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
     }
+  }
   } else {
+    ptx::setmaxnreg_inc<kRegsEpilogue>();
     // ============================== epilogue ==================================
+    const int ew = warp - kEpiWarp0;
     const int quad = warp & 3;               // TMEM lane quadrant this warp may access
+    const int grp = ew >> 2;                 // which group of columns this warp owns
     const int row = quad * 32 + lane;        // pixel index inside the TH x TW patch
     const int py = row / g.TW, px = row - py * g.TW;
     const int n_total = p.n_tiles * p.n_pad;
-    int acc = 0;
-    uint32_t acc_phase = 0;
+    const int nch = p.n_pad >> 4;
+    const int per = (nch + kColSplit - 1) / kColSplit;
+    const int first_chunk = grp * per;
+    const int my_chunks = (nch - first_chunk) < per ? ((nch - first_chunk) > 0 ? nch - first_chunk : 0) : per;
+    const int col_base = first_chunk * 16;
+    const int total_chunks = taps * p.chunks;
+    const int nseg = (total_chunks + p.seg_chunks - 1) / p.seg_chunks;
+    uint32_t seg_count = 0;
     for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
       const int n_tile = work % p.n_tiles;
       const int tile = work / p.n_tiles;
@@ -194,18 +221,36 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
       const int y = ty * g.TH + py, x = tx * g.TW + px;
       const bool valid = (y < g.H) && (x < g.W);
 
-      ptx::mbar_wait(&acc_full[acc], acc_phase);
-      ptx::tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kAccStride);
-      for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
-        float v[16];
-        ptx::tmem_ld16(taddr + c0, v);
-        if (valid) epilogue_store16(p.epi, g, n_total, img, y, x, n_tile * p.n_pad + c0, v);
+      float sum[kMaxColChunks][16];
+      for (int s = 0; s < nseg; ++s) {
+        const int acc = seg_count & 1;
+        ptx::mbar_wait(&acc_full[acc], (seg_count >> 1) & 1);
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kAccStride + col_base);
+#pragma unroll
+        for (int j = 0; j < kMaxColChunks; ++j) {
+          if (j < my_chunks) {
+            float v[16];
+            ptx::tmem_ld16(taddr + j * 16, v);
+            if (s == 0) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) sum[j][i] = v[i];
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) sum[j][i] += v[i];  // fp32 round-to-nearest promotion
+            }
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&acc_empty[acc]);
+        ++seg_count;
       }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&acc_empty[acc]);
-      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < kMaxColChunks; ++j)
+          if (j < my_chunks) epilogue_store16(p.epi, g, n_total, img, y, x, n_tile * p.n_pad + col_base + j * 16, sum[j]);
+      }
     }
   }
 

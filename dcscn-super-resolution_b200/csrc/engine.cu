@@ -138,6 +138,7 @@ struct dcscn_handle {
 
   int conv_impl = 0;
   int kc = 64;
+  int seg_chunks = 1;
   int64_t launches = 0;
   PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
 };
@@ -524,6 +525,7 @@ static int add_tc_launch(dcscn_handle* h, Plan* pl, const TcLayer& t, const __ha
   L.p.chunks = (t.cin_pad + h->kc - 1) / h->kc;
   L.p.n_tiles = t.n_tiles;
   L.p.n_pad = t.n_pad;
+  L.p.seg_chunks = h->seg_chunks;
   L.p.wpack = t.d_wpack;
   L.p.epi = epi;
   L.p.epi.bias = t.d_bias;
@@ -902,6 +904,11 @@ int dcscn_set_option(dcscn_handle* h, const char* key, int64_t value) {
       h->plans.clear();
       h->last_plan = nullptr;
     }
+  } else if (k == "seg_chunks") {
+    if (value < 1 || value > 4096) return fail("seg_chunks must be >= 1");
+    h->seg_chunks = (int)value;
+    h->plans.clear();
+    h->last_plan = nullptr;
   } else {
     return fail("dcscn_set_option: unknown option '%s'", key);
   }

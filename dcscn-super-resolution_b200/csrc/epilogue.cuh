@@ -27,18 +27,27 @@ __host__ __device__ __forceinline__ bool dropout_keep(uint32_t seed, uint32_t la
   return (float)(dropout_hash(seed, layer, idx) >> 8) * (1.0f / 16777216.0f) < keep_prob;
 }
 
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
+  return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+
 __device__ __forceinline__ void store_planes16(__half* dst_hi, __half* dst_lo, size_t off, const float (&v)[16]) {
-  __align__(16) __half hi[16];
-  __align__(16) __half lo[16];
+  uint32_t ph[8], pl[8];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) split_f16(v[i], hi[i], lo[i]);
-  uint4* ph = reinterpret_cast<uint4*>(dst_hi + off);
-  ph[0] = reinterpret_cast<const uint4*>(hi)[0];
-  ph[1] = reinterpret_cast<const uint4*>(hi)[1];
+  for (int i = 0; i < 8; ++i) {
+    __half h0, l0, h1, l1;
+    split_f16(v[2 * i], h0, l0);
+    split_f16(v[2 * i + 1], h1, l1);
+    ph[i] = pack_h2(h0, h1);
+    pl[i] = pack_h2(l0, l1);
+  }
+  uint4* qh = reinterpret_cast<uint4*>(dst_hi + off);
+  qh[0] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+  qh[1] = make_uint4(ph[4], ph[5], ph[6], ph[7]);
   if (dst_lo != nullptr) {
-    uint4* pl = reinterpret_cast<uint4*>(dst_lo + off);
-    pl[0] = reinterpret_cast<const uint4*>(lo)[0];
-    pl[1] = reinterpret_cast<const uint4*>(lo)[1];
+    uint4* ql = reinterpret_cast<uint4*>(dst_lo + off);
+    ql[0] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+    ql[1] = make_uint4(pl[4], pl[5], pl[6], pl[7]);
   }
 }
 
@@ -101,7 +110,7 @@ __device__ __forceinline__ void epilogue_store16(const EpiParams& e, const ConvG
 #pragma unroll
     for (int t = 0; t < 16; ++t) {
       const int col = cg + t;
-      if (col >= e.n_valid) break;
+      if (col >= e.n_valid) continue;
       const int ij = col / co, c = col - ij * co;
       const int i = ij / r, j = ij - i * r;
       const size_t pix = (size_t)((size_t)img * HR_H + (y * r + i)) * HR_W + (x * r + j);

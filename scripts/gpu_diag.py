@@ -19,7 +19,7 @@ from helper import engine as E  # noqa: E402
 from helper import tf_bundle  # noqa: E402
 
 
-def run_case(name, cfg_kwargs, weights, n, h, w, seed=0, precision=E.PRECISION_F16X3, modes=((1, 64), (0, 64), (0, 32))):
+def run_case(name, cfg_kwargs, weights, n, h, w, seed=0, precision=E.PRECISION_F16X3, modes=((1, 64, 1), (0, 64, 1), (0, 32, 1), (0, 64, 4), (0, 64, 10000))):
     ocfg = O.OracleConfig(**cfg_kwargs)
     if weights is None:
         weights = O.he_init_weights(ocfg, seed=seed)
@@ -35,18 +35,19 @@ def run_case(name, cfg_kwargs, weights, n, h, w, seed=0, precision=E.PRECISION_F
     eng.set_params(weights)
     xd, x2d = torch.from_numpy(x).cuda(), torch.from_numpy(x2).cuda()
     ok = True
-    for impl, kc in modes:
+    for impl, kc, seg in modes:
         eng.set_option("kc", kc)
+        eng.set_option("seg_chunks", seg)
         eng.set_option("conv_impl", impl)
         t = time.time()
         y = eng.forward(xd, x2d)
         torch.cuda.synchronize()
         dt = time.time() - t
         y = y.cpu().numpy()
-        line = "  impl=%s kc=%d  y max|d| vs fp64 %.3e  (%.1f ms)" % ("ref" if impl else "tc ", kc, np.abs(y - y64).max(), dt * 1e3)
+        line = "  impl=%s kc=%d seg=%d  y max|d| vs fp64 %.3e  vs fp32 %.3e (%.1f ms)" % ("ref" if impl else "tc ", kc, seg, np.abs(y - y64).max(), np.abs(y - y32).max(), dt * 1e3)
         bad = not np.isfinite(y).all() or np.abs(y - y64).max() > 2e-3
         print(line + ("   <-- MISMATCH" if bad else ""))
-        if bad or "-v" in sys.argv:
+        if "-v" in sys.argv or (bad and "-q" not in sys.argv):
             for k in inter:
                 key = "Up-PS" if k == "Up-PS" else k
                 if k == "R-CNN":
@@ -67,7 +68,7 @@ def load_golden(name):
 def main():
     print(torch.cuda.get_device_name(0))
     small = dict(scale=2, layers=4, filters=40, min_filters=24, filters_decay_gamma=1.5, nin_filters=24, nin_filters2=16)
-    ok = run_case("small odd", small, None, 1, 20, 37, modes=((1, 64), (0, 64)))
+    ok = run_case("small odd", small, None, 1, 20, 37, modes=((1, 64, 1), (0, 64, 1)))
     if "--first" in sys.argv:
         return
     ok &= run_case("small 48", small, None, 2, 48, 48)
@@ -76,9 +77,9 @@ def main():
     ok &= run_case("c-DCSCN x2 ckpt", cd, load_golden("dcscn_L7_F32to8_G1.20_NIN_A24_B8_PS_R1F32"), 1, 33, 50)
     ok &= run_case("L12 x2 ckpt", dict(), load_golden("dcscn_L12_F196to48_NIN_A64_PS_R1F32"), 2, 48, 48)
     ok &= run_case("L12 x4 ckpt", dict(scale=4), load_golden("dcscn_L12_F196to48_Sc4_NIN_A64_PS_R1F32"), 1, 24, 40,
-                   modes=((1, 64), (0, 64)))
+                   modes=((1, 64, 1), (0, 64, 1)))
     ok &= run_case("L12 x2 ckpt fast(f16x1)", dict(), load_golden("dcscn_L12_F196to48_NIN_A64_PS_R1F32"), 1, 48, 48,
-                   precision=E.PRECISION_F16X1, modes=((0, 64),))
+                   precision=E.PRECISION_F16X1, modes=((0, 64, 1),))
     print("ALL OK" if ok else "SOME MISMATCH")
 
 

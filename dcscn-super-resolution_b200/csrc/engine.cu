@@ -139,6 +139,9 @@ struct dcscn_handle {
   int conv_impl = 0;
   int kc = 64;
   int seg_chunks = 1;
+  int timing = 0;
+  std::vector<cudaEvent_t> ev;       // timing events (launch boundaries of the last forward)
+  int ev_used = 0;
   int64_t launches = 0;
   PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
 };
@@ -687,6 +690,17 @@ static int launch_tc(dcscn_handle* h, const TcLaunch& L, cudaStream_t st) {
   return npl == 2 ? launch_tc_inst<32, 2>(h, L, st) : launch_tc_inst<32, 1>(h, L, st);
 }
 
+static int mark(dcscn_handle* h, cudaStream_t st) {
+  if (!h->timing) return 0;
+  if (h->ev_used >= (int)h->ev.size()) {
+    cudaEvent_t e;
+    CUDA_TRY(cudaEventCreate(&e));
+    h->ev.push_back(e);
+  }
+  CUDA_TRY(cudaEventRecord(h->ev[h->ev_used++], st));
+  return 0;
+}
+
 static int forward_impl(dcscn_handle* h, const float* x, const float* x2, float* y, int n, int H, int W,
                         cudaStream_t st) {
   if (n <= 0 || H <= 0 || W <= 0) return fail("forward: bad shape n=%d h=%d w=%d", n, H, W);
@@ -696,6 +710,8 @@ static int forward_impl(dcscn_handle* h, const float* x, const float* x2, float*
   Plan* pl = get_plan(h, n, H, W);
   if (!pl) return 1;
   h->last_plan = pl;
+  h->ev_used = 0;
+  if (mark(h, st)) return 1;
 
   {  // CNN1
     ConvFirstParams p = pl->first;
@@ -706,9 +722,12 @@ static int forward_impl(dcscn_handle* h, const float* x, const float* x2, float*
     conv_first_kernel<<<grid, 256, smem, st>>>(p);
     CUDA_TRY(cudaGetLastError());
     h->launches++;
+    if (mark(h, st)) return 1;
   }
-  for (const TcLaunch& L : pl->tc)
+  for (const TcLaunch& L : pl->tc) {
     if (launch_tc(h, L, st)) return 1;
+    if (mark(h, st)) return 1;
+  }
   {  // R-CNN1 + x2
     ConvLastParams p = pl->last;
     p.x2 = x2;
@@ -719,6 +738,7 @@ static int forward_impl(dcscn_handle* h, const float* x, const float* x2, float*
     conv_last_kernel<<<tiles, 256, smem, st>>>(p);
     CUDA_TRY(cudaGetLastError());
     h->launches++;
+    if (mark(h, st)) return 1;
   }
   return 0;
 }
@@ -904,6 +924,8 @@ int dcscn_set_option(dcscn_handle* h, const char* key, int64_t value) {
       h->plans.clear();
       h->last_plan = nullptr;
     }
+  } else if (k == "timing") {
+    h->timing = value ? 1 : 0;
   } else if (k == "seg_chunks") {
     if (value < 1 || value > 4096) return fail("seg_chunks must be >= 1");
     h->seg_chunks = (int)value;
@@ -911,6 +933,23 @@ int dcscn_set_option(dcscn_handle* h, const char* key, int64_t value) {
     h->last_plan = nullptr;
   } else {
     return fail("dcscn_set_option: unknown option '%s'", key);
+  }
+  return 0;
+}
+
+int dcscn_get_timings(dcscn_handle* h, float* ms, int capacity, int* count, char* names, int names_len) {
+  if (!h || !count) return fail("dcscn_get_timings: null argument");
+  *count = 0;
+  if (h->ev_used < 2) return 0;
+  CUDA_TRY(cudaEventSynchronize(h->ev[h->ev_used - 1]));
+  const int n = h->ev_used - 1;
+  for (int i = 0; i < n && i < capacity; ++i) CUDA_TRY(cudaEventElapsedTime(&ms[i], h->ev[i], h->ev[i + 1]));
+  *count = n;
+  if (names && names_len > 0) {
+    std::string s = "CNN1";
+    for (const TcLayer& t : h->tcl) s += "," + t.name;
+    s += ",R-CNN1";
+    snprintf(names, names_len, "%s", s.c_str());
   }
   return 0;
 }

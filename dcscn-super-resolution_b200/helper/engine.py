@@ -51,7 +51,7 @@ class DcscnConfig(ctypes.Structure):
 EXPORTED_SYMBOLS = [
     "dcscn_create", "dcscn_destroy", "dcscn_last_error", "dcscn_num_params", "dcscn_param_info",
     "dcscn_set_param", "dcscn_get_param", "dcscn_forward", "dcscn_forward_host", "dcscn_get_activation",
-    "dcscn_set_option", "dcscn_launch_count", "dcscn_device_bytes",
+    "dcscn_set_option", "dcscn_get_timings", "dcscn_launch_count", "dcscn_device_bytes",
 ]
 
 _lib = None
@@ -84,6 +84,7 @@ def load_library(path=None):
     lib.dcscn_forward_host.argtypes = [vp, vp, vp, vp, ci, ci, ci]
     lib.dcscn_get_activation.argtypes = [vp, ctypes.c_char_p, fp, c64]
     lib.dcscn_set_option.argtypes = [vp, ctypes.c_char_p, c64]
+    lib.dcscn_get_timings.argtypes = [vp, fp, ci, ctypes.POINTER(ci), ctypes.c_char_p, ci]
     lib.dcscn_launch_count.argtypes = [vp]
     lib.dcscn_launch_count.restype = c64
     lib.dcscn_device_bytes.argtypes = [vp]
@@ -203,6 +204,14 @@ class Engine:
 
     def set_option(self, key, value):
         self._check(self.lib.dcscn_set_option(self.handle, key.encode(), int(value)))
+
+    def timings(self):
+        """[(launch name, ms)] of the last forward (needs set_option("timing", 1) before it)."""
+        ms = (ctypes.c_float * 64)()
+        cnt = ctypes.c_int()
+        names = ctypes.create_string_buffer(1024)
+        self._check(self.lib.dcscn_get_timings(self.handle, ms, 64, ctypes.byref(cnt), names, 1024))
+        return list(zip(names.value.decode().split(","), [float(ms[i]) for i in range(cnt.value)]))
 
     @property
     def launch_count(self):

@@ -89,8 +89,13 @@ int dcscn_forward_host(dcscn_handle* h, const float* x, const float* x2, float* 
 int dcscn_get_activation(dcscn_handle* h, const char* tensor, float* host_data, int64_t numel);
 
 /* Options: "conv_impl" 0 = tcgen05 (default), 1 = CUDA-core fp32 validation kernels;
- *          "kc" 64 | 32 = K-chunk (channels per pipeline stage) of the tensor-core kernel. */
+ *          "kc" 64 | 32 = K-chunk (channels per pipeline stage) of the tensor-core kernel;
+ *          "seg_chunks" = pipeline stages per fp32-promotion segment (default 1);
+ *          "timing" 0 | 1 = record per-launch CUDA events (see dcscn_get_timings). */
 int dcscn_set_option(dcscn_handle* h, const char* key, int64_t value);
+/* With option "timing" = 1 every launch of a forward is bracketed by CUDA events on its stream; this returns the
+ * device time in ms of each launch of the LAST forward (in launch order) and their comma-separated names. */
+int dcscn_get_timings(dcscn_handle* h, float* ms, int capacity, int* count, char* names, int names_len);
 /* Number of kernels this handle has launched so far (bench.py "gpu_launches"). */
 int64_t dcscn_launch_count(dcscn_handle* h);
 /* Bytes of device memory currently held by the handle. */

@@ -155,7 +155,7 @@ def he_init_weights(cfg, seed=0):
 # ------------------------------------------------------------------ ops ----
 
 def _t(a, dtype):
-    return torch.as_tensor(np.ascontiguousarray(a)).to(dtype)
+    return torch.from_numpy(np.array(a, copy=True, order="C")).to(dtype)
 
 
 def conv2d_same(x_nchw, w_hwio, dtype):

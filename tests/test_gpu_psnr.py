@@ -1,0 +1,87 @@
+"""PSNR / pixel parity on Set5 through the drop-in class (DCSCN.SuperResolution + evaluate pipeline), GPU."""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import dcscn_oracle as O
+from conftest import GOLDEN, MODEL_FLAGS, load_golden_weights
+
+pytestmark = pytest.mark.gpu
+
+KA = json.load(open(os.path.join(GOLDEN, "psnr_known_answers.json")))
+
+
+def build_model(tmp_path, flag_args, ensemble):
+    from helper import args as A
+    import DCSCN
+    f = A._Flags()
+    for name, (kind, default, help_text) in A.FLAGS._defs.items():
+        f._define(name, default, help_text, kind)
+    f.parse(["prog", "--checkpoint_dir=" + os.path.join(GOLDEN, "models"), "--self_ensemble=%d" % ensemble,
+             "--log_filename=" + str(tmp_path / "log.txt"), "--tf_log_dir=" + str(tmp_path / "tf_log"),
+             "--graph_dir=" + str(tmp_path / "graphs"), "--output_dir=" + str(tmp_path / "out")] + flag_args)
+    m = DCSCN.SuperResolution(f, model_name=f.model_name)
+    m.build_graph()
+    m.build_summary_saver()
+    m.init_all_variables()
+    m.load_model(f.load_model_name)
+    return m
+
+
+CD = ["--scale=2", "--layers=7", "--filters=32", "--min_filters=8", "--filters_decay_gamma=1.2", "--nin_filters=24",
+      "--nin_filters2=8", "--reconstruct_layers=0", "--pixel_shuffler_filters=1"]
+
+
+@pytest.mark.parametrize("flag_args,model,ens", [
+    (CD, "dcscn_L7_F32to8_G1.20_NIN_A24_B8_PS_R1F32", 1),
+    ([], "dcscn_L12_F196to48_NIN_A64_PS_R1F32", 1),
+], ids=["c-DCSCN", "L12"])
+def test_set5_psnr_and_pixels(tmp_path, flag_args, model, ens):
+    m = build_model(tmp_path, flag_args, ens)
+    assert m.name == model
+    case = [c for c in KA["cases"] if c["model"] == model and c["dataset"] == "set5" and c["ensemble"] == ens][0]
+    orc = O.Oracle(O.OracleConfig(**MODEL_FLAGS[model]), load_golden_weights(model), torch.float32)
+    ps = []
+    for f in sorted(glob.glob(os.path.join(GOLDEN, "data", "set5", "*.png"))):
+        psnr, ssim = m.do_for_evaluate(f)
+        p_orc = O.do_for_evaluate(orc, f, ens)
+        assert abs(psnr - p_orc) <= 0.01, (f, psnr, p_orc)       # north_star: PSNR within 0.01 dB
+        ps.append(psnr)
+        lr, bic, _ = O.build_inputs_for_evaluate(f, 2)
+        out = m.do(lr, bic)
+        ref = O.do(orc, lr, bic, ens)
+        assert np.abs(out - ref).max() <= 1e-3, f                 # north_star: 1e-3 absolute vs the fp32 CPU forward
+    assert abs(np.mean(ps) - case["probe"]) <= 0.01
+    assert abs(np.mean(ps) - case["readme"]) <= 0.021
+
+
+def test_self_ensemble_8_matches_oracle(tmp_path):
+    m = build_model(tmp_path, [], 8)
+    model = "dcscn_L12_F196to48_NIN_A64_PS_R1F32"
+    orc = O.Oracle(O.OracleConfig(), load_golden_weights(model), torch.float32)
+    f = sorted(glob.glob(os.path.join(GOLDEN, "data", "set5", "*.png")))[4]  # 172x114 LR: both orientations
+    lr, bic, true_y = O.build_inputs_for_evaluate(f, 2)
+    out = m.do(lr, bic)
+    ref = O.do(orc, lr, bic, 8)
+    assert np.abs(out - ref).max() <= 1e-3
+    assert abs(O.compute_psnr(true_y, out, 2) - KA["l12_x2_set5_ens8_per_image"][4]) <= 0.01
+
+
+def test_save_and_reload_checkpoint(tmp_path):
+    """save_model writes a TF V2 bundle that load_model (and the reference's Saver) can read back."""
+    import shutil
+    m = build_model(tmp_path, CD, 1)
+    f = sorted(glob.glob(os.path.join(GOLDEN, "data", "set5", "*.png")))[0]
+    p0, _ = m.do_for_evaluate(f)
+    m.checkpoint_dir = str(tmp_path / "ckpt")
+    m.save_model()
+    m.init_all_variables()                       # scramble
+    p_rand, _ = m.do_for_evaluate(f)
+    assert abs(p_rand - p0) > 1.0
+    m.load_model()
+    p1, _ = m.do_for_evaluate(f)
+    assert p1 == p0

@@ -1,0 +1,142 @@
+"""Host-side logic of the drop-in (flags, model-name grammar, utilities, loader) - CPU only."""
+import glob
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from helper import args as A
+from helper import loader, utilty as util
+
+from conftest import GOLDEN, PKG, ROOT
+import dcscn_oracle as O
+
+
+def fresh_flags(argv):
+    f = A._Flags()
+    for name, (kind, default, help_text) in A.FLAGS._defs.items():
+        f._define(name, default, help_text, kind)
+    rest = f.parse(["prog"] + argv)
+    return f, rest
+
+
+def test_flag_defaults_match_reference():
+    f, _ = fresh_flags([])
+    # helper/args.py:16-98 defaults of the reference
+    expect = dict(scale=2, layers=12, filters=196, min_filters=48, filters_decay_gamma=1.5, use_nin=True,
+                  nin_filters=64, nin_filters2=32, cnn_size=3, reconstruct_layers=1, reconstruct_filters=32,
+                  dropout_rate=0.8, activator="prelu", pixel_shuffler=True, pixel_shuffler_filters=0,
+                  self_ensemble=8, batch_norm=False, depthwise_separable=False, clipping_norm=5.0,
+                  initializer="he", l2_decay=0.0001, optimizer="adam", beta1=0.9, beta2=0.999, epsilon=1e-8,
+                  batch_num=20, batch_image_size=48, training_images=24000, initial_lr=0.002, lr_decay=0.5,
+                  lr_decay_epoch=9, end_lr=2e-5, dataset="bsd200", test_dataset="set5", max_value=255.0,
+                  channels=1, psnr_calc_border_size=-1, checkpoint_dir="models", output_dir="output",
+                  gpu_device_id=0)
+    for k, v in expect.items():
+        assert getattr(f, k) == v, k
+
+
+def test_flag_parsing_forms():
+    f, rest = fresh_flags(["--scale=4", "--layers", "7", "--nouse_nin", "--batch_norm", "--pixel_shuffler=false",
+                           "--filters_decay_gamma=1.2", "positional"])
+    assert f.scale == 4 and f.layers == 7 and f.use_nin is False and f.batch_norm is True
+    assert f.pixel_shuffler is False and abs(f.filters_decay_gamma - 1.2) < 1e-12
+    assert rest == ["prog", "positional"]
+    with pytest.raises(SystemExit):
+        fresh_flags(["--no_such_flag=1"])
+
+
+class _NameOnly:
+    """get_model_name without constructing an engine."""
+    from DCSCN import SuperResolution as _SR
+    get_model_name = _SR.get_model_name
+
+
+def name_for(**kw):
+    f, _ = fresh_flags(["--%s=%s" % (k, v) for k, v in kw.items()])
+    o = _NameOnly()
+    o.layers, o.filters, o.min_filters = f.layers, f.filters, min(f.filters, f.min_filters)
+    o.filters_decay_gamma, o.cnn_size, o.scale, o.use_nin = f.filters_decay_gamma, f.cnn_size, f.scale, f.use_nin
+    o.nin_filters, o.nin_filters2, o.pixel_shuffler, o.max_value = f.nin_filters, f.nin_filters2, f.pixel_shuffler, f.max_value
+    o.activator, o.batch_norm, o.depthwise_separable = f.activator, f.batch_norm, f.depthwise_separable
+    o.reconstruct_layers, o.reconstruct_filters = max(f.reconstruct_layers, 1), f.reconstruct_filters
+    return o.get_model_name("")
+
+
+def test_model_name_grammar_matches_shipped_checkpoints():
+    # every name below is a file the reference ships under models/
+    assert name_for() == "dcscn_L12_F196to48_NIN_A64_PS_R1F32"
+    assert name_for(scale=4) == "dcscn_L12_F196to48_Sc4_NIN_A64_PS_R1F32"
+    assert name_for(layers=8, filters=96, scale=3) == "dcscn_L8_F96to48_Sc3_NIN_A64_PS_R1F32"
+    c = dict(layers=7, filters=32, min_filters=8, filters_decay_gamma=1.2, nin_filters=24, nin_filters2=8,
+             reconstruct_layers=0, pixel_shuffler_filters=1)
+    assert name_for(**c) == "dcscn_L7_F32to8_G1.20_NIN_A24_B8_PS_R1F32"
+    assert name_for(scale=4, depthwise_separable="true", **c) == "dcscn_L7_F32to8_G1.20_Sc4_NIN_A24_B8_PS_DS_R1F32"
+    for n in (name_for(), name_for(scale=4), name_for(**c)):
+        assert os.path.isfile(os.path.join(GOLDEN, "models", n + ".ckpt.index"))
+
+
+def test_flip_round_trip_and_shapes():
+    g = np.random.RandomState(0)
+    img = g.rand(5, 7, 1)
+    for t in range(8):
+        f = util.flip(img, t)
+        assert f.shape == ((7, 5, 1) if t >= 4 else (5, 7, 1))
+        np.testing.assert_array_equal(util.flip(f, t, invert=True), img)
+        np.testing.assert_array_equal(f, O.flip(img, t))
+
+
+def test_colour_and_psnr():
+    g = np.random.RandomState(1)
+    rgb = (g.rand(6, 8, 3) * 255)
+    y = util.convert_rgb_to_y(rgb)
+    ycc = util.convert_rgb_to_ycbcr(rgb)
+    np.testing.assert_allclose(y[:, :, 0], ycc[:, :, 0], atol=1e-9)
+    back = util.convert_ycbcr_to_rgb(ycc)
+    assert np.abs(back - rgb).max() < 0.5  # the reference's 3-decimal matrices are not exact inverses
+    a = g.rand(20, 20, 1) * 255
+    b = a + g.randn(20, 20, 1) * 3
+    psnr, ssim = util.compute_psnr_and_ssim(a, b, border_size=2)
+    assert abs(psnr - O.compute_psnr(a, b, border_size=2)) < 1e-12
+    assert 0 < ssim <= 1
+    assert util.get_psnr(4.0) == pytest.approx(20 * np.log10(255 / 2.0))
+
+
+def test_alignment_and_resize():
+    img = np.zeros((11, 14, 3), np.uint8)
+    assert util.set_image_alignment(img, 4).shape == (8, 12, 3)
+    f = np.random.RandomState(0).rand(12, 16, 1) * 255
+    up = util.resize_image_by_pil(f, 2)
+    assert up.shape == (24, 32, 1) and up.dtype == np.float32
+    np.testing.assert_array_equal(up, O.resize_image_by_pil(f, 2))
+
+
+def test_evaluation_inputs_match_oracle_pipeline():
+    f = sorted(glob.glob(os.path.join(GOLDEN, "data", "set5", "*.png")))[1]
+    true_image = util.set_image_alignment(util.load_image(f, print_console=False), 2)
+    lr = loader.build_input_image(true_image, channels=1, scale=2, alignment=2, convert_ycbcr=True)
+    o_lr, o_bic, o_true = O.build_inputs_for_evaluate(f, 2)
+    np.testing.assert_array_equal(lr, o_lr)
+    np.testing.assert_array_equal(util.resize_image_by_pil(lr, 2), o_bic)
+    np.testing.assert_array_equal(util.convert_rgb_to_y(true_image), o_true)
+
+
+def test_split_images():
+    img = np.arange(10 * 12, dtype=np.float64).reshape(10, 12, 1)
+    w = util.get_split_images(img, 4, stride=2)
+    assert w.shape == (4 * 5, 4, 4, 1)
+    np.testing.assert_array_equal(w[1, :, :, 0], img[0:4, 2:6, 0])
+    assert util.get_split_images(img, 16) is None
+
+
+def test_package_does_not_import_oracle():
+    """The product path must never route through the oracle."""
+    for path in glob.glob(os.path.join(PKG, "**", "*.py"), recursive=True) + glob.glob(os.path.join(PKG, "csrc", "*")):
+        if path.endswith((".so", ".o")):
+            continue
+        text = open(path, errors="replace").read()
+        assert not re.search(r"^\s*(import|from)\s+dcscn_oracle", text, re.M), path
+        assert "oracle/" not in text, path

@@ -20,6 +20,8 @@ enum EpilogueMode : int {
   EPI_PLANES = 0,      // fp16 hi/lo planes, same resolution (up to 2 column segments)
   EPI_D2S_F32 = 1,     // depth_to_space scatter into an fp32 NHWC buffer
   EPI_D2S_PLANES = 2,  // depth_to_space scatter into fp16 hi/lo planes
+  EPI_D2S_RDOT = 3,    // depth_to_space fused with the per-pixel half of the final cout=1 conv (R-CNN1):
+                       // writes, per HR pixel and filter tap, dot(h[pixel, :], w_last[tap, :])
 };
 
 struct EpiSegment {
@@ -43,6 +45,10 @@ struct EpiParams {
   int d2s_cout;        // channels after depth_to_space
   float* dst_f32;      // EPI_D2S_F32 destination [N, r*H, r*W, d2s_pitch]
   int d2s_pitch;
+  // EPI_D2S_RDOT: final conv weights [taps][d2s_cout] and tap-planar output [taps][N][rH][rW]
+  const float* rdot_w;
+  float* rdot_out;
+  int rdot_taps;
   // inverted dropout (training): keep-mask generated from a counter hash; keep_prob==1 -> off
   float keep_prob;
   uint32_t drop_seed;

@@ -22,11 +22,16 @@ struct ConvFirstParams {
 };
 
 __global__ void __launch_bounds__(256) conv_first_kernel(const ConvFirstParams p) {
-  extern __shared__ float s_w[];  // [taps][n_pad]
+  // weights as float4 [tap][q][group]: consecutive lanes (= consecutive channel groups) read consecutive 16 bytes
+  extern __shared__ float4 s_w4[];
   const int taps = p.ksz * p.ksz;
-  for (int i = threadIdx.x; i < taps * p.n_pad; i += blockDim.x) s_w[i] = p.w[i];
-  __syncthreads();
   const int groups = p.n_pad >> 4;
+  for (int i = threadIdx.x; i < taps * 4 * groups; i += blockDim.x) {
+    const int grp = i % groups, q = (i / groups) & 3, t = i / (4 * groups);
+    const float* src = p.w + t * p.n_pad + grp * 16 + q * 4;
+    s_w4[i] = make_float4(src[0], src[1], src[2], src[3]);
+  }
+  __syncthreads();
   const int half = p.ksz >> 1;
   const long long total = (long long)p.g.n_img * p.g.H * p.g.W * groups;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -44,9 +49,14 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const ConvFirstParams p
       const int yy = y + t / p.ksz - half, xx = x + t % p.ksz - half;
       if (yy < 0 || yy >= p.g.H || xx < 0 || xx >= p.g.W) continue;
       const float v = __ldg(xi + (size_t)yy * p.g.W + xx);
-      const float* wr = s_w + t * p.n_pad + grp * 16;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) acc[i] = fmaf(v, wr[i], acc[i]);
+      for (int q = 0; q < 4; ++q) {
+        const float4 w = s_w4[(t * 4 + q) * groups + grp];
+        acc[4 * q + 0] = fmaf(v, w.x, acc[4 * q + 0]);
+        acc[4 * q + 1] = fmaf(v, w.y, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(v, w.z, acc[4 * q + 2]);
+        acc[4 * q + 3] = fmaf(v, w.w, acc[4 * q + 3]);
+      }
     }
     epilogue_store16(p.epi, p.g, p.n_pad, img, y, x, grp * 16, acc);
   }
@@ -109,6 +119,32 @@ __global__ void __launch_bounds__(256) conv_last_kernel(const ConvLastParams p) 
   if (ox < p.W && oy < p.H) {
     const size_t o = ((size_t)img * p.H + oy) * p.W + ox;
     p.y[o] = acc + __ldg(p.x2 + o);
+  }
+}
+
+// Second half of the fused R-CNN1: y = sum over taps of the tap-planar partial products (written by the Up-PS
+// epilogue, EPI_D2S_RDOT) at the tap-shifted pixel, + x2  (DCSCN.py:318-325).
+struct ConvGatherParams {
+  int n_img, H, W;   // HR resolution
+  int ksz;
+  const float* v;    // [taps][n_img][H][W]
+  const float* x2;
+  float* y;
+};
+
+__global__ void __launch_bounds__(256) conv_last_gather_kernel(const ConvGatherParams p) {
+  const int half = p.ksz >> 1;
+  const size_t plane = (size_t)p.n_img * p.H * p.W;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < plane; idx += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(idx % p.W);
+    const int y = (int)((idx / p.W) % p.H);
+    float acc = 0.f;
+    for (int t = 0; t < p.ksz * p.ksz; ++t) {
+      const int yy = y + t / p.ksz - half, xx = x + t % p.ksz - half;
+      if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W)
+        acc += __ldg(p.v + (size_t)t * plane + idx + (ptrdiff_t)(yy - y) * p.W + (xx - x));
+    }
+    p.y[idx] = acc + __ldg(p.x2 + idx);
   }
 }
 

@@ -246,7 +246,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
         if (lane == 0) ptx::mbar_arrive(&acc_empty[acc]);
         ++seg_count;
       }
-      if (valid) {
+      if (p.epi.mode == EPI_D2S_RDOT) {
+        // this thread owns whole sub-pixel channel groups (host guarantees (columns per thread) % d2s_cout == 0)
+        float v[9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) v[t] = 0.f;
+#pragma unroll
+        for (int j = 0; j < kMaxColChunks; ++j) {
+          if (j < my_chunks) {
+            const int cg = n_tile * p.n_pad + col_base + j * 16;
+            if (cg < p.epi.n_valid) {
+              const int ij = cg / p.epi.d2s_cout, c = cg - ij * p.epi.d2s_cout;
+              rdot_accumulate16(p.epi, cg, c, sum[j], v);
+              if (c + 16 == p.epi.d2s_cout && valid) rdot_flush(p.epi, g, img, y, x, ij, v);
+            }
+          }
+        }
+      } else if (valid) {
 #pragma unroll
         for (int j = 0; j < kMaxColChunks; ++j)
           if (j < my_chunks) epilogue_store16(p.epi, g, n_total, img, y, x, n_tile * p.n_pad + col_base + j * 16, sum[j]);

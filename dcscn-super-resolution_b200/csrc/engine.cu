@@ -97,6 +97,11 @@ struct Plan {
   ConvFirstParams first;
   std::vector<TcLaunch> tc;      // in execution order
   ConvLastParams last;
+  bool fused_last = false;       // Up-PS epilogue computes the per-pixel half of R-CNN1 (EPI_D2S_RDOT)
+  int fused_index = -1;          // index into tc of the launch that carries the fused epilogue
+  TcLaunch unfused;              // same layer with the plain depth_to_space epilogue (validation path)
+  ConvGatherParams gather;
+  bool ran_fused = false;
 };
 
 struct dcscn_handle {
@@ -129,6 +134,7 @@ struct dcscn_handle {
   __half *nin_hi = nullptr, *nin_lo = nullptr;
   __half *mid_hi = nullptr, *mid_lo = nullptr;
   float* hr = nullptr;
+  float* vbuf = nullptr;             // tap-planar partial products of the fused R-CNN1 [9][N][sH][sW]
   float *io_x = nullptr, *io_x2 = nullptr, *io_y = nullptr;  // staging for forward_host
   size_t io_cap = 0;
   int64_t device_bytes = 0;
@@ -140,6 +146,7 @@ struct dcscn_handle {
   int kc = 64;
   int seg_chunks = 1;
   int timing = 0;
+  int fuse_last = 1;                 // fold the per-pixel half of R-CNN1 into the last Up-PS epilogue
   std::vector<cudaEvent_t> ev;       // timing events (launch boundaries of the last forward)
   int ev_used = 0;
   int64_t launches = 0;
@@ -472,6 +479,7 @@ static int ensure_workspace(dcscn_handle* h, size_t lr_px) {
     if (dev_alloc(h, &h->mid_lo, two ? lr_px * 4 * h->mid_pitch : 0, true)) return 1;
   }
   if (dev_alloc(h, &h->hr, lr_px * s2 * h->ps_out, true)) return 1;
+  if (dev_alloc(h, &h->vbuf, lr_px * s2 * 9, true)) return 1;
   h->cap_px = lr_px;
   return 0;
 }
@@ -648,6 +656,26 @@ static Plan* get_plan(dcscn_handle* h, int n, int H, int W) {
     HR_H *= 2;
     HR_W *= 2;
   }
+  {  // the last depth_to_space layer can carry the per-pixel half of R-CNN1 in its epilogue
+    TcLaunch& L = pl->tc.back();
+    const int cout = h->ps_out, nch = L.p.n_pad >> 4, per = (nch + kColSplit - 1) / kColSplit;
+    const int klast = find_layer(h, "R-CNN1")->k;
+    pl->unfused = L;
+    pl->fused_index = (int)pl->tc.size() - 1;
+    pl->fused_last = (klast == 3) && (cout % 16 == 0) && (nch % kColSplit == 0) && ((per * 16) % cout == 0);
+    if (pl->fused_last) {
+      L.p.epi.mode = EPI_D2S_RDOT;
+      L.p.epi.rdot_w = h->d_last_w;
+      L.p.epi.rdot_out = h->vbuf;
+      L.p.epi.rdot_taps = klast * klast;
+    }
+    memset(&pl->gather, 0, sizeof(pl->gather));
+    pl->gather.n_img = n;
+    pl->gather.H = HR_H;
+    pl->gather.W = HR_W;
+    pl->gather.ksz = klast;
+    pl->gather.v = h->vbuf;
+  }
   memset(&pl->last, 0, sizeof(pl->last));
   pl->last.n_img = n;
   pl->last.H = HR_H;
@@ -724,9 +752,24 @@ static int forward_impl(dcscn_handle* h, const float* x, const float* x2, float*
     h->launches++;
     if (mark(h, st)) return 1;
   }
-  for (const TcLaunch& L : pl->tc) {
+  const bool fused = pl->fused_last && h->fuse_last && h->conv_impl == 0;
+  for (size_t i = 0; i < pl->tc.size(); ++i) {
+    const TcLaunch& L = ((int)i == pl->fused_index && !fused) ? pl->unfused : pl->tc[i];
     if (launch_tc(h, L, st)) return 1;
     if (mark(h, st)) return 1;
+  }
+  pl->ran_fused = fused;
+  if (fused) {  // R-CNN1 second half: 9-tap gather of the tap-planar partial products + x2
+    ConvGatherParams p = pl->gather;
+    p.x2 = x2;
+    p.y = y;
+    const size_t total = (size_t)p.n_img * p.H * p.W;
+    const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)h->sm_count * 16);
+    conv_last_gather_kernel<<<grid, 256, 0, st>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    if (mark(h, st)) return 1;
+    return 0;
   }
   {  // R-CNN1 + x2
     ConvLastParams p = pl->last;
@@ -794,6 +837,7 @@ int dcscn_destroy(dcscn_handle* h) {
   cudaFree(h->mid_hi);
   cudaFree(h->mid_lo);
   cudaFree(h->hr);
+  cudaFree(h->vbuf);
   cudaFree(h->io_x);
   cudaFree(h->io_x2);
   cudaFree(h->io_y);
@@ -888,6 +932,8 @@ int dcscn_get_activation(dcscn_handle* h, const char* tensor, float* host_data, 
     hi = h->b1_hi; lo = h->b1_lo; pitch = h->b1_w; off = 0; ch = c.nin_filters2;
   } else if (t == "Up-PS" && c.scale == 4) {
     hi = h->mid_hi; lo = h->mid_lo; pitch = h->mid_pitch; off = 0; ch = c.nin_filters + c.nin_filters2; px *= 4;
+  } else if (((t == "Up-PS" && c.scale != 4) || (t == "Up-PS2" && c.scale == 4)) && pl->ran_fused) {
+    return fail("dcscn_get_activation: '%s' is not materialised when the R-CNN1 fusion is on (set option fuse_last=0)", tensor);
   } else if ((t == "Up-PS" && c.scale != 4) || (t == "Up-PS2" && c.scale == 4)) {
     f32 = h->hr; pitch = h->ps_out; ch = h->ps_out; px *= (size_t)c.scale * c.scale;
   } else {
@@ -924,6 +970,8 @@ int dcscn_set_option(dcscn_handle* h, const char* key, int64_t value) {
       h->plans.clear();
       h->last_plan = nullptr;
     }
+  } else if (k == "fuse_last") {
+    h->fuse_last = value ? 1 : 0;
   } else if (k == "timing") {
     h->timing = value ? 1 : 0;
   } else if (k == "seg_chunks") {

@@ -126,4 +126,50 @@ __device__ __forceinline__ void epilogue_store16(const EpiParams& e, const ConvG
   }
 }
 
+// EPI_D2S_RDOT: 16 linear (bias only) columns of one sub-pixel -> accumulate the 9 per-tap dot products of the final
+// cout=1 convolution (R-CNN1, DCSCN.py:318-323) so that only `taps` floats per HR pixel ever reach HBM.
+__device__ __forceinline__ void rdot_accumulate16(const EpiParams& e, int cg, int c, const float (&acc)[16],
+                                                  float (&v)[9]) {
+  float t[16];
+  const float4* b4 = reinterpret_cast<const float4*>(e.bias + cg);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float4 b = __ldg(b4 + q);
+    t[4 * q + 0] = fmaf(acc[4 * q + 0], e.out_scale, b.x);
+    t[4 * q + 1] = fmaf(acc[4 * q + 1], e.out_scale, b.y);
+    t[4 * q + 2] = fmaf(acc[4 * q + 2], e.out_scale, b.z);
+    t[4 * q + 3] = fmaf(acc[4 * q + 3], e.out_scale, b.w);
+  }
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    if (tap < e.rdot_taps) {
+      const float4* w4 = reinterpret_cast<const float4*>(e.rdot_w + tap * e.d2s_cout + c);
+      float s = v[tap];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float4 w = __ldg(w4 + q);
+        s = fmaf(t[4 * q + 0], w.x, s);
+        s = fmaf(t[4 * q + 1], w.y, s);
+        s = fmaf(t[4 * q + 2], w.z, s);
+        s = fmaf(t[4 * q + 3], w.w, s);
+      }
+      v[tap] = s;
+    }
+  }
+}
+
+__device__ __forceinline__ void rdot_flush(const EpiParams& e, const ConvGeom& g, int img, int y, int x, int ij,
+                                           float (&v)[9]) {
+  const int r = e.d2s_r;
+  const int i = ij / r, j = ij - i * r;
+  const size_t HR_H = (size_t)g.H * r, HR_W = (size_t)g.W * r;
+  const size_t plane = (size_t)g.n_img * HR_H * HR_W;
+  const size_t pix = ((size_t)img * HR_H + (size_t)(y * r + i)) * HR_W + (size_t)(x * r + j);
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    if (tap < e.rdot_taps) e.rdot_out[(size_t)tap * plane + pix] = v[tap];
+    v[tap] = 0.f;
+  }
+}
+
 }  // namespace dcscn

@@ -69,6 +69,7 @@ struct ConvTCParams {
   int n_tiles;           // column tiles (N > 256 is split)
   int n_pad;             // columns per tile, multiple of 16, <= 256
   int seg_chunks;        // pipeline stages per accumulation segment (fp32 promotion period)
+  int cluster_size;      // CTAs per cluster sharing (multicasting) the weight tiles: 1, 2 or 4
   const __half* wpack;   // packed weights [n_tile][tap][chunk][plane][n_pad x KC] (pre-swizzled)
   EpiParams epi;
 };

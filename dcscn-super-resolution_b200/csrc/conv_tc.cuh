@@ -16,6 +16,10 @@
 //     333 UMMAs of CNN2).  K is therefore cut into short segments (`seg_chunks` pipeline stages): each segment
 //     accumulates in TMEM from zero, and the epilogue warps add the segment sums into fp32 registers with
 //     round-to-nearest ("promotion"), double-buffered against the next segment's UMMAs.
+//   * Weight tiles are the dominant L2->SM traffic (every 128-pixel tile streams the whole layer's weights).  CTAs
+//     are launched in clusters of `cs` (1, 2 or 4) that walk pixel tiles in lockstep; each CTA fetches 1/cs of
+//     every weight tile and multicasts it to the whole cluster (cp.async.bulk ... .multicast::cluster), and every
+//     CTA's MMA warp releases a pipeline stage in all cluster members (tcgen05.commit ... .multicast::cluster).
 //   * Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 4..11 = epilogue (registers re-balanced with setmaxnreg)
 //     (TMEM -> registers, running fp32 sums, then bias/PReLU/split -> global), persistent CTAs striding
 //     over (pixel-tile, column-tile) work items.
@@ -83,11 +87,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int cs = p.cluster_size;
+  const uint32_t rank = cs > 1 ? ptx::cluster_ctarank() : 0u;
+  const uint16_t cta_mask = (uint16_t)((1u << cs) - 1u);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < num_stages; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
-      ptx::mbar_init(&empty_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], cs);        // one tcgen05.commit arrival from every CTA of the cluster
     }
     for (int s = 0; s < kAccStages; ++s) {
       ptx::mbar_init(&acc_full[s], 1);
@@ -102,99 +109,119 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (cs > 1) ptx::cluster_sync();               // peers' barriers are initialised before anything targets them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const ConvGeom& g = p.g;
   const int tiles_per_img = g.tiles_x * g.tiles_y;
-  const int num_work = g.n_img * tiles_per_img * p.n_tiles;
+  const int num_tiles = g.n_img * tiles_per_img;
+  const int groups = (num_tiles + cs - 1) / cs;  // cs pixel tiles are processed by one cluster iteration
+  const int num_items = groups * p.n_tiles;
+  const int cluster_id = blockIdx.x / cs;
+  const int num_clusters = gridDim.x / cs;
   const int taps = p.ksz * p.ksz;
   const int half = p.ksz >> 1;
+  const int total_chunks = taps * p.chunks;
 
   if (warp < kEpiWarp0) {
-  ptx::setmaxnreg_dec<kRegsIssue>();
-  if (warp == 0) {
-    // ============================== TMA producer ==============================
-    if (lane == 0) {
-      ptx::prefetch_tensormap(&tm_hi);
-      if (NPLANES == 2) ptx::prefetch_tensormap(&tm_lo);
+    ptx::setmaxnreg_dec<kRegsIssue>();
+    if (warp == 0) {
+      // ============================== TMA producer ==============================
+      if (lane == 0) {
+        ptx::prefetch_tensormap(&tm_hi);
+        if (NPLANES == 2) ptx::prefetch_tensormap(&tm_lo);
+        const int slice_rows = p.n_pad / cs;                       // this CTA's share of every weight tile
+        const uint32_t slice_bytes = (uint32_t)(slice_rows * KC * 2);
+        const uint32_t slice_off = rank * slice_bytes;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int item = cluster_id; item < num_items; item += num_clusters) {
+          const int n_tile = item % p.n_tiles;
+          int tile = (item / p.n_tiles) * cs + (int)rank;
+          if (tile >= num_tiles) tile = num_tiles - 1;             // lockstep filler (stores are masked)
+          const int img = tile / tiles_per_img;
+          const int t2 = tile - img * tiles_per_img;
+          const int ty = t2 / g.tiles_x, tx = t2 - ty * g.tiles_x;
+          const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(p.wpack) +
+                                (size_t)n_tile * total_chunks * (size_t)(NPLANES * B_BYTES);
+          for (int tap = 0; tap < taps; ++tap) {
+            const int dy = tap / p.ksz - half, dx = tap % p.ksz - half;
+            for (int ch = 0; ch < p.chunks; ++ch) {
+              ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+              uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
+              ptx::mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)STAGE_BYTES);
+              ptx::tma_load_4d(st, &tm_hi, &full_bar[stage], ch * KC, tx * g.TW + dx, ty * g.TH + dy, img);
+              if (NPLANES == 2)
+                ptx::tma_load_4d(st + A_BYTES, &tm_lo, &full_bar[stage], ch * KC, tx * g.TW + dx, ty * g.TH + dy, img);
+              const uint8_t* wtile = wsrc + (size_t)(tap * p.chunks + ch) * (NPLANES * B_BYTES);
+              uint8_t* bdst = st + NPLANES * A_BYTES;
+              if (cs == 1) {
+                ptx::bulk_load(bdst, wtile, (uint32_t)(NPLANES * B_BYTES), &full_bar[stage]);
+              } else {
+#pragma unroll
+                for (int pl = 0; pl < NPLANES; ++pl)
+                  ptx::bulk_load_multicast(bdst + pl * B_BYTES + slice_off, wtile + (size_t)pl * B_BYTES + slice_off,
+                                           slice_bytes, &full_bar[stage], cta_mask);
+              }
+              if (++stage == num_stages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ============================== MMA issuer ================================
+      const uint32_t idesc = make_idesc_f16(p.n_pad);
       int stage = 0;
       uint32_t phase = 0;
-      for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
-        const int n_tile = work % p.n_tiles;
-        const int tile = work / p.n_tiles;
-        const int img = tile / tiles_per_img;
-        const int t2 = tile - img * tiles_per_img;
-        const int ty = t2 / g.tiles_x, tx = t2 - ty * g.tiles_x;
-        const __half* wsrc = p.wpack + (size_t)n_tile * taps * p.chunks * (size_t)(NPLANES * p.n_pad * KC);
-        for (int tap = 0; tap < taps; ++tap) {
-          const int dy = tap / p.ksz - half, dx = tap % p.ksz - half;
-          for (int ch = 0; ch < p.chunks; ++ch) {
-            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
-            ptx::mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)STAGE_BYTES);
-            ptx::tma_load_4d(st, &tm_hi, &full_bar[stage], ch * KC, tx * g.TW + dx, ty * g.TH + dy, img);
-            if (NPLANES == 2)
-              ptx::tma_load_4d(st + A_BYTES, &tm_lo, &full_bar[stage], ch * KC, tx * g.TW + dx, ty * g.TH + dy, img);
-            ptx::bulk_load(st + NPLANES * A_BYTES, wsrc + (size_t)(tap * p.chunks + ch) * (NPLANES * p.n_pad * KC),
-                           (uint32_t)(NPLANES * B_BYTES), &full_bar[stage]);
-            if (++stage == num_stages) { stage = 0; phase ^= 1; }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ============================== MMA issuer ================================
-    const uint32_t idesc = make_idesc_f16(p.n_pad);
-    const int total_chunks = taps * p.chunks;
-    int stage = 0;
-    uint32_t phase = 0;
-    uint32_t seg_count = 0;
-    for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
-      for (int c0 = 0; c0 < total_chunks; c0 += p.seg_chunks) {
-        const int acc = seg_count & 1;
-        ptx::mbar_wait(&acc_empty[acc], ((seg_count >> 1) & 1) ^ 1);
-        ptx::tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kAccStride);
-        uint32_t accumulate = 0;  // every segment starts from zero
-        const int c1 = (c0 + p.seg_chunks < total_chunks) ? c0 + p.seg_chunks : total_chunks;
-        for (int c = c0; c < c1; ++c) {
-          const int ch = c % p.chunks;
-          ptx::mbar_wait(&full_bar[stage], phase);
+      uint32_t seg_count = 0;
+      for (int item = cluster_id; item < num_items; item += num_clusters) {
+        for (int c0 = 0; c0 < total_chunks; c0 += p.seg_chunks) {
+          const int acc = seg_count & 1;
+          ptx::mbar_wait(&acc_empty[acc], ((seg_count >> 1) & 1) ^ 1);
           ptx::tc_fence_after();
-          if (lane == 0) {
-            const uint32_t a_hi = ptx::smem_u32(smem + (size_t)stage * STAGE_BYTES);
-            const uint32_t a_lo = a_hi + A_BYTES;
-            const uint32_t b_hi = a_hi + NPLANES * A_BYTES;
-            const uint32_t b_lo = b_hi + B_BYTES;
-            int ksteps = (p.cin_pad - ch * KC);
-            ksteps = (ksteps > KC ? KC : ksteps) >> 4;
-            for (int ks = 0; ks < ksteps; ++ks) {
-              const uint32_t koff = ks * 32;  // 16 fp16 along K inside the swizzled row
-              const uint64_t da_hi = make_smem_desc<KC>(a_hi + koff);
-              const uint64_t db_hi = make_smem_desc<KC>(b_hi + koff);
-              if (NPLANES == 2) {
-                // small correction terms first, the dominant hi*hi product last
-                const uint64_t da_lo = make_smem_desc<KC>(a_lo + koff);
-                const uint64_t db_lo = make_smem_desc<KC>(b_lo + koff);
-                ptx::mma_f16_ss(tmem_d, da_lo, db_hi, idesc, accumulate);
-                ptx::mma_f16_ss(tmem_d, da_hi, db_lo, idesc, 1);
+          const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kAccStride);
+          uint32_t accumulate = 0;  // every segment starts from zero
+          const int c1 = (c0 + p.seg_chunks < total_chunks) ? c0 + p.seg_chunks : total_chunks;
+          for (int c = c0; c < c1; ++c) {
+            const int ch = c % p.chunks;
+            ptx::mbar_wait(&full_bar[stage], phase);
+            ptx::tc_fence_after();
+            if (lane == 0) {
+              const uint32_t a_hi = ptx::smem_u32(smem + (size_t)stage * STAGE_BYTES);
+              const uint32_t a_lo = a_hi + A_BYTES;
+              const uint32_t b_hi = a_hi + NPLANES * A_BYTES;
+              const uint32_t b_lo = b_hi + B_BYTES;
+              int ksteps = (p.cin_pad - ch * KC);
+              ksteps = (ksteps > KC ? KC : ksteps) >> 4;
+              for (int ks = 0; ks < ksteps; ++ks) {
+                const uint32_t koff = ks * 32;  // 16 fp16 along K inside the swizzled row
+                const uint64_t da_hi = make_smem_desc<KC>(a_hi + koff);
+                const uint64_t db_hi = make_smem_desc<KC>(b_hi + koff);
+                if (NPLANES == 2) {
+                  // small correction terms first, the dominant hi*hi product last
+                  const uint64_t da_lo = make_smem_desc<KC>(a_lo + koff);
+                  const uint64_t db_lo = make_smem_desc<KC>(b_lo + koff);
+                  ptx::mma_f16_ss(tmem_d, da_lo, db_hi, idesc, accumulate);
+                  ptx::mma_f16_ss(tmem_d, da_hi, db_lo, idesc, 1);
+                  accumulate = 1;
+                }
+                ptx::mma_f16_ss(tmem_d, da_hi, db_hi, idesc, accumulate);
                 accumulate = 1;
               }
-              ptx::mma_f16_ss(tmem_d, da_hi, db_hi, idesc, accumulate);
-              accumulate = 1;
+              // free this smem stage (in every CTA of the cluster: peers multicast into it) once the MMAs have read it
+              if (cs == 1) ptx::mma_commit(&empty_bar[stage]);
+              else ptx::mma_commit_multicast(&empty_bar[stage], cta_mask);
             }
-            ptx::mma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs have read it
+            __syncwarp();
+            if (++stage == num_stages) { stage = 0; phase ^= 1; }
           }
+          if (lane == 0) ptx::mma_commit(&acc_full[acc]);  // segment complete -> epilogue promotes it
           __syncwarp();
-          if (++stage == num_stages) { stage = 0; phase ^= 1; }
+          ++seg_count;
         }
-        if (lane == 0) ptx::mma_commit(&acc_full[acc]);  // segment complete -> epilogue promotes it
-        __syncwarp();
-        ++seg_count;
       }
     }
-  }
   } else {
     ptx::setmaxnreg_inc<kRegsEpilogue>();
     // ============================== epilogue ==================================
@@ -209,17 +236,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     const int first_chunk = grp * per;
     const int my_chunks = (nch - first_chunk) < per ? ((nch - first_chunk) > 0 ? nch - first_chunk : 0) : per;
     const int col_base = first_chunk * 16;
-    const int total_chunks = taps * p.chunks;
     const int nseg = (total_chunks + p.seg_chunks - 1) / p.seg_chunks;
     uint32_t seg_count = 0;
-    for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
-      const int n_tile = work % p.n_tiles;
-      const int tile = work / p.n_tiles;
+    for (int item = cluster_id; item < num_items; item += num_clusters) {
+      const int n_tile = item % p.n_tiles;
+      const int tile = (item / p.n_tiles) * cs + (int)rank;
+      const bool real = tile < num_tiles;
       const int img = tile / tiles_per_img;
       const int t2 = tile - img * tiles_per_img;
       const int ty = t2 / g.tiles_x, tx = t2 - ty * g.tiles_x;
       const int y = ty * g.TH + py, x = tx * g.TW + px;
-      const bool valid = (y < g.H) && (x < g.W);
+      const bool valid = real && (y < g.H) && (x < g.W);
 
       float sum[kMaxColChunks][16];
       for (int s = 0; s < nseg; ++s) {
@@ -272,6 +299,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (cs > 1) ptx::cluster_sync();  // nobody exits while a peer may still signal its barriers
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, kAccStages * kAccStride);

@@ -145,6 +145,7 @@ struct dcscn_handle {
   int conv_impl = 0;
   int kc = 64;
   int seg_chunks = 1;
+  int cluster = 2;                   // CTAs per cluster multicasting the weight tiles
   int timing = 0;
   int fuse_last = 1;                 // fold the per-pixel half of R-CNN1 into the last Up-PS epilogue
   std::vector<cudaEvent_t> ev;       // timing events (launch boundaries of the last forward)
@@ -537,6 +538,9 @@ static int add_tc_launch(dcscn_handle* h, Plan* pl, const TcLayer& t, const __ha
   L.p.n_tiles = t.n_tiles;
   L.p.n_pad = t.n_pad;
   L.p.seg_chunks = h->seg_chunks;
+  int cs = h->cluster;
+  while (cs > 1 && (t.n_pad % cs != 0 || h->sm_count % cs != 0)) cs >>= 1;
+  L.p.cluster_size = cs;
   L.p.wpack = t.d_wpack;
   L.p.epi = epi;
   L.p.epi.bias = t.d_bias;
@@ -550,8 +554,9 @@ static int add_tc_launch(dcscn_handle* h, Plan* pl, const TcLayer& t, const __ha
   if (stages < 2) return fail("layer %s: pipeline stage of %zu bytes does not fit twice in shared memory", t.name.c_str(), stage);
   L.stages = stages;
   L.smem = stages * stage + 1024 + 256;
-  const long long work = (long long)n * g.tiles_x * g.tiles_y * t.n_tiles;
-  L.grid = (int)std::min<long long>(work, h->sm_count);
+  const long long tiles = (long long)n * g.tiles_x * g.tiles_y;
+  const long long items = ((tiles + cs - 1) / cs) * t.n_tiles;    // cluster iterations
+  L.grid = (int)std::min<long long>(items, h->sm_count / cs) * cs;
 
   // validation twin
   L.ref.g = g;
@@ -699,8 +704,20 @@ static int launch_tc_inst(dcscn_handle* h, const TcLaunch& L, cudaStream_t st) {
     CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<KC, NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  conv_tc_kernel<KC, NPL><<<L.grid, kTcThreads, L.smem, st>>>(L.tm_hi, L.tm_lo, L.p, L.stages);
-  CUDA_TRY(cudaGetLastError());
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(L.grid);
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = L.smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = L.p.cluster_size;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = L.p.cluster_size > 1 ? 1 : 0;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc_kernel<KC, NPL>, L.tm_hi, L.tm_lo, L.p, L.stages));
   return 0;
 }
 
@@ -970,6 +987,11 @@ int dcscn_set_option(dcscn_handle* h, const char* key, int64_t value) {
       h->plans.clear();
       h->last_plan = nullptr;
     }
+  } else if (k == "cluster") {
+    if (value != 1 && value != 2 && value != 4) return fail("cluster must be 1, 2 or 4");
+    h->cluster = (int)value;
+    h->plans.clear();
+    h->last_plan = nullptr;
   } else if (k == "fuse_last") {
     h->fuse_last = value ? 1 : 0;
   } else if (k == "timing") {

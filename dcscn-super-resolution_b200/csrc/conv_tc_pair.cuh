@@ -1,0 +1,305 @@
+// CTA-pair variant of the tcgen05 implicit-GEMM convolution (see conv_tc.cuh for the single-CTA description).
+//
+// Measured on B200 (profiles/r1a_*): the single-CTA kernel is bound by bytes entering each SM (TMA -> shared memory,
+// ~28 B/clk/SM) - every 128-pixel tile streams the whole layer's weight tiles - not by the tensor pipe (25 % active).
+// Here two CTAs of one TPC form a cluster and issue `tcgen05.mma.cta_group::2` with M = 256 (two 128-pixel tiles):
+// each CTA stages only HALF of every weight tile (N/2 rows) and the tensor core reads the other half from the
+// peer's shared memory, so weight bytes per SM (and weight shared-memory reads) are halved.
+//   * rank 0 ("leader") issues all UMMAs; both CTAs run a TMA producer for their own pixel tile + weight half,
+//     completing transactions on the LEADER's `full` barrier (cp.async.bulk.tensor ... .cta_group::2);
+//   * tcgen05.commit.cta_group::2 ... .multicast::cluster releases pipeline stages / publishes accumulator segments
+//     to both CTAs; both CTAs' epilogue warps promote their own 128 TMEM lanes and release the accumulator on the
+//     leader's barrier (remote mbarrier arrive).
+#pragma once
+#include "conv_tc.cuh"
+
+namespace dcscn {
+
+namespace ptx {
+
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA loads whose completion is signalled on an mbarrier that may live in the peer CTA of the pair.
+__device__ __forceinline__ void tma_load_4d_2sm(void* smem_dst, const CUtensorMap* tm, uint32_t bar_cluster_addr, int c0,
+                                                int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* tm, uint32_t bar_cluster_addr, int c0,
+                                                int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_result, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+               "r"(cols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2sm() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void mma_f16_ss_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit_2sm(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
+
+}  // namespace ptx
+
+__host__ __device__ inline size_t tc_pair_stage_bytes(int nplanes, int n_pad) {
+  return (size_t)nplanes * ((size_t)kTileM * 64 * 2 + (size_t)(n_pad / 2) * 64 * 2);
+}
+
+template <int NPLANES>
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
+                    const __grid_constant__ CUtensorMap tm_w, const ConvTCParams p, const int num_stages) {
+  constexpr int KC = 64;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int A_BYTES = TcSmem<KC>::kABytes;
+  const int half_rows = p.n_pad >> 1;                 // weight-tile rows staged by each CTA of the pair
+  const int BH_BYTES = half_rows * KC * 2;            // one plane of this CTA's weight half
+  const int STAGE_BYTES = NPLANES * (A_BYTES + BH_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)num_stages * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* acc_full = empty_bar + kMaxStages;
+  uint64_t* acc_empty = acc_full + kAccStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kAccStages);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < num_stages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);                     // leader's producer arrive + both CTAs' TMA bytes
+      ptx::mbar_init(&empty_bar[s], 1);                    // leader's tcgen05.commit (multicast to both CTAs)
+    }
+    for (int s = 0; s < kAccStages; ++s) {
+      ptx::mbar_init(&acc_full[s], 1);                     // leader's tcgen05.commit (multicast)
+      ptx::mbar_init(&acc_empty[s], 2 * kEpiWarps);        // epilogue warps of both CTAs (used on the leader only)
+    }
+    ptx::fence_barrier_init();
+    ptx::fence_proxy_async();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc_2sm(tmem_slot, kAccStages * kAccStride);
+    ptx::tmem_relinquish_2sm();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const ConvGeom& g = p.g;
+  const int tiles_per_img = g.tiles_x * g.tiles_y;
+  const int num_tiles = g.n_img * tiles_per_img;
+  const int groups = (num_tiles + 1) >> 1;
+  const int num_items = groups * p.n_tiles;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int taps = p.ksz * p.ksz;
+  const int half = p.ksz >> 1;
+  const int total_chunks = taps * p.chunks;
+
+  if (warp < kEpiWarp0) {
+    ptx::setmaxnreg_dec<kRegsIssue>();
+    if (warp == 0) {
+      // ============================== TMA producer (both CTAs) ==============================
+      if (lane == 0) {
+        ptx::prefetch_tensormap(&tm_hi);
+        if (NPLANES == 2) ptx::prefetch_tensormap(&tm_lo);
+        ptx::prefetch_tensormap(&tm_w);
+        const int wrows = NPLANES * half_rows;               // rows of one (tile, rank) block in the packed weights
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int item = cluster_id; item < num_items; item += num_clusters) {
+          const int n_tile = item % p.n_tiles;
+          int tile = (item / p.n_tiles) * 2 + (int)rank;
+          if (tile >= num_tiles) tile = num_tiles - 1;       // lockstep filler (stores are masked)
+          const int img = tile / tiles_per_img;
+          const int t2 = tile - img * tiles_per_img;
+          const int ty = t2 / g.tiles_x, tx = t2 - ty * g.tiles_x;
+          for (int tap = 0; tap < taps; ++tap) {
+            const int dy = tap / p.ksz - half, dx = tap % p.ksz - half;
+            for (int ch = 0; ch < p.chunks; ++ch) {
+              ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+              uint8_t* st = smem + (size_t)stage * STAGE_BYTES;
+              const uint32_t lead_full = ptx::mapa_shared(ptx::smem_u32(&full_bar[stage]), 0);
+              if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(2 * STAGE_BYTES));
+              ptx::tma_load_4d_2sm(st, &tm_hi, lead_full, ch * KC, tx * g.TW + dx, ty * g.TH + dy, img);
+              if (NPLANES == 2)
+                ptx::tma_load_4d_2sm(st + A_BYTES, &tm_lo, lead_full, ch * KC, tx * g.TW + dx, ty * g.TH + dy, img);
+              const int wblock = ((n_tile * taps + tap) * p.chunks + ch) * 2 + (int)rank;
+              ptx::tma_load_2d_2sm(st + NPLANES * A_BYTES, &tm_w, lead_full, 0, wblock * wrows);
+              if (++stage == num_stages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    } else if (warp == 1 && leader) {
+      // ============================== MMA issuer (leader CTA only) ================================
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.n_pad >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t seg_count = 0;
+      for (int item = cluster_id; item < num_items; item += num_clusters) {
+        for (int c0 = 0; c0 < total_chunks; c0 += p.seg_chunks) {
+          const int acc = seg_count & 1;
+          ptx::mbar_wait(&acc_empty[acc], ((seg_count >> 1) & 1) ^ 1);
+          ptx::tc_fence_after();
+          const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kAccStride);
+          uint32_t accumulate = 0;
+          const int c1 = (c0 + p.seg_chunks < total_chunks) ? c0 + p.seg_chunks : total_chunks;
+          for (int c = c0; c < c1; ++c) {
+            const int ch = c % p.chunks;
+            ptx::mbar_wait(&full_bar[stage], phase);
+            ptx::tc_fence_after();
+            if (lane == 0) {
+              const uint32_t a_hi = ptx::smem_u32(smem + (size_t)stage * STAGE_BYTES);
+              const uint32_t a_lo = a_hi + A_BYTES;
+              const uint32_t b_hi = a_hi + NPLANES * A_BYTES;
+              const uint32_t b_lo = b_hi + BH_BYTES;
+              int ksteps = (p.cin_pad - ch * KC);
+              ksteps = (ksteps > KC ? KC : ksteps) >> 4;
+              for (int ks = 0; ks < ksteps; ++ks) {
+                const uint32_t koff = ks * 32;
+                const uint64_t da_hi = make_smem_desc<KC>(a_hi + koff);
+                const uint64_t db_hi = make_smem_desc<KC>(b_hi + koff);
+                if (NPLANES == 2) {
+                  const uint64_t da_lo = make_smem_desc<KC>(a_lo + koff);
+                  const uint64_t db_lo = make_smem_desc<KC>(b_lo + koff);
+                  ptx::mma_f16_ss_2sm(tmem_d, da_lo, db_hi, idesc, accumulate);
+                  ptx::mma_f16_ss_2sm(tmem_d, da_hi, db_lo, idesc, 1);
+                  accumulate = 1;
+                }
+                ptx::mma_f16_ss_2sm(tmem_d, da_hi, db_hi, idesc, accumulate);
+                accumulate = 1;
+              }
+              ptx::mma_commit_2sm(&empty_bar[stage], 3);   // release this stage in both CTAs
+            }
+            __syncwarp();
+            if (++stage == num_stages) { stage = 0; phase ^= 1; }
+          }
+          if (lane == 0) ptx::mma_commit_2sm(&acc_full[acc], 3);  // segment complete in both CTAs' TMEM
+          __syncwarp();
+          ++seg_count;
+        }
+      }
+    }
+  } else {
+    ptx::setmaxnreg_inc<kRegsEpilogue>();
+    // ============================== epilogue (both CTAs, own 128 TMEM lanes) ==================================
+    const int ew = warp - kEpiWarp0;
+    const int quad = warp & 3;
+    const int grp = ew >> 2;
+    const int row = quad * 32 + lane;
+    const int py = row / g.TW, px = row - py * g.TW;
+    const int n_total = p.n_tiles * p.n_pad;
+    const int nch = p.n_pad >> 4;
+    const int per = (nch + kColSplit - 1) / kColSplit;
+    const int first_chunk = grp * per;
+    const int my_chunks = (nch - first_chunk) < per ? ((nch - first_chunk) > 0 ? nch - first_chunk : 0) : per;
+    const int col_base = first_chunk * 16;
+    const int nseg = (total_chunks + p.seg_chunks - 1) / p.seg_chunks;
+    const uint32_t lead_acc_empty0 = ptx::mapa_shared(ptx::smem_u32(&acc_empty[0]), 0);
+    uint32_t seg_count = 0;
+    for (int item = cluster_id; item < num_items; item += num_clusters) {
+      const int n_tile = item % p.n_tiles;
+      const int tile = (item / p.n_tiles) * 2 + (int)rank;
+      const bool real = tile < num_tiles;
+      const int img = tile / tiles_per_img;
+      const int t2 = tile - img * tiles_per_img;
+      const int ty = t2 / g.tiles_x, tx = t2 - ty * g.tiles_x;
+      const int y = ty * g.TH + py, x = tx * g.TW + px;
+      const bool valid = real && (y < g.H) && (x < g.W);
+
+      float sum[kMaxColChunks][16];
+      for (int s = 0; s < nseg; ++s) {
+        const int acc = seg_count & 1;
+        ptx::mbar_wait(&acc_full[acc], (seg_count >> 1) & 1);
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kAccStride + col_base);
+#pragma unroll
+        for (int j = 0; j < kMaxColChunks; ++j) {
+          if (j < my_chunks) {
+            float v[16];
+            ptx::tmem_ld16(taddr + j * 16, v);
+            if (s == 0) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) sum[j][i] = v[i];
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) sum[j][i] += v[i];
+            }
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cluster(lead_acc_empty0 + (uint32_t)(acc * sizeof(uint64_t)));
+        ++seg_count;
+      }
+      if (p.epi.mode == EPI_D2S_RDOT) {
+        float v[9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) v[t] = 0.f;
+#pragma unroll
+        for (int j = 0; j < kMaxColChunks; ++j) {
+          if (j < my_chunks) {
+            const int cg = n_tile * p.n_pad + col_base + j * 16;
+            if (cg < p.epi.n_valid) {
+              const int ij = cg / p.epi.d2s_cout, c = cg - ij * p.epi.d2s_cout;
+              rdot_accumulate16(p.epi, cg, c, sum[j], v);
+              if (c + 16 == p.epi.d2s_cout && valid) rdot_flush(p.epi, g, img, y, x, ij, v);
+            }
+          }
+        }
+      } else if (valid) {
+#pragma unroll
+        for (int j = 0; j < kMaxColChunks; ++j)
+          if (j < my_chunks) epilogue_store16(p.epi, g, n_total, img, y, x, n_tile * p.n_pad + col_base + j * 16, sum[j]);
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_2sm(tmem_base, kAccStages * kAccStride);
+  }
+}
+
+}  // namespace dcscn

@@ -20,6 +20,7 @@
 #include "common.h"
 #include "conv_aux.cuh"
 #include "conv_tc.cuh"
+#include "conv_tc_pair.cuh"
 
 using namespace dcscn;
 
@@ -81,10 +82,16 @@ struct TcLayer {
   float* d_wref = nullptr;      // fp32 HWIO for the validation kernel
   int* d_in_map = nullptr;
   int packed_kc = 0, packed_planes = 0;
+  __half* d_wpair = nullptr;    // CTA-pair layout [n_tile][tap][chunk][rank][plane][n_pad/2 x 64]
+  CUtensorMap tm_w;             // 2-D map over d_wpair (rows of 128 bytes)
+  bool has_pair = false;
 };
 
 struct TcLaunch {
-  CUtensorMap tm_hi, tm_lo;
+  CUtensorMap tm_hi, tm_lo, tm_w;
+  bool pair = false;
+  int pair_grid = 0, pair_stages = 0;
+  size_t pair_smem = 0;
   ConvTCParams p;
   ConvRefParams ref;
   int grid = 0;
@@ -145,7 +152,8 @@ struct dcscn_handle {
   int conv_impl = 0;
   int kc = 64;
   int seg_chunks = 1;
-  int cluster = 2;                   // CTAs per cluster multicasting the weight tiles
+  int cluster = 1;                   // CTAs per cluster multicasting the weight tiles (single-CTA kernel)
+  int pair = 1;                      // use the CTA-pair (tcgen05 cta_group::2) kernel when KC == 64
   int timing = 0;
   int fuse_last = 1;                 // fold the per-pixel half of R-CNN1 into the last Up-PS epilogue
   std::vector<cudaEvent_t> ev;       // timing events (launch boundaries of the last forward)
@@ -329,6 +337,42 @@ static int pack_tc_layer(dcscn_handle* h, TcLayer& t) {
         }
       }
   if (upload(&t.d_wpack, pack, h)) return 1;
+  t.has_pair = false;
+  if (KC == 64) {
+    const int half_rows = t.n_pad / 2;
+    const size_t half_elems = (size_t)half_rows * 64;
+    std::vector<__half> pp((size_t)t.n_tiles * taps * chunks * 2 * NPL * half_elems);
+    for (int nt = 0; nt < t.n_tiles; ++nt)
+      for (int tp = 0; tp < taps; ++tp)
+        for (int ch = 0; ch < chunks; ++ch)
+          for (int rk = 0; rk < 2; ++rk) {
+            __half* base = pp.data() + ((((size_t)nt * taps + tp) * chunks + ch) * 2 + rk) * NPL * half_elems;
+            for (int r = 0; r < half_rows; ++r) {
+              const int n = nt * t.n_pad + rk * half_rows + r;
+              const int sw = r & 7;
+              for (int kk = 0; kk < 64; ++kk) {
+                const int q = ch * 64 + kk;
+                float v = (q < t.cin_pad) ? wq[((size_t)tp * t.cin_pad + q) * n_total + n] : 0.f;
+                __half hi = __float2half_rn(v);
+                __half lo = __float2half_rn(v - __half2float(hi));
+                const size_t pos = (size_t)r * 64 + (size_t)((kk / 8) ^ sw) * 8 + (kk % 8);
+                base[pos] = hi;
+                if (NPL == 2) base[half_elems + pos] = lo;
+              }
+            }
+          }
+    if (upload(&t.d_wpair, pp, h)) return 1;
+    const size_t total_rows = pp.size() / 64;
+    cuuint64_t dims[2] = {64, (cuuint64_t)total_rows};
+    cuuint64_t strides[1] = {128};
+    cuuint32_t box[2] = {64, (cuuint32_t)(NPL * half_rows)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = h->encode(&t.tm_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)t.d_wpair, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (weights, layer %s) failed: %d", t.name.c_str(), (int)r);
+    t.has_pair = true;
+  }
   if (upload(&t.d_bias, t.bias_host, h)) return 1;
   if (upload(&t.d_alpha, t.alpha_host, h)) return 1;
   if (upload(&t.d_wref, t.w_host, h)) return 1;
@@ -355,6 +399,8 @@ static TcLayer make_tc(const std::string& name, int ksz, int cin, int cout_cols,
 
 static void free_tc(TcLayer& t) {
   cudaFree(t.d_wpack);
+  cudaFree(t.d_wpair);
+  t.d_wpair = nullptr;
   cudaFree(t.d_bias);
   cudaFree(t.d_alpha);
   cudaFree(t.d_wref);
@@ -558,6 +604,18 @@ static int add_tc_launch(dcscn_handle* h, Plan* pl, const TcLayer& t, const __ha
   const long long items = ((tiles + cs - 1) / cs) * t.n_tiles;    // cluster iterations
   L.grid = (int)std::min<long long>(items, h->sm_count / cs) * cs;
 
+  // CTA-pair launch shape
+  L.pair = t.has_pair && (h->sm_count % 2 == 0);
+  if (L.pair) {
+    L.tm_w = t.tm_w;
+    const size_t pstage = tc_pair_stage_bytes(planes(h), t.n_pad);
+    L.pair_stages = (int)std::min<size_t>(kMaxStages, budget / pstage);
+    L.pair_smem = L.pair_stages * pstage + 1024 + 256;
+    const long long pitems = ((tiles + 1) / 2) * t.n_tiles;
+    L.pair_grid = (int)std::min<long long>(pitems, h->sm_count / 2) * 2;
+    if (L.pair_stages < 2) L.pair = false;
+  }
+
   // validation twin
   L.ref.g = g;
   L.ref.ksz = t.ksz;
@@ -721,6 +779,32 @@ static int launch_tc_inst(dcscn_handle* h, const TcLaunch& L, cudaStream_t st) {
   return 0;
 }
 
+template <int NPL>
+static int launch_tc_pair(dcscn_handle* h, const TcLaunch& L, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(conv_tc_pair_kernel<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(L.pair_grid);
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = L.pair_smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ConvTCParams p = L.p;
+  p.cluster_size = 2;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc_pair_kernel<NPL>, L.tm_hi, L.tm_lo, L.tm_w, p, L.pair_stages));
+  return 0;
+}
+
 static int launch_tc(dcscn_handle* h, const TcLaunch& L, cudaStream_t st) {
   h->launches++;
   if (h->conv_impl == 1) {
@@ -731,6 +815,7 @@ static int launch_tc(dcscn_handle* h, const TcLaunch& L, cudaStream_t st) {
     return 0;
   }
   const int npl = planes(h);
+  if (h->pair && L.pair && h->kc == 64) return npl == 2 ? launch_tc_pair<2>(h, L, st) : launch_tc_pair<1>(h, L, st);
   if (h->kc == 64) return npl == 2 ? launch_tc_inst<64, 2>(h, L, st) : launch_tc_inst<64, 1>(h, L, st);
   return npl == 2 ? launch_tc_inst<32, 2>(h, L, st) : launch_tc_inst<32, 1>(h, L, st);
 }
@@ -987,6 +1072,8 @@ int dcscn_set_option(dcscn_handle* h, const char* key, int64_t value) {
       h->plans.clear();
       h->last_plan = nullptr;
     }
+  } else if (k == "pair") {
+    h->pair = value ? 1 : 0;
   } else if (k == "cluster") {
     if (value != 1 && value != 2 && value != 4) return fail("cluster must be 1, 2 or 4");
     h->cluster = (int)value;

@@ -60,6 +60,17 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   return d;
 }
 
+// Split form for the issue loop: the upper word is constant, the lower word is (address >> 4) | LBO.
+template <int KC>
+__device__ __forceinline__ uint32_t desc_lo_t(uint32_t saddr) {
+  return ((saddr & 0x3FFFFu) >> 4) | (1u << 16);
+}
+template <int KC>
+__device__ __forceinline__ uint64_t make_desc64_t(uint32_t lo) {
+  constexpr uint32_t hi = (uint32_t)(TcSmem<KC>::kSbo >> 4) | (1u << 14) | ((uint32_t)TcSmem<KC>::kLayout << 29);
+  return ((uint64_t)hi << 32) | (uint64_t)lo;
+}
+
 // kind::f16 instruction descriptor: fp16 x fp16 -> fp32, A and B K-major, M = 128, N = n_pad.
 __device__ __forceinline__ uint32_t make_idesc_f16(int n_pad) {
   return (1u << 4) | ((uint32_t)(n_pad >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
@@ -172,6 +183,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     } else if (warp == 1) {
       // ============================== MMA issuer ================================
       const uint32_t idesc = make_idesc_f16(p.n_pad);
+      const uint32_t smem_base_u32 = ptx::smem_u32(smem);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t seg_count = 0;
@@ -187,36 +199,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
             const int ch = c % p.chunks;
             ptx::mbar_wait(&full_bar[stage], phase);
             ptx::tc_fence_after();
-            if (lane == 0) {
-              const uint32_t a_hi = ptx::smem_u32(smem + (size_t)stage * STAGE_BYTES);
-              const uint32_t a_lo = a_hi + A_BYTES;
-              const uint32_t b_hi = a_hi + NPLANES * A_BYTES;
-              const uint32_t b_lo = b_hi + B_BYTES;
+            {
+              // Warp-uniform descriptor arithmetic; only the UMMA / commit instructions are single-lane (elect.sync),
+              // which keeps the issue loop on the uniform datapath (a divergent `if (lane == 0)` costs ~40 SASS
+              // instructions per UMMA and made the kernel issue-bound).
+              const uint32_t st_addr = smem_base_u32 + (uint32_t)stage * (uint32_t)STAGE_BYTES;
+              const uint32_t la_hi = desc_lo_t<KC>(st_addr);
+              const uint32_t la_lo = desc_lo_t<KC>(st_addr + A_BYTES);
+              const uint32_t lb_hi = desc_lo_t<KC>(st_addr + NPLANES * A_BYTES);
+              const uint32_t lb_lo = desc_lo_t<KC>(st_addr + NPLANES * A_BYTES + B_BYTES);
               int ksteps = (p.cin_pad - ch * KC);
               ksteps = (ksteps > KC ? KC : ksteps) >> 4;
-              for (int ks = 0; ks < ksteps; ++ks) {
-                const uint32_t koff = ks * 32;  // 16 fp16 along K inside the swizzled row
-                const uint64_t da_hi = make_smem_desc<KC>(a_hi + koff);
-                const uint64_t db_hi = make_smem_desc<KC>(b_hi + koff);
-                if (NPLANES == 2) {
-                  // small correction terms first, the dominant hi*hi product last
-                  const uint64_t da_lo = make_smem_desc<KC>(a_lo + koff);
-                  const uint64_t db_lo = make_smem_desc<KC>(b_lo + koff);
-                  ptx::mma_f16_ss(tmem_d, da_lo, db_hi, idesc, accumulate);
-                  ptx::mma_f16_ss(tmem_d, da_hi, db_lo, idesc, 1);
+              if (ptx::elect_one()) {
+#pragma unroll 1
+                for (int ks = 0; ks < ksteps; ++ks) {
+                  const uint32_t kadd = (uint32_t)ks * 2u;  // 32 bytes (16 fp16 along K) in 16-byte descriptor units
+                  if (NPLANES == 2) {
+                    // small correction terms first, the dominant hi*hi product last
+                    ptx::mma_f16_ss(tmem_d, make_desc64_t<KC>(la_lo + kadd), make_desc64_t<KC>(lb_hi + kadd), idesc, accumulate);
+                    ptx::mma_f16_ss(tmem_d, make_desc64_t<KC>(la_hi + kadd), make_desc64_t<KC>(lb_lo + kadd), idesc, 1);
+                    accumulate = 1;
+                  }
+                  ptx::mma_f16_ss(tmem_d, make_desc64_t<KC>(la_hi + kadd), make_desc64_t<KC>(lb_hi + kadd), idesc, accumulate);
                   accumulate = 1;
                 }
-                ptx::mma_f16_ss(tmem_d, da_hi, db_hi, idesc, accumulate);
-                accumulate = 1;
-              }
-              // free this smem stage (in every CTA of the cluster: peers multicast into it) once the MMAs have read it
+                // free this smem stage once the MMAs have read it
               if (cs == 1) ptx::mma_commit(&empty_bar[stage]);
               else ptx::mma_commit_multicast(&empty_bar[stage], cta_mask);
+              }
+              accumulate = 1;
             }
             __syncwarp();
             if (++stage == num_stages) { stage = 0; phase ^= 1; }
           }
-          if (lane == 0) ptx::mma_commit(&acc_full[acc]);  // segment complete -> epilogue promotes it
+          if (ptx::elect_one()) ptx::mma_commit(&acc_full[acc]);  // segment complete -> epilogue promotes it
           __syncwarp();
           ++seg_count;
         }

@@ -171,6 +171,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
     } else if (warp == 1 && leader) {
       // ============================== MMA issuer (leader CTA only) ================================
       const uint32_t idesc = (1u << 4) | ((uint32_t)(p.n_pad >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      const uint32_t smem_base_u32 = ptx::smem_u32(smem);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t seg_count = 0;
@@ -186,33 +187,39 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
             const int ch = c % p.chunks;
             ptx::mbar_wait(&full_bar[stage], phase);
             ptx::tc_fence_after();
-            if (lane == 0) {
-              const uint32_t a_hi = ptx::smem_u32(smem + (size_t)stage * STAGE_BYTES);
-              const uint32_t a_lo = a_hi + A_BYTES;
-              const uint32_t b_hi = a_hi + NPLANES * A_BYTES;
-              const uint32_t b_lo = b_hi + BH_BYTES;
+            {
+              // Warp-uniform descriptor arithmetic; only the UMMA / commit instructions are single-lane (elect.sync),
+              // which keeps the issue loop on the uniform datapath (a divergent `if (lane == 0)` costs ~40 SASS
+              // instructions per UMMA and made the kernel issue-bound).
+              const uint32_t st_addr = smem_base_u32 + (uint32_t)stage * (uint32_t)STAGE_BYTES;
+              const uint32_t la_hi = desc_lo_t<KC>(st_addr);
+              const uint32_t la_lo = desc_lo_t<KC>(st_addr + A_BYTES);
+              const uint32_t lb_hi = desc_lo_t<KC>(st_addr + NPLANES * A_BYTES);
+              const uint32_t lb_lo = desc_lo_t<KC>(st_addr + NPLANES * A_BYTES + BH_BYTES);
               int ksteps = (p.cin_pad - ch * KC);
               ksteps = (ksteps > KC ? KC : ksteps) >> 4;
-              for (int ks = 0; ks < ksteps; ++ks) {
-                const uint32_t koff = ks * 32;
-                const uint64_t da_hi = make_smem_desc<KC>(a_hi + koff);
-                const uint64_t db_hi = make_smem_desc<KC>(b_hi + koff);
-                if (NPLANES == 2) {
-                  const uint64_t da_lo = make_smem_desc<KC>(a_lo + koff);
-                  const uint64_t db_lo = make_smem_desc<KC>(b_lo + koff);
-                  ptx::mma_f16_ss_2sm(tmem_d, da_lo, db_hi, idesc, accumulate);
-                  ptx::mma_f16_ss_2sm(tmem_d, da_hi, db_lo, idesc, 1);
+              if (ptx::elect_one()) {
+#pragma unroll 1
+                for (int ks = 0; ks < ksteps; ++ks) {
+                  const uint32_t kadd = (uint32_t)ks * 2u;  // 32 bytes (16 fp16 along K) in 16-byte descriptor units
+                  if (NPLANES == 2) {
+                    // small correction terms first, the dominant hi*hi product last
+                    ptx::mma_f16_ss_2sm(tmem_d, make_desc64_t<KC>(la_lo + kadd), make_desc64_t<KC>(lb_hi + kadd), idesc, accumulate);
+                    ptx::mma_f16_ss_2sm(tmem_d, make_desc64_t<KC>(la_hi + kadd), make_desc64_t<KC>(lb_lo + kadd), idesc, 1);
+                    accumulate = 1;
+                  }
+                  ptx::mma_f16_ss_2sm(tmem_d, make_desc64_t<KC>(la_hi + kadd), make_desc64_t<KC>(lb_hi + kadd), idesc, accumulate);
                   accumulate = 1;
                 }
-                ptx::mma_f16_ss_2sm(tmem_d, da_hi, db_hi, idesc, accumulate);
-                accumulate = 1;
-              }
+                // free this smem stage once the MMAs have read it
               ptx::mma_commit_2sm(&empty_bar[stage], 3);   // release this stage in both CTAs
+              }
+              accumulate = 1;
             }
             __syncwarp();
             if (++stage == num_stages) { stage = 0; phase ^= 1; }
           }
-          if (lane == 0) ptx::mma_commit_2sm(&acc_full[acc], 3);  // segment complete in both CTAs' TMEM
+          if (ptx::elect_one()) ptx::mma_commit_2sm(&acc_full[acc], 3);  // segment complete in both CTAs' TMEM
           __syncwarp();
           ++seg_count;
         }

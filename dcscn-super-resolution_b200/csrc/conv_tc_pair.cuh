@@ -183,15 +183,19 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
           const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kAccStride);
           uint32_t accumulate = 0;
           const int c1 = (c0 + p.seg_chunks < total_chunks) ? c0 + p.seg_chunks : total_chunks;
+          // Pass A: as the stages of this segment land, issue the small correction products (a_lo*w_hi, a_hi*w_lo).
+          // Pass B: the dominant a_hi*w_hi products, releasing each stage.  The accumulator only becomes large in
+          // pass B, so only those UMMAs contribute truncation error: 3x fewer "effective" steps per segment.
+          // Warp-uniform descriptor arithmetic; only the UMMA / commit instructions are single-lane (elect.sync), which
+          // keeps the issue loop on the uniform datapath.
+          int st = stage;
+          uint32_t ph = phase;
           for (int c = c0; c < c1; ++c) {
             const int ch = c % p.chunks;
-            ptx::mbar_wait(&full_bar[stage], phase);
+            ptx::mbar_wait(&full_bar[st], ph);
             ptx::tc_fence_after();
-            {
-              // Warp-uniform descriptor arithmetic; only the UMMA / commit instructions are single-lane (elect.sync),
-              // which keeps the issue loop on the uniform datapath (a divergent `if (lane == 0)` costs ~40 SASS
-              // instructions per UMMA and made the kernel issue-bound).
-              const uint32_t st_addr = smem_base_u32 + (uint32_t)stage * (uint32_t)STAGE_BYTES;
+            if (NPLANES == 2) {
+              const uint32_t st_addr = smem_base_u32 + (uint32_t)st * (uint32_t)STAGE_BYTES;
               const uint32_t la_hi = desc_lo_t<KC>(st_addr);
               const uint32_t la_lo = desc_lo_t<KC>(st_addr + A_BYTES);
               const uint32_t lb_hi = desc_lo_t<KC>(st_addr + NPLANES * A_BYTES);
@@ -202,23 +206,39 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
 #pragma unroll 1
                 for (int ks = 0; ks < ksteps; ++ks) {
                   const uint32_t kadd = (uint32_t)ks * 2u;  // 32 bytes (16 fp16 along K) in 16-byte descriptor units
-                  if (NPLANES == 2) {
-                    // small correction terms first, the dominant hi*hi product last
-                    ptx::mma_f16_ss_2sm(tmem_d, make_desc64_t<KC>(la_lo + kadd), make_desc64_t<KC>(lb_hi + kadd), idesc, accumulate);
-                    ptx::mma_f16_ss_2sm(tmem_d, make_desc64_t<KC>(la_hi + kadd), make_desc64_t<KC>(lb_lo + kadd), idesc, 1);
-                    accumulate = 1;
-                  }
-                  ptx::mma_f16_ss_2sm(tmem_d, make_desc64_t<KC>(la_hi + kadd), make_desc64_t<KC>(lb_hi + kadd), idesc, accumulate);
+                  ptx::mma_f16_ss_2sm(tmem_d, make_desc64_t<KC>(la_lo + kadd), make_desc64_t<KC>(lb_hi + kadd), idesc, accumulate);
+                  ptx::mma_f16_ss_2sm(tmem_d, make_desc64_t<KC>(la_hi + kadd), make_desc64_t<KC>(lb_lo + kadd), idesc, 1);
                   accumulate = 1;
                 }
-                // free this smem stage once the MMAs have read it
-              ptx::mma_commit_2sm(&empty_bar[stage], 3);   // release this stage in both CTAs
               }
               accumulate = 1;
+              __syncwarp();
             }
-            __syncwarp();
-            if (++stage == num_stages) { stage = 0; phase ^= 1; }
+            if (++st == num_stages) { st = 0; ph ^= 1; }
           }
+          st = stage;
+          for (int c = c0; c < c1; ++c) {
+            const int ch = c % p.chunks;
+            const uint32_t st_addr = smem_base_u32 + (uint32_t)st * (uint32_t)STAGE_BYTES;
+            const uint32_t la_hi = desc_lo_t<KC>(st_addr);
+            const uint32_t lb_hi = desc_lo_t<KC>(st_addr + NPLANES * A_BYTES);
+            int ksteps = (p.cin_pad - ch * KC);
+            ksteps = (ksteps > KC ? KC : ksteps) >> 4;
+            if (ptx::elect_one()) {
+#pragma unroll 1
+              for (int ks = 0; ks < ksteps; ++ks) {
+                const uint32_t kadd = (uint32_t)ks * 2u;
+                ptx::mma_f16_ss_2sm(tmem_d, make_desc64_t<KC>(la_hi + kadd), make_desc64_t<KC>(lb_hi + kadd), idesc, accumulate);
+                accumulate = 1;
+              }
+              ptx::mma_commit_2sm(&empty_bar[st], 3);  // frees this smem stage once the UMMAs have read it
+            }
+            accumulate = 1;
+            __syncwarp();
+            if (++st == num_stages) st = 0;
+          }
+          stage = st;
+          phase = ph;
           if (ptx::elect_one()) ptx::mma_commit_2sm(&acc_full[acc], 3);  // segment complete in both CTAs' TMEM
           __syncwarp();
           ++seg_count;
@@ -241,6 +261,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
     const int col_base = first_chunk * 16;
     const int nseg = (total_chunks + p.seg_chunks - 1) / p.seg_chunks;
     const uint32_t lead_acc_empty0 = ptx::mapa_shared(ptx::smem_u32(&acc_empty[0]), 0);
+    const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)col_base;
     uint32_t seg_count = 0;
     for (int item = cluster_id; item < num_items; item += num_clusters) {
       const int n_tile = item % p.n_tiles;
@@ -253,22 +274,30 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
       const bool valid = real && (y < g.H) && (x < g.W);
 
       float sum[kMaxColChunks][16];
+#pragma unroll
+      for (int j = 0; j < kMaxColChunks; ++j)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) sum[j][i] = 0.f;
       for (int s = 0; s < nseg; ++s) {
         const int acc = seg_count & 1;
         ptx::mbar_wait(&acc_full[acc], (seg_count >> 1) & 1);
         ptx::tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kAccStride + col_base);
+        const uint32_t taddr = taddr0 + (uint32_t)(acc * kAccStride);
+        // fp32 round-to-nearest promotion of the segment: wide TMEM loads (64 / 32 columns per instruction); columns
+        // past this thread's share may be read (they stay inside the accumulator stage) but are never stored.
 #pragma unroll
-        for (int j = 0; j < kMaxColChunks; ++j) {
+        for (int j = 0; j < kMaxColChunks; j += 4) {
           if (j < my_chunks) {
-            float v[16];
-            ptx::tmem_ld16(taddr + j * 16, v);
-            if (s == 0) {
+            if (my_chunks - j > 2) {
+              float v[64];
+              ptx::tmem_ld64(taddr + j * 16, v);
 #pragma unroll
-              for (int i = 0; i < 16; ++i) sum[j][i] = v[i];
+              for (int i = 0; i < 64; ++i) sum[j + (i >> 4)][i & 15] += v[i];
             } else {
+              float v[32];
+              ptx::tmem_ld32(taddr + j * 16, v);
 #pragma unroll
-              for (int i = 0; i < 16; ++i) sum[j][i] += v[i];
+              for (int i = 0; i < 32; ++i) sum[j + (i >> 4)][i & 15] += v[i];
             }
           }
         }

@@ -90,7 +90,7 @@ struct TcLayer {
 struct TcLaunch {
   CUtensorMap tm_hi, tm_lo, tm_w;
   bool pair = false;
-  int pair_grid = 0, pair_stages = 0;
+  int pair_grid = 0, pair_stages = 0, pair_seg = 1;
   size_t pair_smem = 0;
   ConvTCParams p;
   ConvRefParams ref;
@@ -151,7 +151,7 @@ struct dcscn_handle {
 
   int conv_impl = 0;
   int kc = 64;
-  int seg_chunks = 1;
+  int seg_chunks = 0;                // pipeline stages per fp32-promotion segment; 0 = automatic
   int cluster = 1;                   // CTAs per cluster multicasting the weight tiles (single-CTA kernel)
   int pair = 1;                      // use the CTA-pair (tcgen05 cta_group::2) kernel when KC == 64
   int timing = 0;
@@ -583,7 +583,7 @@ static int add_tc_launch(dcscn_handle* h, Plan* pl, const TcLayer& t, const __ha
   L.p.chunks = (t.cin_pad + h->kc - 1) / h->kc;
   L.p.n_tiles = t.n_tiles;
   L.p.n_pad = t.n_pad;
-  L.p.seg_chunks = h->seg_chunks;
+  L.p.seg_chunks = h->seg_chunks;  // finalised per kernel variant below (needs the stage count)
   int cs = h->cluster;
   while (cs > 1 && (t.n_pad % cs != 0 || h->sm_count % cs != 0)) cs >>= 1;
   L.p.cluster_size = cs;
@@ -599,6 +599,10 @@ static int add_tc_launch(dcscn_handle* h, Plan* pl, const TcLayer& t, const __ha
   int stages = (int)std::min<size_t>(kMaxStages, budget / stage);
   if (stages < 2) return fail("layer %s: pipeline stage of %zu bytes does not fit twice in shared memory", t.name.c_str(), stage);
   L.stages = stages;
+  {
+    int seg = h->seg_chunks > 0 ? h->seg_chunks : (t.n_pad >= 112 ? 2 : 3);
+    L.p.seg_chunks = std::max(1, std::min(seg, stages - 1));   // a segment's stages stay resident until its 2nd pass
+  }
   L.smem = stages * stage + 1024 + 256;
   const long long tiles = (long long)n * g.tiles_x * g.tiles_y;
   const long long items = ((tiles + cs - 1) / cs) * t.n_tiles;    // cluster iterations
@@ -614,6 +618,8 @@ static int add_tc_launch(dcscn_handle* h, Plan* pl, const TcLayer& t, const __ha
     const long long pitems = ((tiles + 1) / 2) * t.n_tiles;
     L.pair_grid = (int)std::min<long long>(pitems, h->sm_count / 2) * 2;
     if (L.pair_stages < 2) L.pair = false;
+    int seg = h->seg_chunks > 0 ? h->seg_chunks : (t.n_pad >= 112 ? 2 : 3);
+    L.pair_seg = std::max(1, std::min(seg, L.pair_stages - 1));
   }
 
   // validation twin
@@ -801,6 +807,7 @@ static int launch_tc_pair(dcscn_handle* h, const TcLaunch& L, cudaStream_t st) {
   cfg.numAttrs = 1;
   ConvTCParams p = L.p;
   p.cluster_size = 2;
+  p.seg_chunks = L.pair_seg;
   CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc_pair_kernel<NPL>, L.tm_hi, L.tm_lo, L.tm_w, p, L.pair_stages));
   return 0;
 }
@@ -1084,7 +1091,7 @@ int dcscn_set_option(dcscn_handle* h, const char* key, int64_t value) {
   } else if (k == "timing") {
     h->timing = value ? 1 : 0;
   } else if (k == "seg_chunks") {
-    if (value < 1 || value > 4096) return fail("seg_chunks must be >= 1");
+    if (value < 0 || value > 4096) return fail("seg_chunks must be >= 0 (0 = automatic)");
     h->seg_chunks = (int)value;
     h->plans.clear();
     h->last_plan = nullptr;

@@ -19,7 +19,7 @@ from helper import engine as E  # noqa: E402
 from helper import tf_bundle  # noqa: E402
 
 
-def run_case(name, cfg_kwargs, weights, n, h, w, seed=0, precision=E.PRECISION_F16X3, modes=((1, 64, 1), (0, 64, 1), (0, 32, 1), (0, 64, 4), (0, 64, 4000))):
+def run_case(name, cfg_kwargs, weights, n, h, w, seed=0, precision=E.PRECISION_F16X3, modes=((1, 64, 1), (0, 64, 1), (0, 32, 1), (0, 64, 0), (0, 64, 3), (0, 64, 4000))):
     ocfg = O.OracleConfig(**cfg_kwargs)
     if weights is None:
         weights = O.he_init_weights(ocfg, seed=seed)

@@ -24,6 +24,28 @@ from helper import loader, tf_bundle, utilty as util
 BICUBIC_METHOD_STRING = "bicubic"
 
 
+def _dist_rank_world():
+    """(rank, world_size) of the torch.distributed job this process belongs to, (0, 1) outside one."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+    except ImportError:
+        pass
+    return 0, 1
+
+
+def _all_reduce_sum(array):
+    """Sum a float64 numpy array over all ranks (one NCCL all-reduce when the backend is nccl, gloo on CPU)."""
+    import torch
+    import torch.distributed as dist
+    t = torch.from_numpy(np.ascontiguousarray(array))
+    if dist.get_backend() == "nccl":
+        t = t.cuda()
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.cpu().numpy()
+
+
 class SuperResolution:
     def __init__(self, flags, model_name=""):
         # ---- TensorflowGraph.__init__ (tf_graph.py:19-63) ----
@@ -434,12 +456,18 @@ class SuperResolution:
             bicubic_input_image = np.multiply(bicubic_input_image, self.max_value / 255.0)
 
         if self.self_ensemble > 1:
+            # The flips are independent: rank r of a torch.distributed job computes flips r, r + world, ... and the
+            # inverse-flipped partial sums meet in ONE all-reduce (NCCL over NVLink on GPUs); single process = the
+            # reference's serial loop.  float64 accumulation like the reference's np.zeros default (DCSCN.py:560).
+            rank, world = _dist_rank_world()
             output = np.zeros([self.scale * h, self.scale * w, 1])
-            for i in range(self.self_ensemble):
+            for i in range(rank, self.self_ensemble, world):
                 image = util.flip(input_image, i)
                 bicubic_image = util.flip(bicubic_input_image, i)
                 y = self._run(image, bicubic_image)
                 output += util.flip(y[0], i, invert=True)
+            if world > 1:
+                output = _all_reduce_sum(output)
             output /= self.self_ensemble
         else:
             output = self._run(input_image, bicubic_input_image)[0]

@@ -21,6 +21,7 @@
 #include "conv_aux.cuh"
 #include "conv_tc.cuh"
 #include "conv_tc_pair.cuh"
+#include "conv_tc_halo.cuh"
 
 using namespace dcscn;
 
@@ -91,6 +92,11 @@ struct TcLaunch {
   CUtensorMap tm_hi, tm_lo, tm_w;
   bool pair = false;
   int pair_grid = 0, pair_stages = 0, pair_seg = 1;
+  bool halo = false;             // 3x3 layers: halo-reuse CTA-pair kernel
+  CUtensorMap th_hi, th_lo;      // A maps with box {64, 8, 18, 1}
+  ConvGeom hg;
+  int halo_grid = 0, halo_na = 0, halo_nb = 0, halo_seg = 1;
+  size_t halo_smem = 0;
   size_t pair_smem = 0;
   ConvTCParams p;
   ConvRefParams ref;
@@ -154,6 +160,7 @@ struct dcscn_handle {
   int seg_chunks = 0;                // pipeline stages per fp32-promotion segment; 0 = automatic
   int cluster = 1;                   // CTAs per cluster multicasting the weight tiles (single-CTA kernel)
   int pair = 1;                      // use the CTA-pair (tcgen05 cta_group::2) kernel when KC == 64
+  int halo = 1;                      // 3x3 layers: halo-reuse variant of the CTA-pair kernel
   int timing = 0;
   int fuse_last = 1;                 // fold the per-pixel half of R-CNN1 into the last Up-PS epilogue
   std::vector<cudaEvent_t> ev;       // timing events (launch boundaries of the last forward)
@@ -548,8 +555,8 @@ static void choose_patch(int H, int W, int* TH, int* TW) {
 }
 
 static int encode_map(dcscn_handle* h, CUtensorMap* tm, const __half* base, int cin_pad, int pitch, int n, int H,
-                      int W, int TH, int TW) {
-  const int KC = h->kc;
+                      int W, int TH, int TW, int kc_override = 0) {
+  const int KC = kc_override ? kc_override : h->kc;
   cuuint64_t dims[4] = {(cuuint64_t)cin_pad, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
   cuuint64_t strides[3] = {(cuuint64_t)pitch * 2, (cuuint64_t)W * pitch * 2, (cuuint64_t)H * W * pitch * 2};
   cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)TW, (cuuint32_t)TH, 1};
@@ -620,6 +627,42 @@ static int add_tc_launch(dcscn_handle* h, Plan* pl, const TcLayer& t, const __ha
     if (L.pair_stages < 2) L.pair = false;
     int seg = h->seg_chunks > 0 ? h->seg_chunks : (t.n_pad >= 112 ? 2 : 3);
     L.pair_seg = std::max(1, std::min(seg, L.pair_stages - 1));
+  }
+
+  // halo-reuse launch shape (3x3 layers, CTA pair, KC = 64)
+  L.halo = L.pair && t.ksz == 3;
+  if (L.halo) {
+    ConvGeom hg{n, H, W, (W + kHaloTW - 1) / kHaloTW, (H + kHaloTH - 1) / kHaloTH, kHaloTW, kHaloTH};
+    L.hg = hg;
+    if (encode_map(h, &L.th_hi, src_hi, t.cin_pad, src_pitch, n, H, W, kHaloTH + 2, kHaloTW, 64)) return 1;
+    if (planes(h) == 2) {
+      if (encode_map(h, &L.th_lo, src_lo, t.cin_pad, src_pitch, n, H, W, kHaloTH + 2, kHaloTW, 64)) return 1;
+    } else {
+      L.th_lo = L.th_hi;
+    }
+    const size_t a_slot = tc_halo_a_slot_bytes(planes(h)), b_stage = tc_halo_b_stage_bytes(planes(h), t.n_pad);
+    int seg = h->seg_chunks > 0 ? h->seg_chunks : (t.n_pad >= 112 ? 1 : 2);
+    for (;; --seg) {
+      const int na = seg + 2;
+      const long long left = (long long)budget - (long long)na * (long long)a_slot;
+      const int nb = left > 0 ? (int)std::min<long long>(kMaxStages, left / (long long)b_stage) : 0;
+      if (nb >= 3 * seg + 1 && na <= kMaxStages) {
+        L.halo_seg = seg;
+        L.halo_na = na;
+        L.halo_nb = nb;
+        break;
+      }
+      if (seg == 1) {
+        L.halo = false;
+        break;
+      }
+    }
+    if (L.halo) {
+      L.halo_smem = L.halo_na * a_slot + L.halo_nb * b_stage + 1024 + 512;
+      const long long htiles = (long long)n * hg.tiles_x * hg.tiles_y;
+      const long long hitems = ((htiles + 1) / 2) * t.n_tiles;
+      L.halo_grid = (int)std::min<long long>(hitems, h->sm_count / 2) * 2;
+    }
   }
 
   // validation twin
@@ -812,6 +855,34 @@ static int launch_tc_pair(dcscn_handle* h, const TcLaunch& L, cudaStream_t st) {
   return 0;
 }
 
+template <int NPL>
+static int launch_tc_halo(dcscn_handle* h, const TcLaunch& L, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(conv_tc_halo_kernel<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(L.halo_grid);
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = L.halo_smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ConvTCParams p = L.p;
+  p.g = L.hg;
+  p.cluster_size = 2;
+  p.seg_chunks = L.halo_seg;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc_halo_kernel<NPL>, L.th_hi, L.th_lo, L.tm_w, p, L.halo_na, L.halo_nb));
+  return 0;
+}
+
 static int launch_tc(dcscn_handle* h, const TcLaunch& L, cudaStream_t st) {
   h->launches++;
   if (h->conv_impl == 1) {
@@ -822,6 +893,7 @@ static int launch_tc(dcscn_handle* h, const TcLaunch& L, cudaStream_t st) {
     return 0;
   }
   const int npl = planes(h);
+  if (h->pair && h->halo && L.halo && h->kc == 64) return npl == 2 ? launch_tc_halo<2>(h, L, st) : launch_tc_halo<1>(h, L, st);
   if (h->pair && L.pair && h->kc == 64) return npl == 2 ? launch_tc_pair<2>(h, L, st) : launch_tc_pair<1>(h, L, st);
   if (h->kc == 64) return npl == 2 ? launch_tc_inst<64, 2>(h, L, st) : launch_tc_inst<64, 1>(h, L, st);
   return npl == 2 ? launch_tc_inst<32, 2>(h, L, st) : launch_tc_inst<32, 1>(h, L, st);
@@ -1079,6 +1151,8 @@ int dcscn_set_option(dcscn_handle* h, const char* key, int64_t value) {
       h->plans.clear();
       h->last_plan = nullptr;
     }
+  } else if (k == "halo") {
+    h->halo = value ? 1 : 0;
   } else if (k == "pair") {
     h->pair = value ? 1 : 0;
   } else if (k == "cluster") {

@@ -22,43 +22,54 @@ struct ConvFirstParams {
 };
 
 __global__ void __launch_bounds__(256) conv_first_kernel(const ConvFirstParams p) {
-  // weights as float4 [tap][q][group]: consecutive lanes (= consecutive channel groups) read consecutive 16 bytes
-  extern __shared__ float4 s_w4[];
+  // One lane = one pixel: its k*k input taps are loaded once and reused for every 16-channel group; the weights of a
+  // group are warp-uniform, so the float4 shared-memory reads are broadcasts (one wavefront each).
+  extern __shared__ float4 s_w4[];  // [tap][group][4]
   const int taps = p.ksz * p.ksz;
   const int groups = p.n_pad >> 4;
-  for (int i = threadIdx.x; i < taps * 4 * groups; i += blockDim.x) {
-    const int grp = i % groups, q = (i / groups) & 3, t = i / (4 * groups);
+  for (int i = threadIdx.x; i < taps * groups * 4; i += blockDim.x) {
+    const int q = i & 3, grp = (i >> 2) % groups, t = (i >> 2) / groups;
     const float* src = p.w + t * p.n_pad + grp * 16 + q * 4;
     s_w4[i] = make_float4(src[0], src[1], src[2], src[3]);
   }
   __syncthreads();
   const int half = p.ksz >> 1;
-  const long long total = (long long)p.g.n_img * p.g.H * p.g.W * groups;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int grp = (int)(idx % groups);
-    const long long pix = idx / groups;
+  const long long total = (long long)p.g.n_img * p.g.H * p.g.W;
+  for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < total;
+       pix += (long long)gridDim.x * blockDim.x) {
     const int x = (int)(pix % p.g.W);
     const int y = (int)((pix / p.g.W) % p.g.H);
     const int img = (int)(pix / ((long long)p.g.W * p.g.H));
-    float acc[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
     const float* xi = p.x + (size_t)img * p.g.H * p.g.W;
-    for (int t = 0; t < taps; ++t) {
-      const int yy = y + t / p.ksz - half, xx = x + t % p.ksz - half;
-      if (yy < 0 || yy >= p.g.H || xx < 0 || xx >= p.g.W) continue;
-      const float v = __ldg(xi + (size_t)yy * p.g.W + xx);
+    float in[25];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 w = s_w4[(t * 4 + q) * groups + grp];
-        acc[4 * q + 0] = fmaf(v, w.x, acc[4 * q + 0]);
-        acc[4 * q + 1] = fmaf(v, w.y, acc[4 * q + 1]);
-        acc[4 * q + 2] = fmaf(v, w.z, acc[4 * q + 2]);
-        acc[4 * q + 3] = fmaf(v, w.w, acc[4 * q + 3]);
+    for (int t = 0; t < 25; ++t) {
+      if (t < taps) {
+        const int yy = y + t / p.ksz - half, xx = x + t % p.ksz - half;
+        in[t] = (yy >= 0 && yy < p.g.H && xx >= 0 && xx < p.g.W) ? __ldg(xi + (size_t)yy * p.g.W + xx) : 0.f;
       }
     }
-    epilogue_store16(p.epi, p.g, p.n_pad, img, y, x, grp * 16, acc);
+    for (int grp = 0; grp < groups; ++grp) {
+      float acc[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+#pragma unroll
+      for (int t = 0; t < 25; ++t) {
+        if (t < taps) {
+          const float v = in[t];
+          const float4* w4 = s_w4 + (t * groups + grp) * 4;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 w = w4[q];
+            acc[4 * q + 0] = fmaf(v, w.x, acc[4 * q + 0]);
+            acc[4 * q + 1] = fmaf(v, w.y, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(v, w.z, acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(v, w.w, acc[4 * q + 3]);
+          }
+        }
+      }
+      epilogue_store16(p.epi, p.g, p.n_pad, img, y, x, grp * 16, acc);
+    }
   }
 }
 

@@ -35,6 +35,7 @@ constexpr int kEpiWarp0 = 4;                       // warpgroup 0 = {TMA, MMA, 2
 constexpr int kTcThreads = (kEpiWarp0 + kEpiWarps) * 32;
 constexpr int kRegsIssue = 40, kRegsEpilogue = 232;  // setmaxnreg budgets (128*56 + 256*224 <= 64K)
 constexpr int kMaxStages = 8;
+constexpr int kRdotSmemBytes = 9 * 128 * 4;         // fused R-CNN1 filter taps (d2s_cout <= 128) staged in shared memory
 constexpr int kAccStages = 2;
 constexpr int kAccStride = 256;  // TMEM columns per accumulator stage
 constexpr int kColSplit = kEpiWarps / 4;           // column groups
@@ -95,6 +96,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
   uint64_t* acc_full = empty_bar + kMaxStages;
   uint64_t* acc_empty = acc_full + kAccStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kAccStages);
+  float* s_rdot = reinterpret_cast<float*>(tmem_slot + 4);   // 16-byte aligned (barriers start 1024-aligned)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -118,6 +120,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     ptx::tmem_alloc(tmem_slot, kAccStages * kAccStride);
     ptx::tmem_relinquish();
   }
+  if (p.epi.mode == EPI_D2S_RDOT)
+    for (int i = threadIdx.x; i < p.epi.rdot_taps * p.epi.d2s_cout; i += blockDim.x) s_rdot[i] = p.epi.rdot_w[i];
   ptx::tc_fence_before();
   __syncthreads();
   if (cs > 1) ptx::cluster_sync();               // peers' barriers are initialised before anything targets them
@@ -328,7 +332,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
             const int cg = n_tile * p.n_pad + col_base + j * 16;
             if (cg < p.epi.n_valid) {
               const int ij = cg / p.epi.d2s_cout, c = cg - ij * p.epi.d2s_cout;
-              rdot_accumulate16(p.epi, cg, c, sum[j], v);
+              rdot_accumulate16(p.epi, s_rdot, cg, c, sum[j], v);
               if (c + 16 == p.epi.d2s_cout && valid) rdot_flush(p.epi, g, img, y, x, ij, v);
             }
           }

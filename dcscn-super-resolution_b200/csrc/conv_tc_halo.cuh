@@ -44,6 +44,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
   uint64_t* acc_full = b_empty + kMaxStages;
   uint64_t* acc_empty = acc_full + kAccStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kAccStages);
+  float* s_rdot = reinterpret_cast<float*>(tmem_slot + 4);   // 16-byte aligned (barriers start 1024-aligned)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -70,6 +71,8 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
     ptx::tmem_alloc_2sm(tmem_slot, kAccStages * kAccStride);
     ptx::tmem_relinquish_2sm();
   }
+  if (p.epi.mode == EPI_D2S_RDOT)
+    for (int i = threadIdx.x; i < p.epi.rdot_taps * p.epi.d2s_cout; i += blockDim.x) s_rdot[i] = p.epi.rdot_w[i];
   ptx::tc_fence_before();
   __syncthreads();
   ptx::cluster_sync();
@@ -286,7 +289,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
             const int cg = n_tile * p.n_pad + col_base + j * 16;
             if (cg < p.epi.n_valid) {
               const int ij = cg / p.epi.d2s_cout, c = cg - ij * p.epi.d2s_cout;
-              rdot_accumulate16(p.epi, cg, c, sum[j], v);
+              rdot_accumulate16(p.epi, s_rdot, cg, c, sum[j], v);
               if (c + 16 == p.epi.d2s_cout && valid) rdot_flush(p.epi, g, img, y, x, ij, v);
             }
           }

@@ -602,7 +602,7 @@ static int add_tc_launch(dcscn_handle* h, Plan* pl, const TcLayer& t, const __ha
   L.p.epi.n_valid = t.n_valid;
 
   const size_t stage = tc_stage_bytes(h->kc, planes(h), t.n_pad);
-  const size_t budget = 227 * 1024 - 2048;
+  const size_t budget = 227 * 1024 - 2048 - kRdotSmemBytes;
   int stages = (int)std::min<size_t>(kMaxStages, budget / stage);
   if (stages < 2) return fail("layer %s: pipeline stage of %zu bytes does not fit twice in shared memory", t.name.c_str(), stage);
   L.stages = stages;
@@ -610,7 +610,7 @@ static int add_tc_launch(dcscn_handle* h, Plan* pl, const TcLayer& t, const __ha
     int seg = h->seg_chunks > 0 ? h->seg_chunks : (t.n_pad >= 112 ? 2 : 3);
     L.p.seg_chunks = std::max(1, std::min(seg, stages - 1));   // a segment's stages stay resident until its 2nd pass
   }
-  L.smem = stages * stage + 1024 + 256;
+  L.smem = stages * stage + 1024 + 256 + kRdotSmemBytes;
   const long long tiles = (long long)n * g.tiles_x * g.tiles_y;
   const long long items = ((tiles + cs - 1) / cs) * t.n_tiles;    // cluster iterations
   L.grid = (int)std::min<long long>(items, h->sm_count / cs) * cs;
@@ -621,7 +621,7 @@ static int add_tc_launch(dcscn_handle* h, Plan* pl, const TcLayer& t, const __ha
     L.tm_w = t.tm_w;
     const size_t pstage = tc_pair_stage_bytes(planes(h), t.n_pad);
     L.pair_stages = (int)std::min<size_t>(kMaxStages, budget / pstage);
-    L.pair_smem = L.pair_stages * pstage + 1024 + 256;
+    L.pair_smem = L.pair_stages * pstage + 1024 + 256 + kRdotSmemBytes;
     const long long pitems = ((tiles + 1) / 2) * t.n_tiles;
     L.pair_grid = (int)std::min<long long>(pitems, h->sm_count / 2) * 2;
     if (L.pair_stages < 2) L.pair = false;
@@ -658,7 +658,7 @@ static int add_tc_launch(dcscn_handle* h, Plan* pl, const TcLayer& t, const __ha
       }
     }
     if (L.halo) {
-      L.halo_smem = L.halo_na * a_slot + L.halo_nb * b_stage + 1024 + 512;
+      L.halo_smem = L.halo_na * a_slot + L.halo_nb * b_stage + 1024 + 512 + kRdotSmemBytes;
       const long long htiles = (long long)n * hg.tiles_x * hg.tiles_y;
       const long long hitems = ((htiles + 1) / 2) * t.n_tiles;
       L.halo_grid = (int)std::min<long long>(hitems, h->sm_count / 2) * 2;
@@ -774,7 +774,7 @@ static Plan* get_plan(dcscn_handle* h, int n, int H, int W) {
     const int klast = find_layer(h, "R-CNN1")->k;
     pl->unfused = L;
     pl->fused_index = (int)pl->tc.size() - 1;
-    pl->fused_last = (klast == 3) && (cout % 16 == 0) && (nch % kColSplit == 0) && ((per * 16) % cout == 0);
+    pl->fused_last = (klast == 3) && (cout % 16 == 0) && (cout <= 128) && (nch % kColSplit == 0) && ((per * 16) % cout == 0);
     if (pl->fused_last) {
       L.p.epi.mode = EPI_D2S_RDOT;
       L.p.epi.rdot_w = h->d_last_w;
@@ -925,7 +925,8 @@ static int forward_impl(dcscn_handle* h, const float* x, const float* x2, float*
   {  // CNN1
     ConvFirstParams p = pl->first;
     p.x = x;
-    const long long total = (long long)n * H * W * (p.n_pad >> 4);
+    if (p.ksz > 5) return fail("cnn_size %d is not supported by the first-layer kernel", p.ksz);
+    const long long total = (long long)n * H * W;
     const int grid = (int)std::min<long long>((total + 255) / 256, (long long)h->sm_count * 8);
     const size_t smem = (size_t)p.ksz * p.ksz * p.n_pad * sizeof(float);
     conv_first_kernel<<<grid, 256, smem, st>>>(p);

@@ -128,8 +128,8 @@ __device__ __forceinline__ void epilogue_store16(const EpiParams& e, const ConvG
 
 // EPI_D2S_RDOT: 16 linear (bias only) columns of one sub-pixel -> accumulate the 9 per-tap dot products of the final
 // cout=1 convolution (R-CNN1, DCSCN.py:318-323) so that only `taps` floats per HR pixel ever reach HBM.
-__device__ __forceinline__ void rdot_accumulate16(const EpiParams& e, int cg, int c, const float (&acc)[16],
-                                                  float (&v)[9]) {
+__device__ __forceinline__ void rdot_accumulate16(const EpiParams& e, const float* w_smem, int cg, int c,
+                                                  const float (&acc)[16], float (&v)[9]) {
   float t[16];
   const float4* b4 = reinterpret_cast<const float4*>(e.bias + cg);
 #pragma unroll
@@ -143,11 +143,12 @@ __device__ __forceinline__ void rdot_accumulate16(const EpiParams& e, int cg, in
 #pragma unroll
   for (int tap = 0; tap < 9; ++tap) {
     if (tap < e.rdot_taps) {
-      const float4* w4 = reinterpret_cast<const float4*>(e.rdot_w + tap * e.d2s_cout + c);
+      // filter taps staged in shared memory: every lane reads the same address (broadcast, one wavefront)
+      const float4* w4 = reinterpret_cast<const float4*>(w_smem + tap * e.d2s_cout + c);
       float s = v[tap];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        float4 w = __ldg(w4 + q);
+        float4 w = w4[q];
         s = fmaf(t[4 * q + 0], w.x, s);
         s = fmaf(t[4 * q + 1], w.y, s);
         s = fmaf(t[4 * q + 2], w.z, s);

@@ -22,6 +22,7 @@
 #include "conv_tc.cuh"
 #include "conv_tc_pair.cuh"
 #include "conv_tc_halo.cuh"
+#include "conv_tc_halo1.cuh"
 
 using namespace dcscn;
 
@@ -97,6 +98,10 @@ struct TcLaunch {
   ConvGeom hg;
   int halo_grid = 0, halo_na = 0, halo_nb = 0, halo_seg = 1;
   size_t halo_smem = 0;
+  bool halo1 = false;            // single 18x10 box per chunk (experimental)
+  CUtensorMap t1_hi, t1_lo;
+  int halo1_na = 0, halo1_nb = 0, halo1_seg = 1;
+  size_t halo1_smem = 0;
   size_t pair_smem = 0;
   ConvTCParams p;
   ConvRefParams ref;
@@ -160,7 +165,8 @@ struct dcscn_handle {
   int seg_chunks = 0;                // pipeline stages per fp32-promotion segment; 0 = automatic
   int cluster = 1;                   // CTAs per cluster multicasting the weight tiles (single-CTA kernel)
   int pair = 1;                      // use the CTA-pair (tcgen05 cta_group::2) kernel when KC == 64
-  int halo = 1;                      // 3x3 layers: halo-reuse variant of the CTA-pair kernel
+  int halo = 1;                      // 3x3 layers: halo-reuse variant of the CTA-pair kernel (2 = single-box variant)
+  int halo_base = 0;                 // single-box variant: set the descriptor base-offset field
   int timing = 0;
   int fuse_last = 1;                 // fold the per-pixel half of R-CNN1 into the last Up-PS epilogue
   std::vector<cudaEvent_t> ev;       // timing events (launch boundaries of the last forward)
@@ -665,6 +671,33 @@ static int add_tc_launch(dcscn_handle* h, Plan* pl, const TcLayer& t, const __ha
     }
   }
 
+  L.halo1 = false;
+  if (L.halo) {
+    const size_t a_slot = tc_halo1_a_slot_bytes(planes(h)), b_stage = tc_halo_b_stage_bytes(planes(h), t.n_pad);
+    int seg = h->seg_chunks > 0 ? h->seg_chunks : (t.n_pad >= 112 ? 1 : 2);
+    for (; seg >= 1; --seg) {
+      const int na = 2;
+      const long long left = (long long)budget - (long long)na * (long long)a_slot;
+      const int nb = left > 0 ? (int)std::min<long long>(kMaxStages, left / (long long)b_stage) : 0;
+      if (nb >= 3 * seg + 1) {
+        L.halo1 = true;
+        L.halo1_seg = seg;
+        L.halo1_na = na;
+        L.halo1_nb = nb;
+        L.halo1_smem = na * a_slot + nb * b_stage + 1024 + 512 + kRdotSmemBytes;
+        break;
+      }
+    }
+    if (L.halo1) {
+      if (encode_map(h, &L.t1_hi, src_hi, t.cin_pad, src_pitch, n, H, W, kHaloTH + 2, kHalo1W, 64)) return 1;
+      if (planes(h) == 2) {
+        if (encode_map(h, &L.t1_lo, src_lo, t.cin_pad, src_pitch, n, H, W, kHaloTH + 2, kHalo1W, 64)) return 1;
+      } else {
+        L.t1_lo = L.t1_hi;
+      }
+    }
+  }
+
   // validation twin
   L.ref.g = g;
   L.ref.ksz = t.ksz;
@@ -883,6 +916,34 @@ static int launch_tc_halo(dcscn_handle* h, const TcLaunch& L, cudaStream_t st) {
   return 0;
 }
 
+template <int NPL>
+static int launch_tc_halo1(dcscn_handle* h, const TcLaunch& L, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(conv_tc_halo1_kernel<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(L.halo_grid);
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = L.halo1_smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ConvTCParams p = L.p;
+  p.g = L.hg;
+  p.cluster_size = 2;
+  p.seg_chunks = L.halo1_seg;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc_halo1_kernel<NPL>, L.t1_hi, L.t1_lo, L.tm_w, p, L.halo1_na, L.halo1_nb, h->halo_base));
+  return 0;
+}
+
 static int launch_tc(dcscn_handle* h, const TcLaunch& L, cudaStream_t st) {
   h->launches++;
   if (h->conv_impl == 1) {
@@ -893,6 +954,7 @@ static int launch_tc(dcscn_handle* h, const TcLaunch& L, cudaStream_t st) {
     return 0;
   }
   const int npl = planes(h);
+  if (h->pair && h->halo == 2 && L.halo1 && h->kc == 64) return npl == 2 ? launch_tc_halo1<2>(h, L, st) : launch_tc_halo1<1>(h, L, st);
   if (h->pair && h->halo && L.halo && h->kc == 64) return npl == 2 ? launch_tc_halo<2>(h, L, st) : launch_tc_halo<1>(h, L, st);
   if (h->pair && L.pair && h->kc == 64) return npl == 2 ? launch_tc_pair<2>(h, L, st) : launch_tc_pair<1>(h, L, st);
   if (h->kc == 64) return npl == 2 ? launch_tc_inst<64, 2>(h, L, st) : launch_tc_inst<64, 1>(h, L, st);
@@ -1152,8 +1214,11 @@ int dcscn_set_option(dcscn_handle* h, const char* key, int64_t value) {
       h->plans.clear();
       h->last_plan = nullptr;
     }
+  } else if (k == "halo_base") {
+    h->halo_base = (int)value;
   } else if (k == "halo") {
-    h->halo = value ? 1 : 0;
+    if (value < 0 || value > 2) return fail("halo must be 0, 1 or 2");
+    h->halo = (int)value;
   } else if (k == "pair") {
     h->pair = value ? 1 : 0;
   } else if (k == "cluster") {

@@ -34,7 +34,7 @@ constexpr int kEpiWarps = 8;                       // two warps per TMEM lane qu
 constexpr int kEpiWarp0 = 4;                       // warpgroup 0 = {TMA, MMA, 2 idle}; warpgroups 1.. = epilogue
 constexpr int kTcThreads = (kEpiWarp0 + kEpiWarps) * 32;
 constexpr int kRegsIssue = 40, kRegsEpilogue = 232;  // setmaxnreg budgets (128*56 + 256*224 <= 64K)
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 12;
 constexpr int kRdotSmemBytes = 9 * 128 * 4;         // fused R-CNN1 filter taps (d2s_cout <= 128) staged in shared memory
 constexpr int kAccStages = 2;
 constexpr int kAccStride = 256;  // TMEM columns per accumulator stage

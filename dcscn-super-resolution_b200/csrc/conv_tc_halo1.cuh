@@ -1,8 +1,9 @@
-// Single-box halo variant (experimental until validated): ONE {64, 10, 18, 1} TMA box per channel chunk serves all
+// Single-box halo variant (validated on B200: bit-level agreement with the three-box variant up to fp32 summation order): ONE {64, 10, 18, 1} TMA box per channel chunk serves all
 // nine taps.  The smem rows are (hy * 10 + hx); tap (dy, dx) starts (dy * 10 + dx) rows into the box and the 16 eight-row
 // groups of the UMMA A operand are 10 rows (1280 B) apart, so operand rows are NOT aligned to the 1024-byte swizzle
 // atom.  This relies on the tensor core applying the 128B-swizzle XOR on absolute shared-memory address bits [7,10)
-// (like TMA does when writing); `base_mode` = 1 additionally sets the descriptor's base-offset field.
+// (like TMA does when writing) - measured: correct with the descriptor base-offset field left 0, wrong with it set
+// (`base_mode` = 1 keeps that experiment reproducible).
 #pragma once
 #include "conv_tc_halo.cuh"
 

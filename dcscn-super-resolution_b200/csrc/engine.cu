@@ -165,7 +165,7 @@ struct dcscn_handle {
   int seg_chunks = 0;                // pipeline stages per fp32-promotion segment; 0 = automatic
   int cluster = 1;                   // CTAs per cluster multicasting the weight tiles (single-CTA kernel)
   int pair = 1;                      // use the CTA-pair (tcgen05 cta_group::2) kernel when KC == 64
-  int halo = 1;                      // 3x3 layers: halo-reuse variant of the CTA-pair kernel (2 = single-box variant)
+  int halo = 2;                      // 3x3 layers: halo-reuse CTA-pair kernel, 1 = three 18x8 boxes, 2 = one 18x10 box per chunk
   int halo_base = 0;                 // single-box variant: set the descriptor base-offset field
   int timing = 0;
   int fuse_last = 1;                 // fold the per-pixel half of R-CNN1 into the last Up-PS epilogue
@@ -674,7 +674,9 @@ static int add_tc_launch(dcscn_handle* h, Plan* pl, const TcLayer& t, const __ha
   L.halo1 = false;
   if (L.halo) {
     const size_t a_slot = tc_halo1_a_slot_bytes(planes(h)), b_stage = tc_halo_b_stage_bytes(planes(h), t.n_pad);
-    int seg = h->seg_chunks > 0 ? h->seg_chunks : (t.n_pad >= 112 ? 1 : 2);
+    // fp32-promotion period in (chunk, dx) units of 3 taps: thin layers are latency-bound, give them longer segments
+    int seg = h->seg_chunks > 0 ? h->seg_chunks : (t.n_pad >= 144 ? 1 : (t.n_pad >= 112 ? 2 : 3));
+    seg = std::min(seg, 3 * ((t.cin_pad + 63) / 64));
     for (; seg >= 1; --seg) {
       const int na = 2;
       const long long left = (long long)budget - (long long)na * (long long)a_slot;

@@ -91,7 +91,8 @@ int dcscn_get_activation(dcscn_handle* h, const char* tensor, float* host_data, 
 /* Options: "conv_impl" 0 = tcgen05 (default), 1 = CUDA-core fp32 validation kernels;
  *          "kc" 64 | 32 = K-chunk (channels per pipeline stage) of the tensor-core kernel;
  *          "seg_chunks" = pipeline stages per fp32-promotion segment (default 0 = automatic: 2, or 3 for thin layers);
- *          "halo" 1 | 0 = 3x3 layers fetch one 18x8 box per horizontal tap offset instead of one tile per tap (default 1);
+ *          "halo" 0 | 1 | 2 = 3x3 layers: one A tile per tap (0), three 18x8 boxes per channel chunk (1), or one
+ *                     18x10 box per channel chunk serving all nine taps (2, default);
  *          "pair" 1 | 0 = CTA-pair kernel (tcgen05 cta_group::2, weight tiles split across two SMs; default 1);
  *          "cluster" 1 | 2 | 4 = CTAs per cluster multicasting weight tiles in the single-CTA kernel (default 1);
  *          "fuse_last" 1 | 0 = compute the per-pixel half of R-CNN1 inside the last Up-PS epilogue (default 1);

@@ -73,6 +73,69 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const ConvFirstParams p
   }
 }
 
+// 3x3 fast path: lane = 8 consecutive output channels (weights, bias, alpha live in registers for the whole kernel),
+// warp = one pixel at a time, so each pixel's 2 x n_pad fp16 values leave the SM as two contiguous, fully coalesced
+// rows.  HBM-write-bound by construction (CNN1 writes 2 x 208 fp16 per LR pixel and reads 4 bytes).
+__global__ void __launch_bounds__(256) conv_first3x3_kernel(const ConvFirstParams p) {
+  const int lane = threadIdx.x & 31;
+  const int lanes_used = p.n_pad >> 3;
+  const bool active = lane < lanes_used;
+  const int c0 = lane * 8;
+  float w[9][8], bias[8], alpha[8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[t][i] = active ? __ldg(p.w + t * p.n_pad + c0 + i) : 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    bias[i] = active ? __ldg(p.epi.bias + c0 + i) : 0.f;
+    alpha[i] = active ? __ldg(p.epi.alpha + c0 + i) : 1.f;
+  }
+  const EpiSegment seg = p.epi.seg[0];
+  const float keep = p.epi.keep_prob, inv_keep = 1.0f / keep;
+  const long long total = (long long)p.g.n_img * p.g.H * p.g.W;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long pix = warp0; pix < total; pix += nwarps) {
+    const int x = (int)(pix % p.g.W);
+    const int y = (int)((pix / p.g.W) % p.g.H);
+    const float* row = p.x + (pix - x);            // start of this image row
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int dy = t / 3 - 1, dx = t % 3 - 1;
+      const int yy = y + dy, xx = x + dx;
+      const float v = (yy >= 0 && yy < p.g.H && xx >= 0 && xx < p.g.W) ? __ldg(row + (long long)dy * p.g.W + xx) : 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(v, w[t][i], acc[i]);
+    }
+    uint32_t ph[4], pl[4];
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+      float t0 = acc[i] + bias[i], t1 = acc[i + 1] + bias[i + 1];
+      t0 = t0 > 0.f ? t0 : alpha[i] * t0;
+      t1 = t1 > 0.f ? t1 : alpha[i + 1] * t1;
+      if (keep < 1.0f) {
+        const uint64_t base = (uint64_t)pix * (uint64_t)p.n_pad + c0 + i;
+        t0 = dropout_keep(p.epi.drop_seed, p.epi.drop_layer, base, keep) ? t0 * inv_keep : 0.f;
+        t1 = dropout_keep(p.epi.drop_seed, p.epi.drop_layer, base + 1, keep) ? t1 * inv_keep : 0.f;
+      }
+      __half h0, l0, h1, l1;
+      split_f16(t0, h0, l0);
+      split_f16(t1, h1, l1);
+      ph[i >> 1] = pack_h2(h0, h1);
+      pl[i >> 1] = pack_h2(l0, l1);
+    }
+    if (active) {
+      const size_t off = (size_t)pix * seg.pitch + c0;
+      *reinterpret_cast<uint4*>(seg.dst_hi + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+      if (seg.dst_lo != nullptr) *reinterpret_cast<uint4*>(seg.dst_lo + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+    }
+  }
+}
+
 // ---------------------------------------------------------------- R-CNN1 -----------------------------------
 struct ConvLastParams {
   int n_img, H, W;       // HR resolution

@@ -993,7 +993,10 @@ static int forward_impl(dcscn_handle* h, const float* x, const float* x2, float*
     const long long total = (long long)n * H * W;
     const int grid = (int)std::min<long long>((total + 255) / 256, (long long)h->sm_count * 8);
     const size_t smem = (size_t)p.ksz * p.ksz * p.n_pad * sizeof(float);
-    conv_first_kernel<<<grid, 256, smem, st>>>(p);
+    if (p.ksz == 3 && p.n_pad <= 256)
+      conv_first3x3_kernel<<<(int)std::min<long long>((total + 7) / 8, (long long)h->sm_count * 8), 256, 0, st>>>(p);
+    else
+      conv_first_kernel<<<grid, 256, smem, st>>>(p);
     CUDA_TRY(cudaGetLastError());
     h->launches++;
     if (mark(h, st)) return 1;

@@ -23,6 +23,7 @@
 #include "conv_tc_pair.cuh"
 #include "conv_tc_halo.cuh"
 #include "conv_tc_halo1.cuh"
+#include "conv_ds.cuh"
 
 using namespace dcscn;
 
@@ -157,6 +158,14 @@ struct dcscn_handle {
   size_t io_cap = 0;
   int64_t device_bytes = 0;
 
+  // depthwise-separable graphs: fp32 buffers + per-layer device filters
+  struct DsDev { float *dw = nullptr, *pw = nullptr, *bias = nullptr, *alpha = nullptr; };
+  std::vector<DsDev> ds;             // same order as `layers`
+  float *ds_feat = nullptr, *ds_b1 = nullptr, *ds_nin = nullptr, *ds_mid = nullptr, *ds_hr = nullptr;
+  int ds_total = 0;                  // channels of the (unpadded) concat buffer
+  int ds_n = 0, ds_h = 0, ds_w = 0;  // geometry of the last DS forward
+  std::vector<int> ds_off;
+
   std::vector<std::unique_ptr<Plan>> plans;
   Plan* last_plan = nullptr;
 
@@ -205,7 +214,6 @@ static void add_param(dcscn_handle* h, const std::string& name, std::vector<int6
 static int build_graph(dcscn_handle* h) {
   const dcscn_config& c = h->cfg;
   if (!c.use_nin) return fail("use_nin=false is not supported (no shipped checkpoint uses it)");
-  if (c.depthwise_separable) return fail("depthwise_separable graphs are not built by this engine version");
   if (c.channels != 1) return fail("channels must be 1 (helper/args.py: 'Now it should be 1')");
   if (std::max(c.reconstruct_layers, 1) != 1) return fail("reconstruct_layers > 1 is not supported");
   if (c.scale < 2 || c.scale > 4) return fail("scale must be 2, 3 or 4");
@@ -235,6 +243,10 @@ static int build_graph(dcscn_handle* h) {
   for (const LayerDef& l : h->layers) {
     std::string base = l.scope.substr(l.scope.find_last_of('/') == std::string::npos ? 0 : l.scope.find_last_of('/') + 1);
     add_param(h, l.scope + "/conv_W", {l.k, l.k, l.cin, l.cout}, 0.f);
+    if (c.depthwise_separable) {  // tf_graph.py:157-160; conv_W stays as the (dead) variable the reference also creates
+      add_param(h, l.scope + "/depthwise_W", {l.k, l.k, l.cin, 1}, 0.f);
+      add_param(h, l.scope + "/pointwise_W", {1, 1, l.cin, l.cout}, 0.f);
+    }
     if (l.bias) add_param(h, l.scope + "/conv_B", {l.cout}, 0.f);                 // util.bias: zeros
     if (l.prelu) add_param(h, l.scope + "/prelu/" + base + "_prelu", {l.cout}, 0.1f);  // tf_graph.py:91
   }
@@ -424,8 +436,33 @@ static void free_tc(TcLayer& t) {
 }
 
 // (Re)builds every device-side weight image from the host fp32 parameters.
+static int finalize_params_ds(dcscn_handle* h) {
+  for (auto& d : h->ds) {
+    cudaFree(d.dw); cudaFree(d.pw); cudaFree(d.bias); cudaFree(d.alpha);
+  }
+  h->ds.assign(h->layers.size(), dcscn_handle::DsDev());
+  for (size_t i = 0; i < h->layers.size(); ++i) {
+    const LayerDef& l = h->layers[i];
+    std::string base = l.scope.substr(l.scope.find_last_of('/') == std::string::npos ? 0 : l.scope.find_last_of('/') + 1);
+    if (upload(&h->ds[i].dw, P(h, l.scope + "/depthwise_W"), h)) return 1;   // [k,k,cin,1] == [taps][cin]
+    if (upload(&h->ds[i].pw, P(h, l.scope + "/pointwise_W"), h)) return 1;   // [1,1,cin,cout] == [cin][cout]
+    if (l.bias && upload(&h->ds[i].bias, P(h, l.scope + "/conv_B"), h)) return 1;
+    if (l.prelu && upload(&h->ds[i].alpha, P(h, l.scope + "/prelu/" + base + "_prelu"), h)) return 1;
+  }
+  h->ds_off.clear();
+  int off = 0;
+  for (int f : h->filters) {
+    h->ds_off.push_back(off);
+    off += f;
+  }
+  h->ds_total = off;
+  h->params_dirty = false;
+  return 0;
+}
+
 static int finalize_params(dcscn_handle* h) {
   const dcscn_config& c = h->cfg;
+  if (c.depthwise_separable) return finalize_params_ds(h);
   for (TcLayer& t : h->tcl) free_tc(t);
   h->tcl.clear();
   h->plans.clear();
@@ -523,6 +560,18 @@ static int dev_alloc(dcscn_handle* h, T** p, size_t count, bool zero) {
 static int ensure_workspace(dcscn_handle* h, size_t lr_px) {
   if (lr_px <= h->cap_px) return 0;
   const dcscn_config& c = h->cfg;
+  if (c.depthwise_separable) {
+    h->device_bytes = 0;
+    const size_t s2 = (size_t)c.scale * c.scale;
+    const int cps = c.nin_filters + c.nin_filters2;
+    if (dev_alloc(h, &h->ds_feat, lr_px * h->ds_total, false)) return 1;
+    if (dev_alloc(h, &h->ds_b1, lr_px * c.nin_filters2, false)) return 1;
+    if (dev_alloc(h, &h->ds_nin, lr_px * cps, false)) return 1;
+    if (c.scale == 4 && dev_alloc(h, &h->ds_mid, lr_px * 4 * cps, false)) return 1;
+    if (dev_alloc(h, &h->ds_hr, lr_px * s2 * h->ps_out, false)) return 1;
+    h->cap_px = lr_px;
+    return 0;
+  }
   h->plans.clear();
   h->last_plan = nullptr;
   h->device_bytes = 0;
@@ -974,12 +1023,74 @@ static int mark(dcscn_handle* h, cudaStream_t st) {
   return 0;
 }
 
+static int mark(dcscn_handle* h, cudaStream_t st);
+static int launch_ds(dcscn_handle* h, const LayerDef& l, const dcscn_handle::DsDev& d, const float* src, int src_pitch,
+                     float* dst, int dst_pitch, int dst_off, int n, int H, int W, int d2s_r, int d2s_cout,
+                     const float* add, cudaStream_t st) {
+  DsLayerParams p;
+  memset(&p, 0, sizeof(p));
+  p.n_img = n; p.H = H; p.W = W; p.ksz = l.k; p.cin = l.cin; p.cout = l.cout;
+  p.src = src; p.src_pitch = src_pitch; p.dw = d.dw; p.pw = d.pw; p.bias = d.bias; p.alpha = d.alpha;
+  p.dst = dst; p.dst_pitch = dst_pitch; p.dst_off = dst_off; p.d2s_r = d2s_r; p.d2s_cout = d2s_cout; p.add = add;
+  const int segs = (W + kDsPix - 1) / kDsPix;
+  const size_t smem = (size_t)kDsPix * l.cin * sizeof(float);
+  if (smem > 200 * 1024) return fail("depthwise-separable layer %s: %d input channels exceed the kernel's shared memory", l.scope.c_str(), l.cin);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(ds_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  ds_layer_kernel<<<n * H * segs, kDsThreads, smem, st>>>(p);
+  CUDA_TRY(cudaGetLastError());
+  h->launches++;
+  return mark(h, st);
+}
+
+// Depthwise-separable graph (DCSCN.py:246-249, 264-271, 318-320; tf_graph.py:240-243): fp32 NHWC, CUDA cores.
+static int forward_ds(dcscn_handle* h, const float* x, const float* x2, float* y, int n, int H, int W, cudaStream_t st) {
+  const dcscn_config& c = h->cfg;
+  const int L = c.layers, T = h->ds_total, cps = c.nin_filters + c.nin_filters2;
+  h->ev_used = 0;
+  if (mark(h, st)) return 1;
+  size_t li = 0;
+  for (int i = 0; i < L; ++i, ++li) {
+    const float* src = i == 0 ? x : h->ds_feat + h->ds_off[i - 1];
+    if (launch_ds(h, h->layers[li], h->ds[li], src, i == 0 ? c.channels : T, h->ds_feat, T, h->ds_off[i], n, H, W, 0, 0, nullptr, st)) return 1;
+  }
+  if (launch_ds(h, h->layers[li], h->ds[li], h->ds_feat, T, h->ds_nin, cps, c.nin_filters2, n, H, W, 0, 0, nullptr, st)) return 1;  // A1
+  ++li;
+  if (launch_ds(h, h->layers[li], h->ds[li], h->ds_feat, T, h->ds_b1, c.nin_filters2, 0, n, H, W, 0, 0, nullptr, st)) return 1;     // B1
+  ++li;
+  if (launch_ds(h, h->layers[li], h->ds[li], h->ds_b1, c.nin_filters2, h->ds_nin, cps, 0, n, H, W, 0, 0, nullptr, st)) return 1;     // B2
+  ++li;
+  int HH = H, WW = W;
+  if (c.scale == 4) {
+    if (launch_ds(h, h->layers[li], h->ds[li], h->ds_nin, cps, h->ds_mid, cps, 0, n, H, W, 2, cps, nullptr, st)) return 1;           // Up-PS
+    ++li;
+    HH = 2 * H; WW = 2 * W;
+    if (launch_ds(h, h->layers[li], h->ds[li], h->ds_mid, cps, h->ds_hr, h->ps_out, 0, n, HH, WW, 2, h->ps_out, nullptr, st)) return 1;  // Up-PS2
+    ++li;
+    HH *= 2; WW *= 2;
+  } else {
+    if (launch_ds(h, h->layers[li], h->ds[li], h->ds_nin, cps, h->ds_hr, h->ps_out, 0, n, H, W, c.scale, h->ps_out, nullptr, st)) return 1;
+    ++li;
+    HH = c.scale * H; WW = c.scale * W;
+  }
+  // R-CNN1 (no bias / activation) + x2
+  if (launch_ds(h, h->layers[li], h->ds[li], h->ds_hr, h->ps_out, y, 1, 0, n, HH, WW, 0, 0, x2, st)) return 1;
+  return 0;
+}
+
 static int forward_impl(dcscn_handle* h, const float* x, const float* x2, float* y, int n, int H, int W,
                         cudaStream_t st) {
   if (n <= 0 || H <= 0 || W <= 0) return fail("forward: bad shape n=%d h=%d w=%d", n, H, W);
   CUDA_TRY(cudaSetDevice(h->cfg.device_id));
   if (h->params_dirty && finalize_params(h)) return 1;
   if (ensure_workspace(h, (size_t)n * H * W)) return 1;
+  if (h->cfg.depthwise_separable) {
+    h->ds_n = n; h->ds_h = H; h->ds_w = W;
+    return forward_ds(h, x, x2, y, n, H, W, st);
+  }
   Plan* pl = get_plan(h, n, H, W);
   if (!pl) return 1;
   h->last_plan = pl;
@@ -1087,6 +1198,8 @@ int dcscn_destroy(dcscn_handle* h) {
   cudaFree(h->mid_lo);
   cudaFree(h->hr);
   cudaFree(h->vbuf);
+  cudaFree(h->ds_feat); cudaFree(h->ds_b1); cudaFree(h->ds_nin); cudaFree(h->ds_mid); cudaFree(h->ds_hr);
+  for (auto& d : h->ds) { cudaFree(d.dw); cudaFree(d.pw); cudaFree(d.bias); cudaFree(d.alpha); }
   cudaFree(h->io_x);
   cudaFree(h->io_x2);
   cudaFree(h->io_y);
@@ -1159,6 +1272,34 @@ int dcscn_forward_host(dcscn_handle* h, const float* x, const float* x2, float* 
 
 int dcscn_get_activation(dcscn_handle* h, const char* tensor, float* host_data, int64_t numel) {
   if (!h || !tensor || !host_data) return fail("dcscn_get_activation: null argument");
+  if (h->cfg.depthwise_separable) {
+    if (h->ds_n == 0) return fail("dcscn_get_activation: no forward has run yet");
+    CUDA_TRY(cudaSetDevice(h->cfg.device_id));
+    CUDA_TRY(cudaDeviceSynchronize());
+    const dcscn_config& c = h->cfg;
+    const std::string t(tensor);
+    const int cps = c.nin_filters + c.nin_filters2;
+    const float* src = nullptr;
+    int pitch = 0, off = 0, ch = 0;
+    size_t px = (size_t)h->ds_n * h->ds_h * h->ds_w;
+    if (t.rfind("CNN", 0) == 0) {
+      int i = atoi(t.c_str() + 3) - 1;
+      if (i < 0 || i >= c.layers) return fail("dcscn_get_activation: no tensor '%s'", tensor);
+      src = h->ds_feat; pitch = h->ds_total; off = h->ds_off[i]; ch = h->filters[i];
+    } else if (t == "A1") { src = h->ds_nin; pitch = cps; off = c.nin_filters2; ch = c.nin_filters;
+    } else if (t == "B2") { src = h->ds_nin; pitch = cps; off = 0; ch = c.nin_filters2;
+    } else if (t == "B1") { src = h->ds_b1; pitch = c.nin_filters2; off = 0; ch = c.nin_filters2;
+    } else if (t == "Up-PS" && c.scale == 4) { src = h->ds_mid; pitch = cps; off = 0; ch = cps; px *= 4;
+    } else if ((t == "Up-PS" && c.scale != 4) || (t == "Up-PS2" && c.scale == 4)) {
+      src = h->ds_hr; pitch = h->ps_out; off = 0; ch = h->ps_out; px *= (size_t)c.scale * c.scale;
+    } else return fail("dcscn_get_activation: no tensor '%s'", tensor);
+    if (numel != (int64_t)(px * ch)) return fail("dcscn_get_activation: '%s' has %lld elements, got %lld", tensor, (long long)(px * ch), (long long)numel);
+    std::vector<float> full(px * pitch);
+    CUDA_TRY(cudaMemcpy(full.data(), src, full.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    for (size_t p = 0; p < px; ++p)
+      for (int k = 0; k < ch; ++k) host_data[p * ch + k] = full[p * pitch + off + k];
+    return 0;
+  }
   Plan* pl = h->last_plan;
   if (!pl) return fail("dcscn_get_activation: no forward has run yet");
   CUDA_TRY(cudaSetDevice(h->cfg.device_id));
@@ -1256,8 +1397,13 @@ int dcscn_get_timings(dcscn_handle* h, float* ms, int capacity, int* count, char
   *count = n;
   if (names && names_len > 0) {
     std::string s = "CNN1";
-    for (const TcLayer& t : h->tcl) s += "," + t.name;
-    s += ",R-CNN1";
+    if (h->cfg.depthwise_separable) {
+      s = "";
+      for (const LayerDef& l : h->layers) s += (s.empty() ? "" : ",") + l.scope.substr(0, l.scope.find('/'));
+    } else {
+      for (const TcLayer& t : h->tcl) s += "," + t.name;
+      s += ",R-CNN1";
+    }
     snprintf(names, names_len, "%s", s.c_str());
   }
   return 0;

@@ -1,0 +1,348 @@
+// Backward pass + optimizer kernels of the DCSCN train step (reference: DCSCN.py:334-413 `build_optimizer` /
+// `add_optimizer_op`, i.e. what `sess.run(self.training_optimizer)` executed: tf.gradients of
+// mse + l2_decay * sum(l2_loss(W)), tf.clip_by_global_norm, tf.train.AdamOptimizer).
+//
+// Split of the work:
+//   * data gradients (dgrad) of every 3x3 / 1x1 layer run on the SAME tcgen05 implicit-GEMM kernels as the forward
+//     pass (conv_tc*.cuh) with the filters transposed and spatially flipped - no extra MMA code;
+//   * everything else is in this file, on CUDA cores: loss / output gradient, R-CNN1 backward fused with the
+//     depth_to_space gradient (= space_to_depth), PReLU + dropout gradients with the per-channel bias / alpha
+//     reductions, filter gradients (wgrad: a reduction over all pixels, shared-memory tiled, fp32 atomics) and the
+//     fused L2-decay + global-norm + Adam update over one flat parameter buffer.
+//   All activation-sized gradients are kept in the fp16 hi/lo plane format of the forward pass, multiplied by a
+//   power-of-two `grad_scale` (loss scaling) so they sit in fp16's normal range; the scale is removed when the filter
+//   gradients are finalised.
+#pragma once
+#include "common.h"
+#include "epilogue.cuh"
+
+namespace dcscn {
+
+__device__ __forceinline__ float load_planes(const __half* hi, const __half* lo, size_t i) {
+  float v = __half2float(hi[i]);
+  if (lo != nullptr) v += __half2float(lo[i]);
+  return v;
+}
+__device__ __forceinline__ void store_planes(__half* hi, __half* lo, size_t i, float v) {
+  __half h, l;
+  split_f16(v, h, l);
+  hi[i] = h;
+  if (lo != nullptr) lo[i] = l;
+}
+
+// ------------------------------------------------------------------------------------------------ loss ----
+// diff = y_ - y; mse = mean(diff^2) (DCSCN.py:340-347); dY = dL/dy_ * grad_scale = diff * (2 * grad_scale / count).
+struct LossParams {
+  const float* y_pred;
+  const float* y_true;
+  float* dY;
+  size_t count;
+  float dscale;        // 2 * grad_scale / count
+  double* sq_sum;      // sum of diff^2 (one double)
+};
+
+__global__ void __launch_bounds__(256) loss_kernel(const LossParams p) {
+  double acc = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.count; i += (size_t)gridDim.x * blockDim.x) {
+    const float d = p.y_pred[i] - p.y_true[i];
+    p.dY[i] = d * p.dscale;
+    acc += (double)d * (double)d;
+  }
+  __shared__ double s[256];
+  s[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) atomicAdd(p.sq_sum, s[0]);
+}
+
+// --------------------------------------------------------------------------------------- R-CNN1 backward ----
+// forward: out[q] = sum_tap sum_c w[tap][c] * hr[q + off(tap)][c]  (+ x2).
+// (a) dW[tap][c] = sum_q hr[q + off(tap)][c] * dY[q]
+struct LastWgradParams {
+  int n_img, H, W, ksz, C, pitch;
+  const float* hr;     // [N,H,W,pitch]
+  const float* dY;     // [N,H,W]
+  float* dW;           // [taps][C]
+  int px_per_block;
+};
+
+__global__ void __launch_bounds__(1024) last_wgrad_kernel(const LastWgradParams p) {
+  const int taps = p.ksz * p.ksz, half = p.ksz >> 1;
+  const size_t total = (size_t)p.n_img * p.H * p.W;
+  const size_t q0 = (size_t)blockIdx.x * p.px_per_block;
+  const size_t q1 = q0 + p.px_per_block < total ? q0 + p.px_per_block : total;
+  for (int tc = threadIdx.x; tc < taps * p.C; tc += blockDim.x) {
+    const int tap = tc / p.C, c = tc - tap * p.C;
+    const int dy = tap / p.ksz - half, dx = tap % p.ksz - half;
+    float acc = 0.f;
+    for (size_t q = q0; q < q1; ++q) {
+      const int x = (int)(q % p.W), y = (int)((q / p.W) % p.H);
+      const int yy = y + dy, xx = x + dx;
+      if (yy < 0 || yy >= p.H || xx < 0 || xx >= p.W) continue;
+      acc = fmaf(__ldg(p.hr + (q + (ptrdiff_t)dy * p.W + dx) * p.pitch + c), __ldg(p.dY + q), acc);
+    }
+    atomicAdd(p.dW + tc, acc);
+  }
+}
+
+// (b) d hr[q][c] = sum_tap w[tap][c] * dY[q - off(tap)], written straight into the space_to_depth layout that is the
+//     gradient of tf.depth_to_space (tf_graph.py:248): dZ[lr pixel][(i*r + j)*C + c] = d hr[(y*r+i, x*r+j)][c],
+//     as fp16 hi/lo planes (input of the Up-PS dgrad / wgrad).
+struct LastDgradParams {
+  int n_img, H, W;     // LR-side resolution of the layer that feeds depth_to_space
+  int r, C, ksz;
+  const float* w;      // [taps][C]
+  const float* dY;     // [N, r*H, r*W]
+  __half* dz_hi;       // [N,H,W,pitch]
+  __half* dz_lo;
+  int pitch;
+};
+
+__global__ void __launch_bounds__(256) last_dgrad_s2d_kernel(const LastDgradParams p) {
+  const int cols = p.r * p.r * p.C, half = p.ksz >> 1;
+  const int HH = p.H * p.r, WW = p.W * p.r;
+  const size_t total = (size_t)p.n_img * p.H * p.W * cols;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int col = (int)(idx % cols);
+    const size_t pix = idx / cols;
+    const int x = (int)(pix % p.W), y = (int)((pix / p.W) % p.H), img = (int)(pix / ((size_t)p.W * p.H));
+    const int ij = col / p.C, c = col - ij * p.C, i = ij / p.r, j = ij - i * p.r;
+    const int Y = y * p.r + i, X = x * p.r + j;
+    float acc = 0.f;
+    for (int tap = 0; tap < p.ksz * p.ksz; ++tap) {
+      const int yy = Y - (tap / p.ksz - half), xx = X - (tap % p.ksz - half);
+      if (yy < 0 || yy >= HH || xx < 0 || xx >= WW) continue;
+      acc = fmaf(__ldg(p.w + tap * p.C + c), __ldg(p.dY + ((size_t)img * HH + yy) * WW + xx), acc);
+    }
+    store_planes(p.dz_hi, p.dz_lo, pix * p.pitch + col, acc);
+  }
+}
+
+// space_to_depth of a plane tensor (gradient of the first depth_to_space of the x4 graph, DCSCN.py:298-301).
+struct S2dParams {
+  int n_img, H, W, r, C;   // LR-side size; src is [N, r*H, r*W, src_pitch]
+  const __half *src_hi, *src_lo;
+  int src_pitch;
+  __half *dst_hi, *dst_lo;
+  int dst_pitch;
+};
+
+__global__ void __launch_bounds__(256) s2d_planes_kernel(const S2dParams p) {
+  const int cols = p.r * p.r * p.C;
+  const size_t total = (size_t)p.n_img * p.H * p.W * cols;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int col = (int)(idx % cols);
+    const size_t pix = idx / cols;
+    const int x = (int)(pix % p.W), y = (int)((pix / p.W) % p.H), img = (int)(pix / ((size_t)p.W * p.H));
+    const int ij = col / p.C, c = col - ij * p.C, i = ij / p.r, j = ij - i * p.r;
+    const size_t s = (((size_t)img * p.H * p.r + (size_t)(y * p.r + i)) * (p.W * p.r) + (size_t)(x * p.r + j)) * p.src_pitch + c;
+    const size_t d = pix * p.dst_pitch + col;
+    p.dst_hi[d] = p.src_hi[s];
+    if (p.dst_lo != nullptr) p.dst_lo[d] = p.src_lo[s];
+  }
+}
+
+// -------------------------------------------------------------- PReLU + dropout gradient, bias / alpha sums ----
+// out = dropout(prelu(z)) (tf_graph.py:126-130).  g = dL/d out (sum of up to two plane tensors).
+//   dZ     = g * keepmask/keep * (z > 0 ? 1 : alpha)
+//   dalpha = sum g * keepmask/keep * min(z, 0)          db = sum dZ
+// z is recovered from the stored forward output (alpha > 0 is required): z < 0 <=> out < 0, z = out * keep / alpha.
+// Layers without activation (alpha == nullptr): dZ = g.
+struct ActGradParams {
+  size_t pixels;
+  int C;                 // logical channels
+  int n_total;           // padded GEMM width used by the forward dropout hash
+  int col0;              // first column of this tensor inside that GEMM (A1+B1 fusion)
+  const __half *g1_hi, *g1_lo; int g1_pitch;   // gradient source 1 (already offset to channel 0 of this tensor)
+  const __half *g2_hi, *g2_lo; int g2_pitch;   // optional source 2 (nullptr: none)
+  const __half *out_hi, *out_lo; int out_pitch;  // forward output (post activation / dropout)
+  const float* alpha;    // [C] or nullptr
+  float keep;
+  uint32_t seed, layer;
+  __half *dz_hi, *dz_lo; int dz_pitch;         // result planes (pad channels must stay zero)
+  float* dbias;          // [C] accumulators (scaled by grad_scale) or nullptr
+  float* dalpha;         // [C] or nullptr
+  int px_per_block;
+};
+
+__global__ void __launch_bounds__(256) act_grad_kernel(const ActGradParams p) {
+  const size_t q0 = (size_t)blockIdx.x * p.px_per_block;
+  const size_t q1 = q0 + p.px_per_block < p.pixels ? q0 + p.px_per_block : p.pixels;
+  const float inv_keep = 1.0f / p.keep;
+  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+    const float a = p.alpha ? __ldg(p.alpha + c) : 1.f;
+    float sb = 0.f, sa = 0.f;
+    for (size_t q = q0; q < q1; ++q) {
+      float g = load_planes(p.g1_hi, p.g1_lo, q * p.g1_pitch + c);
+      if (p.g2_hi != nullptr) g += load_planes(p.g2_hi, p.g2_lo, q * p.g2_pitch + c);
+      float dz = g;
+      if (p.alpha != nullptr) {
+        if (p.keep < 1.0f) {
+          const bool kept = dropout_keep(p.seed, p.layer, (uint64_t)q * (uint64_t)p.n_total + p.col0 + c, p.keep);
+          g = kept ? g * inv_keep : 0.f;
+        }
+        const float out = load_planes(p.out_hi, p.out_lo, q * p.out_pitch + c);
+        if (out < 0.f) {
+          sa = fmaf(g, out * p.keep / a, sa);
+          dz = g * a;
+        } else {
+          dz = g;
+        }
+      }
+      sb += dz;
+      store_planes(p.dz_hi, p.dz_lo, q * p.dz_pitch + c, dz);
+    }
+    if (p.dbias != nullptr) atomicAdd(p.dbias + c, sb);
+    if (p.dalpha != nullptr) atomicAdd(p.dalpha + c, sa);
+  }
+}
+
+// --------------------------------------------------------------------------------------------- wgrad ----
+// dW[tap][ci][co] += sum_p A[p + off(tap)][pos(ci)] * dZ[p][co]   (gradient of tf.nn.conv2d w.r.t. the HWIO filter)
+// One CTA: one tap, a 64 x 64 (ci x co) tile, a range of image rows; 256 threads, 4 x 4 register micro-tile each,
+// operands staged through shared memory as fp32 in chunks of 32 pixels.
+struct WgradParams {
+  int n_img, H, W, ksz, cin, cout;
+  const __half *a_hi, *a_lo;   // input activation planes (nullptr when a_f32 is used)
+  const float* a_f32;          // fp32 input (CNN1: the LR image, cin == 1)
+  int a_pitch;
+  const int* in_map;           // [cin] channel position inside the input buffer, or nullptr (identity)
+  const __half *dz_hi, *dz_lo; // output-gradient planes [pixels][dz_pitch]
+  int dz_pitch;
+  float* dW;                   // [taps][cin][cout] fp32, accumulated with atomics
+  int rows_per_block;          // image rows (of the N*H row space) per CTA
+};
+
+constexpr int kWgTile = 64, kWgPix = 32;
+
+__global__ void __launch_bounds__(256) wgrad_kernel(const WgradParams p) {
+  __shared__ float sA[kWgPix][kWgTile + 1];
+  __shared__ float sZ[kWgPix][kWgTile + 1];
+  const int taps = p.ksz * p.ksz, half = p.ksz >> 1;
+  const int ci_tiles = (p.cin + kWgTile - 1) / kWgTile, co_tiles = (p.cout + kWgTile - 1) / kWgTile;
+  int b = blockIdx.x;
+  const int co_t = b % co_tiles; b /= co_tiles;
+  const int ci_t = b % ci_tiles; b /= ci_tiles;
+  const int tap = b % taps; b /= taps;
+  const int row0 = b * p.rows_per_block;
+  const int total_rows = p.n_img * p.H;
+  const int row1 = row0 + p.rows_per_block < total_rows ? row0 + p.rows_per_block : total_rows;
+  const int dy = tap / p.ksz - half, dx = tap % p.ksz - half;
+  const int ci0 = ci_t * kWgTile, co0 = co_t * kWgTile;
+  const int tci = (threadIdx.x >> 4) * 4, tco = (threadIdx.x & 15) * 4;   // 16 x 16 threads, 4 x 4 each
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int row = row0; row < row1; ++row) {
+    const int y = row % p.H, img = row / p.H;
+    const int yy = y + dy;
+    if (yy < 0 || yy >= p.H) continue;   // warp-uniform (whole CTA)
+    for (int x0 = 0; x0 < p.W; x0 += kWgPix) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < kWgPix * kWgTile; i += blockDim.x) {
+        const int c = i % kWgTile, px = i / kWgTile;
+        const int x = x0 + px, xx = x + dx;
+        float va = 0.f, vz = 0.f;
+        if (x < p.W) {
+          const size_t q = ((size_t)img * p.H + y) * p.W + x;
+          if (co0 + c < p.cout) vz = load_planes(p.dz_hi, p.dz_lo, q * p.dz_pitch + co0 + c);
+          if (xx >= 0 && xx < p.W && ci0 + c < p.cin) {
+            const size_t qa = ((size_t)img * p.H + yy) * p.W + xx;
+            const int pos = p.in_map ? __ldg(p.in_map + ci0 + c) : ci0 + c;
+            va = p.a_f32 ? __ldg(p.a_f32 + qa * p.a_pitch + pos) : load_planes(p.a_hi, p.a_lo, qa * p.a_pitch + pos);
+          }
+        }
+        sA[px][c] = va;
+        sZ[px][c] = vz;
+      }
+      __syncthreads();
+#pragma unroll 4
+      for (int px = 0; px < kWgPix; ++px) {
+        float a[4], z[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = sA[px][tci + i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) z[j] = sZ[px][tco + j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], z[j], acc[i][j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ci = ci0 + tci + i, co = co0 + tco + j;
+      if (ci < p.cin && co < p.cout && acc[i][j] != 0.f) atomicAdd(p.dW + ((size_t)tap * p.cin + ci) * p.cout + co, acc[i][j]);
+    }
+}
+
+// per-channel sum of a plane tensor (bias gradient of layers without activation)
+struct ColSumParams {
+  size_t pixels; int C; const __half *hi, *lo; int pitch; float* out; int px_per_block;
+};
+__global__ void __launch_bounds__(256) colsum_kernel(const ColSumParams p) {
+  const size_t q0 = (size_t)blockIdx.x * p.px_per_block;
+  const size_t q1 = q0 + p.px_per_block < p.pixels ? q0 + p.px_per_block : p.pixels;
+  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+    float s = 0.f;
+    for (size_t q = q0; q < q1; ++q) s += load_planes(p.hi, p.lo, q * p.pitch + c);
+    atomicAdd(p.out + c, s);
+  }
+}
+
+// ------------------------------------------------------------------------------- clip + Adam (flat buffers) ----
+// g = grad / grad_scale (+ l2_decay * w for conv filters: d/dw of l2_decay * sum(w^2)/2, DCSCN.py:350-351);
+// norm^2 over ALL trainables (tf.clip_by_global_norm, DCSCN.py:407).
+struct GradFinalizeParams {
+  float* grad; const float* w; const uint8_t* is_filter; size_t count; float inv_scale; float l2_decay; double* norm_sq;
+};
+__global__ void __launch_bounds__(256) grad_finalize_kernel(const GradFinalizeParams p) {
+  double acc = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.count; i += (size_t)gridDim.x * blockDim.x) {
+    float g = p.grad[i] * p.inv_scale;
+    if (p.is_filter[i]) g = fmaf(p.l2_decay, p.w[i], g);
+    p.grad[i] = g;
+    acc += (double)g * (double)g;
+  }
+  __shared__ double s[256];
+  s[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) atomicAdd(p.norm_sq, s[0]);
+}
+
+// tf.train.AdamOptimizer (DCSCN.py:388): m = b1*m + (1-b1)*g; v = b2*v + (1-b2)*g*g; w -= lr_t * m / (sqrt(v) + eps),
+// lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t) (host), g = clipped gradient = g * clip / max(norm, clip).
+struct AdamParams {
+  float* w; float* m; float* v; const float* grad; size_t count;
+  const double* norm_sq; float clip; float lr_t, beta1, beta2, eps;
+};
+__global__ void __launch_bounds__(256) adam_kernel(const AdamParams p) {
+  float cscale = 1.f;
+  if (p.clip > 0.f) {
+    const float norm = (float)sqrt(*p.norm_sq);
+    cscale = p.clip / fmaxf(norm, p.clip);
+  }
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.count; i += (size_t)gridDim.x * blockDim.x) {
+    const float g = p.grad[i] * cscale;
+    const float m = p.beta1 * p.m[i] + (1.f - p.beta1) * g;
+    const float v = p.beta2 * p.v[i] + (1.f - p.beta2) * g * g;
+    p.m[i] = m;
+    p.v[i] = v;
+    p.w[i] -= p.lr_t * m / (sqrtf(v) + p.eps);
+  }
+}
+
+}  // namespace dcscn

@@ -42,6 +42,8 @@ def main():
         ("dcscn_L7_F32to8_G1.20_NIN_A24_B8_PS_R1F32", [(48, 48), (48, 48), (48, 48)], 4),
         ("dcscn_L7_F32to8_G1.20_Sc3_NIN_A24_B8_PS_R1F32", [(20, 33)], 5),
         ("dcscn_L7_F32to8_G1.20_Sc4_NIN_A24_B8_PS_R1F32", [(17, 16)], 6),
+        ("dcscn_L7_F32to8_G1.20_Sc4_NIN_A24_B8_PS_DS_R1F32", [(48, 48), (48, 48)], 7),
+        ("dcscn_L7_F32to8_G1.20_Sc4_NIN_A24_B8_PS_DS_R1F32", [(13, 70)], 8),
     ]
     for ci, (model, sizes, seed) in enumerate(cases):
         kw = MODEL_FLAGS[model]

@@ -118,7 +118,7 @@ def golden_cases():
     return d, n
 
 
-@pytest.mark.parametrize("ci", range(6))
+@pytest.mark.parametrize("ci", range(8))
 def test_golden_vectors(ci):
     """Committed fp64-oracle outputs for Set5 crops through the reference's own checkpoints."""
     d, n = golden_cases()
@@ -130,6 +130,28 @@ def test_golden_vectors(ci):
     eng.close()
     err = float(np.abs(y - y64).max())
     assert err <= TOL, (model, err)
+
+
+def test_depthwise_separable_every_layer():
+    """BASELINE configs[4]: the DS c-DCSCN x4 checkpoint (fused depthwise+pointwise CUDA-core kernels)."""
+    model = "dcscn_L7_F32to8_G1.20_Sc4_NIN_A24_B8_PS_DS_R1F32"
+    kw = MODEL_FLAGS[model]
+    w = load_golden_weights(model)
+    cfg = O.OracleConfig(**kw)
+    g = torch.Generator().manual_seed(3)
+    x = (torch.rand(3, 48, 48, 1, generator=g) * 255).numpy()
+    x2 = (torch.rand(3, 192, 192, 1, generator=g) * 255).numpy()
+    y64, inter = O.Oracle(cfg, w, torch.float64).forward(x.astype(np.float64), x2.astype(np.float64),
+                                                         return_intermediates=True)
+    eng = make_engine(kw, w)
+    y = gpu_forward(eng, x, x2)
+    assert np.abs(y - y64).max() <= TOL
+    for name, ref in inter.items():
+        if name == "R-CNN":
+            continue
+        a = eng.get_activation(name, ref.shape)
+        assert np.abs(a - ref).max() <= 2e-6 * max(1.0, np.abs(ref).max()) + 1e-4, name
+    eng.close()
 
 
 def test_l12_stress_noise_tiles():

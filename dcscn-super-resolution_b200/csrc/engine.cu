@@ -24,6 +24,7 @@
 #include "conv_tc_halo.cuh"
 #include "conv_tc_halo1.cuh"
 #include "conv_ds.cuh"
+#include "train.cuh"
 
 using namespace dcscn;
 
@@ -121,6 +122,8 @@ struct Plan {
   TcLaunch unfused;              // same layer with the plain depth_to_space epilogue (validation path)
   ConvGatherParams gather;
   bool ran_fused = false;
+  std::vector<TcLaunch> bwd;     // dgrad launches (built lazily by the train step)
+  bool bwd_built = false;
 };
 
 struct dcscn_handle {
@@ -141,6 +144,9 @@ struct dcscn_handle {
 
   // packed layers
   std::vector<TcLayer> tcl;          // CNN2..CNNL, A1+B1, B2, Up-PS [, Up-PS2]
+  std::vector<TcLayer> bwd;          // data-gradient twins (transposed, flipped filters), see build_bwd_layers
+  bool train_enabled = false;
+  struct TrainState* train = nullptr;
   float* d_first_w = nullptr;        // CNN1 [taps][n_pad]
   float* d_first_bias = nullptr;
   float* d_first_alpha = nullptr;
@@ -276,15 +282,36 @@ static const std::vector<float>& P(const dcscn_handle* h, const std::string& nam
 }
 
 // ------------------------------------------------------------------------------ weight packing ----
+// Device copies of host vectors.  Re-uploading the same number of bytes reuses the allocation, so cached launch
+// plans (which embed these pointers) stay valid across weight updates; `g_upload_realloc` records when that failed.
+static std::map<void*, size_t> g_upload_bytes;
+static bool g_upload_realloc = false;
+
+static void dev_free(void* p) {
+  if (!p) return;
+  g_upload_bytes.erase(p);
+  cudaFree(p);
+}
+
 template <typename T>
 static int upload(T** dptr, const std::vector<T>& host, dcscn_handle* h) {
+  (void)h;
+  const size_t bytes = host.size() * sizeof(T);
   if (*dptr) {
-    cudaFree(*dptr);
+    auto it = g_upload_bytes.find((void*)*dptr);
+    if (it != g_upload_bytes.end() && it->second == bytes && bytes > 0) {
+      CUDA_TRY(cudaMemcpy(*dptr, host.data(), bytes, cudaMemcpyHostToDevice));
+      return 0;
+    }
+    dev_free(*dptr);
     *dptr = nullptr;
+    g_upload_realloc = true;
   }
   if (host.empty()) return 0;
-  CUDA_TRY(cudaMalloc((void**)dptr, host.size() * sizeof(T)));
-  CUDA_TRY(cudaMemcpy(*dptr, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMalloc((void**)dptr, bytes));
+  g_upload_bytes[(void*)*dptr] = bytes;
+  g_upload_realloc = true;
+  CUDA_TRY(cudaMemcpy(*dptr, host.data(), bytes, cudaMemcpyHostToDevice));
   return 0;
 }
 
@@ -423,16 +450,20 @@ static TcLayer make_tc(const std::string& name, int ksz, int cin, int cout_cols,
 }
 
 static void free_tc(TcLayer& t) {
-  cudaFree(t.d_wpack);
-  cudaFree(t.d_wpair);
-  t.d_wpair = nullptr;
-  cudaFree(t.d_bias);
-  cudaFree(t.d_alpha);
-  cudaFree(t.d_wref);
-  cudaFree(t.d_in_map);
-  t.d_wpack = nullptr;
+  dev_free(t.d_wpack);
+  dev_free(t.d_wpair);
+  dev_free(t.d_bias);
+  dev_free(t.d_alpha);
+  dev_free(t.d_wref);
+  dev_free(t.d_in_map);
+  t.d_wpack = t.d_wpair = nullptr;
   t.d_bias = t.d_alpha = t.d_wref = nullptr;
   t.d_in_map = nullptr;
+}
+
+static void adopt_tc(TcLayer& t, const TcLayer& old) {  // keep the device allocations of the previous packing
+  t.d_wpack = old.d_wpack; t.d_wpair = old.d_wpair; t.d_bias = old.d_bias; t.d_alpha = old.d_alpha;
+  t.d_wref = old.d_wref; t.d_in_map = old.d_in_map;
 }
 
 // (Re)builds every device-side weight image from the host fp32 parameters.
@@ -460,13 +491,16 @@ static int finalize_params_ds(dcscn_handle* h) {
   return 0;
 }
 
+static int build_bwd_layers(dcscn_handle* h);
+
 static int finalize_params(dcscn_handle* h) {
   const dcscn_config& c = h->cfg;
   if (c.depthwise_separable) return finalize_params_ds(h);
-  for (TcLayer& t : h->tcl) free_tc(t);
+  std::vector<TcLayer> old_tcl = std::move(h->tcl);
+  std::vector<TcLayer> old_bwd = std::move(h->bwd);
   h->tcl.clear();
-  h->plans.clear();
-  h->last_plan = nullptr;
+  h->bwd.clear();
+  g_upload_realloc = false;
   const int L = c.layers;
 
   // CNN1 (CUDA cores)
@@ -529,8 +563,17 @@ static int finalize_params(dcscn_handle* h) {
       h->tcl.push_back(std::move(t2));
     }
   }
-  for (TcLayer& t : h->tcl)
-    if (pack_tc_layer(h, t)) return 1;
+  if (h->train_enabled && build_bwd_layers(h)) return 1;
+  for (size_t i = 0; i < h->tcl.size(); ++i) {
+    if (i < old_tcl.size()) adopt_tc(h->tcl[i], old_tcl[i]);
+    if (pack_tc_layer(h, h->tcl[i])) return 1;
+  }
+  for (size_t i = h->tcl.size(); i < old_tcl.size(); ++i) free_tc(old_tcl[i]);
+  for (size_t i = 0; i < h->bwd.size(); ++i) {
+    if (i < old_bwd.size()) adopt_tc(h->bwd[i], old_bwd[i]);
+    if (pack_tc_layer(h, h->bwd[i])) return 1;
+  }
+  for (size_t i = h->bwd.size(); i < old_bwd.size(); ++i) free_tc(old_bwd[i]);
   // R-CNN1 (CUDA cores): [taps][C]
   {
     const LayerDef* l = find_layer(h, "R-CNN1");
@@ -538,6 +581,10 @@ static int finalize_params(dcscn_handle* h) {
     std::vector<float> w(W.begin(), W.end());
     (void)l;
     if (upload(&h->d_last_w, w, h)) return 1;
+  }
+  if (g_upload_realloc) {  // some device pointer moved: cached plans embed stale pointers
+    h->plans.clear();
+    h->last_plan = nullptr;
   }
   h->params_dirty = false;
   return 0;
@@ -1146,6 +1193,8 @@ static int forward_impl(dcscn_handle* h, const float* x, const float* x2, float*
   return 0;
 }
 
+#include "train_engine.inc"
+
 // --------------------------------------------------------------------------------------- C ABI ----
 extern "C" {
 
@@ -1184,6 +1233,8 @@ int dcscn_destroy(dcscn_handle* h) {
   cudaSetDevice(h->cfg.device_id);
   cudaDeviceSynchronize();
   for (TcLayer& t : h->tcl) free_tc(t);
+  for (TcLayer& t : h->bwd) free_tc(t);
+  train_free(h);
   cudaFree(h->d_first_w);
   cudaFree(h->d_first_bias);
   cudaFree(h->d_first_alpha);
@@ -1227,6 +1278,7 @@ int dcscn_set_param(dcscn_handle* h, const char* name, const float* host_data, i
   if (numel != p.numel()) return fail("dcscn_set_param: '%s' has %lld elements, got %lld", name, (long long)p.numel(), (long long)numel);
   memcpy(p.host.data(), host_data, (size_t)numel * sizeof(float));
   h->params_dirty = true;
+  if (h->train) h->train->w_synced = false;
   return 0;
 }
 
@@ -1406,6 +1458,83 @@ int dcscn_get_timings(dcscn_handle* h, float* ms, int capacity, int* count, char
     }
     snprintf(names, names_len, "%s", s.c_str());
   }
+  return 0;
+}
+
+int dcscn_train_step(dcscn_handle* h, const float* x_dev, const float* x2_dev, const float* y_dev, int n, int height, int width,
+                     float lr, uint32_t seed, int apply_update, float* out_loss, float* out_mse, void* stream) {
+  if (!h || !x_dev || !x2_dev || !y_dev) return fail("dcscn_train_step: null argument");
+  return train_step_impl(h, x_dev, x2_dev, y_dev, n, height, width, lr, seed, apply_update, out_loss, out_mse, (cudaStream_t)stream);
+}
+
+int dcscn_train_step_host(dcscn_handle* h, const float* x, const float* x2, const float* y, int n, int height, int width, float lr,
+                          uint32_t seed, int apply_update, float* out_loss, float* out_mse) {
+  if (!h || !x || !x2 || !y) return fail("dcscn_train_step_host: null argument");
+  CUDA_TRY(cudaSetDevice(h->cfg.device_id));
+  const size_t lr_px = (size_t)n * height * width;
+  const size_t hr_px = lr_px * h->cfg.scale * h->cfg.scale;
+  if (hr_px > h->io_cap) {
+    cudaFree(h->io_x); cudaFree(h->io_x2); cudaFree(h->io_y);
+    h->io_x = h->io_x2 = h->io_y = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&h->io_x, lr_px * sizeof(float)));
+    CUDA_TRY(cudaMalloc((void**)&h->io_x2, hr_px * sizeof(float)));
+    CUDA_TRY(cudaMalloc((void**)&h->io_y, hr_px * sizeof(float)));
+    h->io_cap = hr_px;
+  }
+  cudaStream_t st = 0;
+  CUDA_TRY(cudaMemcpyAsync(h->io_x, x, lr_px * sizeof(float), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(h->io_x2, x2, hr_px * sizeof(float), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(h->io_y, y, hr_px * sizeof(float), cudaMemcpyHostToDevice, st));
+  return train_step_impl(h, h->io_x, h->io_x2, h->io_y, n, height, width, lr, seed, apply_update, out_loss, out_mse, st);
+}
+
+int dcscn_get_grad(dcscn_handle* h, const char* name, float* host_data, int64_t numel) {
+  if (!h || !name || !host_data) return fail("dcscn_get_grad: null argument");
+  if (!h->train || h->train->total == 0) return fail("dcscn_get_grad: no train step has run yet");
+  auto it = h->param_index.find(name);
+  if (it == h->param_index.end()) return fail("dcscn_get_grad: unknown variable '%s'", name);
+  const ParamDef& p = h->params[it->second];
+  if (numel != p.numel()) return fail("dcscn_get_grad: '%s' has %lld elements, got %lld", name, (long long)p.numel(), (long long)numel);
+  CUDA_TRY(cudaSetDevice(h->cfg.device_id));
+  CUDA_TRY(cudaMemcpy(host_data, h->train->d_g + h->train->off[it->second], (size_t)numel * sizeof(float), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int dcscn_get_adam_slot(dcscn_handle* h, const char* name, int slot, float* host_data, int64_t numel) {
+  if (!h || !name || !host_data) return fail("dcscn_get_adam_slot: null argument");
+  if (!h->train || h->train->total == 0) return fail("dcscn_get_adam_slot: no train step has run yet");
+  auto it = h->param_index.find(name);
+  if (it == h->param_index.end()) return fail("dcscn_get_adam_slot: unknown variable '%s'", name);
+  const ParamDef& p = h->params[it->second];
+  if (numel != p.numel() || (slot != 0 && slot != 1)) return fail("dcscn_get_adam_slot: bad size or slot");
+  CUDA_TRY(cudaSetDevice(h->cfg.device_id));
+  const float* src = (slot == 0 ? h->train->d_m : h->train->d_v) + h->train->off[it->second];
+  CUDA_TRY(cudaMemcpy(host_data, src, (size_t)numel * sizeof(float), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+float dcscn_last_grad_norm(dcscn_handle* h) { return (h && h->train) ? h->train->last_norm : 0.f; }
+
+int dcscn_dropout_mask(dcscn_handle* h, const char* tensor, uint32_t seed, int n, int height, int width, uint8_t* mask, int64_t numel) {
+  if (!h || !tensor || !mask) return fail("dcscn_dropout_mask: null argument");
+  const dcscn_config& c = h->cfg;
+  const std::string t(tensor);
+  const int L = c.layers;
+  int C = 0, n_total = 0, col0 = 0;
+  uint32_t layer = 0;
+  if (t.rfind("CNN", 0) == 0) {
+    const int i = atoi(t.c_str() + 3) - 1;
+    if (i < 0 || i >= L) return fail("dcscn_dropout_mask: no tensor '%s'", tensor);
+    C = h->filters[i]; n_total = h->feat_w[i]; col0 = 0; layer = (uint32_t)(i + 1);
+  } else if (t == "A1") { C = c.nin_filters; n_total = h->a1_w + h->b1_w; col0 = 0; layer = (uint32_t)(L + 1);
+  } else if (t == "B1") { C = c.nin_filters2; n_total = h->a1_w + h->b1_w; col0 = h->a1_w; layer = (uint32_t)(L + 1);
+  } else if (t == "B2") { C = c.nin_filters2; n_total = h->b1_w; col0 = 0; layer = (uint32_t)(L + 2);
+  } else return fail("dcscn_dropout_mask: tensor '%s' has no dropout", tensor);
+  const size_t px = (size_t)n * height * width;
+  if (numel != (int64_t)(px * C)) return fail("dcscn_dropout_mask: expected %lld elements", (long long)(px * C));
+  for (size_t q = 0; q < px; ++q)
+    for (int k = 0; k < C; ++k)
+      mask[q * C + k] = dropout_keep(seed, layer, (uint64_t)q * (uint64_t)n_total + col0 + k, c.dropout_keep) ? 1 : 0;
   return 0;
 }
 

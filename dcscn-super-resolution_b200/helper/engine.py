@@ -52,6 +52,8 @@ EXPORTED_SYMBOLS = [
     "dcscn_create", "dcscn_destroy", "dcscn_last_error", "dcscn_num_params", "dcscn_param_info",
     "dcscn_set_param", "dcscn_get_param", "dcscn_forward", "dcscn_forward_host", "dcscn_get_activation",
     "dcscn_set_option", "dcscn_get_timings", "dcscn_launch_count", "dcscn_device_bytes",
+    "dcscn_train_step", "dcscn_train_step_host", "dcscn_get_grad", "dcscn_get_adam_slot", "dcscn_last_grad_norm",
+    "dcscn_dropout_mask",
 ]
 
 _lib = None
@@ -85,6 +87,14 @@ def load_library(path=None):
     lib.dcscn_get_activation.argtypes = [vp, ctypes.c_char_p, fp, c64]
     lib.dcscn_set_option.argtypes = [vp, ctypes.c_char_p, c64]
     lib.dcscn_get_timings.argtypes = [vp, fp, ci, ctypes.POINTER(ci), ctypes.c_char_p, ci]
+    u32, cf = ctypes.c_uint32, ctypes.c_float
+    lib.dcscn_train_step.argtypes = [vp, vp, vp, vp, ci, ci, ci, cf, u32, ci, fp, fp, vp]
+    lib.dcscn_train_step_host.argtypes = [vp, vp, vp, vp, ci, ci, ci, cf, u32, ci, fp, fp]
+    lib.dcscn_get_grad.argtypes = [vp, ctypes.c_char_p, fp, c64]
+    lib.dcscn_get_adam_slot.argtypes = [vp, ctypes.c_char_p, ci, fp, c64]
+    lib.dcscn_last_grad_norm.argtypes = [vp]
+    lib.dcscn_last_grad_norm.restype = cf
+    lib.dcscn_dropout_mask.argtypes = [vp, ctypes.c_char_p, u32, ci, ci, ci, ctypes.POINTER(ctypes.c_uint8), c64]
     lib.dcscn_launch_count.argtypes = [vp]
     lib.dcscn_launch_count.restype = c64
     lib.dcscn_device_bytes.argtypes = [vp]
@@ -195,6 +205,51 @@ class Engine:
         ya = _host_array(y)
         self._check(self.lib.dcscn_forward_host(self.handle, xa.ctypes.data, x2a.ctypes.data, ya.ctypes.data, n, h, w))
         return y
+
+    def train_step_host(self, x, x2, y, lr, seed, apply_update=True):
+        """One optimisation step on host fp32 arrays x [n,h,w,1], x2 / y [n,sh,sw,1]; returns (image_loss, mse)."""
+        xa, x2a, ya = _host_array(x), _host_array(x2), _host_array(y)
+        n, h, w = xa.shape[0], xa.shape[1], xa.shape[2]
+        s = self.config.scale
+        assert tuple(x2a.shape[:3]) == (n, s * h, s * w) and tuple(ya.shape[:3]) == (n, s * h, s * w)
+        loss, mse = ctypes.c_float(), ctypes.c_float()
+        self._check(self.lib.dcscn_train_step_host(self.handle, xa.ctypes.data, x2a.ctypes.data, ya.ctypes.data, n, h, w,
+                                                   float(lr), int(seed) & 0xFFFFFFFF, int(bool(apply_update)),
+                                                   ctypes.byref(loss), ctypes.byref(mse)))
+        return float(loss.value), float(mse.value)
+
+    def train_step(self, x, x2, y, lr, seed, apply_update=True, stream=None):
+        """Same with contiguous fp32 CUDA torch tensors."""
+        import torch
+        n, h, w = int(x.shape[0]), int(x.shape[1]), int(x.shape[2])
+        assert x.is_cuda and x2.is_cuda and y.is_cuda and x.is_contiguous() and x2.is_contiguous() and y.is_contiguous()
+        st = stream if stream is not None else torch.cuda.current_stream(x.device).cuda_stream
+        loss, mse = ctypes.c_float(), ctypes.c_float()
+        self._check(self.lib.dcscn_train_step(self.handle, x.data_ptr(), x2.data_ptr(), y.data_ptr(), n, h, w, float(lr),
+                                              int(seed) & 0xFFFFFFFF, int(bool(apply_update)), ctypes.byref(loss),
+                                              ctypes.byref(mse), ctypes.c_void_p(st)))
+        return float(loss.value), float(mse.value)
+
+    def get_grad(self, name):
+        a = np.empty(self.param_shapes()[name], dtype=np.float32)
+        self._check(self.lib.dcscn_get_grad(self.handle, name.encode(), a.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), a.size))
+        return a
+
+    def get_adam_slot(self, name, slot):
+        a = np.empty(self.param_shapes()[name], dtype=np.float32)
+        self._check(self.lib.dcscn_get_adam_slot(self.handle, name.encode(), slot,
+                                                 a.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), a.size))
+        return a
+
+    @property
+    def last_grad_norm(self):
+        return float(self.lib.dcscn_last_grad_norm(self.handle))
+
+    def dropout_mask(self, tensor, seed, n, h, w, channels):
+        a = np.empty((n, h, w, channels), dtype=np.uint8)
+        self._check(self.lib.dcscn_dropout_mask(self.handle, tensor.encode(), int(seed) & 0xFFFFFFFF, n, h, w,
+                                                a.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), a.size))
+        return a
 
     def get_activation(self, tensor, shape):
         a = np.empty(shape, dtype=np.float32)

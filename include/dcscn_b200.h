@@ -83,6 +83,28 @@ int dcscn_forward(dcscn_handle* h, const float* x_dev, const float* x2_dev, floa
 int dcscn_forward_host(dcscn_handle* h, const float* x, const float* x2, float* y, int n, int height, int width);
 
 /*
+ * sess.run([self.training_optimizer, self.image_loss, self.mse], {x, x2, y, lr, dropout: keep, is_training: 1})
+ * (DCSCN.py:415-425; graph: build_optimizer / add_optimizer_op, DCSCN.py:334-413): forward with inverted dropout
+ * (keep = cfg.dropout_keep, masks from a counter hash of `seed`), mse loss + l2_decay * sum(l2_loss(conv_W)),
+ * gradients of every variable, tf.clip_by_global_norm(cfg.clipping_norm), TF-Adam with learning rate `lr`.
+ * `apply_update` = 0 computes loss and gradients only (dcscn_get_grad), leaving the weights untouched.
+ * x / x2 / y are DEVICE pointers (dcscn_train_step) or HOST pointers (dcscn_train_step_host); both synchronise.
+ */
+int dcscn_train_step(dcscn_handle* h, const float* x_dev, const float* x2_dev, const float* y_dev, int n, int height, int width,
+                     float lr, uint32_t seed, int apply_update, float* out_loss, float* out_mse, void* stream);
+int dcscn_train_step_host(dcscn_handle* h, const float* x, const float* x2, const float* y, int n, int height, int width, float lr,
+                          uint32_t seed, int apply_update, float* out_loss, float* out_mse);
+/* d loss / d variable of the LAST train step (after the L2 term, before clipping): tf.gradients(loss, trainables). */
+int dcscn_get_grad(dcscn_handle* h, const char* name, float* host_data, int64_t numel);
+/* Adam slots of a variable ("<var>/Adam" = slot 0, "<var>/Adam_1" = slot 1 in the reference's checkpoints). */
+int dcscn_get_adam_slot(dcscn_handle* h, const char* name, int slot, float* host_data, int64_t numel);
+/* Global gradient norm of the last train step (what clip_by_global_norm computed). */
+float dcscn_last_grad_norm(dcscn_handle* h);
+/* The keep mask (1 = kept) the train step with `seed` applies to `tensor` ("CNNi", "A1", "B1", "B2"), [n,h,w,C] uint8:
+ * lets a CPU oracle replay the exact same dropout. */
+int dcscn_dropout_mask(dcscn_handle* h, const char* tensor, uint32_t seed, int n, int height, int width, uint8_t* mask, int64_t numel);
+
+/*
  * Parity / debug: output of one layer of the LAST forward as fp32 NHWC [n, H_l, W_l, cout_l]
  * (`tensor` is the reference's self.H entry: "CNN1".."CNNL", "A1", "B1", "B2", "Up-PS", "Up-PS2").
  */

@@ -1,0 +1,88 @@
+"""GPU parity of the train step (loss, every gradient, global-norm clip, TF-Adam) against the fp64 CPU oracle
+(torch autograd of the restated graph, oracle/dcscn_oracle.py).  The oracle replays the engine's dropout masks
+(dcscn_dropout_mask), so the comparison is exact up to fp32-level rounding.  Tolerance: 2e-3 of each gradient
+tensor's max magnitude (data gradients run on the fp16x3 tensor-core path, filter gradients are fp32 atomics)."""
+import numpy as np
+import pytest
+import torch
+
+import dcscn_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+SMALL = dict(scale=2, layers=3, filters=24, min_filters=16, filters_decay_gamma=1.5, nin_filters=16, nin_filters2=16)
+SMALL4 = dict(scale=4, layers=3, filters=20, min_filters=16, filters_decay_gamma=1.5, nin_filters=16, nin_filters2=16)
+
+
+def setup(kw, keep, n, h, w, seed=0):
+    from helper import engine as E
+    cfg = O.OracleConfig(**kw)
+    wts = {k: v.astype(np.float64) for k, v in O.he_init_weights(cfg, seed=seed).items()}
+    eng = E.Engine(E.make_config(dropout_keep=keep, **kw))
+    eng.set_params({k: v.astype(np.float32) for k, v in wts.items()})
+    g = np.random.RandomState(seed + 1)
+    s = cfg.scale
+    x = (g.rand(n, h, w, 1) * 255).astype(np.float32)
+    x2 = (g.rand(n, s * h, s * w, 1) * 255).astype(np.float32)
+    y = np.clip(x2 + g.randn(n, s * h, s * w, 1) * 10, 0, 255).astype(np.float32)
+    return cfg, wts, eng, x, x2, y
+
+
+def oracle_masks(eng, cfg, seed, n, h, w):
+    masks = {}
+    for scope, k, cin, cout, bias, prelu in O.layer_table(cfg):
+        if prelu:
+            m = eng.dropout_mask(scope, seed, n, h, w, cout)
+            masks[scope] = np.ascontiguousarray(m.transpose(0, 3, 1, 2)).astype(np.float64)
+    return masks
+
+
+@pytest.mark.parametrize("kw,keep,shape", [(SMALL, 1.0, (2, 12, 10)), (SMALL, 0.8, (2, 16, 24)), (SMALL4, 0.8, (1, 9, 11))],
+                         ids=["x2-nodrop", "x2-drop", "x4-drop"])
+def test_gradients_match_oracle(kw, keep, shape):
+    n, h, w = shape
+    cfg, wts, eng, x, x2, y = setup(kw, keep, n, h, w)
+    seed = 1234
+    loss, mse = eng.train_step_host(x, x2, y, lr=0.002, seed=seed, apply_update=False)
+    orc = O.Oracle(cfg, wts, torch.float64)
+    masks = oracle_masks(eng, cfg, seed, n, h, w) if keep < 1.0 else None
+    mse_ref, loss_ref, grads_ref = orc.loss_and_grads(x.astype(np.float64), x2.astype(np.float64), y.astype(np.float64),
+                                                      keep_prob=keep, masks=masks)
+    assert mse == pytest.approx(mse_ref, rel=2e-5)
+    assert loss == pytest.approx(mse_ref, rel=2e-5)          # image_loss == mse (DCSCN.py:346-347)
+    norm_ref = np.sqrt(sum(np.sum(v ** 2) for v in grads_ref.values()))
+    assert eng.last_grad_norm == pytest.approx(norm_ref, rel=2e-3)
+    for name, gref in grads_ref.items():
+        g = eng.get_grad(name)
+        tol = 2e-3 * np.abs(gref).max() + 1e-7
+        assert np.abs(g - gref).max() <= tol, (name, float(np.abs(g - gref).max()), float(np.abs(gref).max()))
+    eng.close()
+
+
+def test_adam_step_matches_oracle_and_loss_decreases():
+    n, h, w = 2, 16, 16
+    cfg, wts, eng, x, x2, y = setup(SMALL, 0.8, n, h, w, seed=3)
+    orc = O.Oracle(cfg, wts, torch.float64)
+    m = {k: np.zeros_like(v) for k, v in wts.items()}
+    v = {k: np.zeros_like(v_) for k, v_ in wts.items()}
+    losses = []
+    for step in range(1, 4):
+        seed = 100 + step
+        loss, mse = eng.train_step_host(x, x2, y, lr=0.002, seed=seed)
+        losses.append(mse)
+        masks = oracle_masks(eng, cfg, seed, n, h, w)
+        _, _, grads = orc.loss_and_grads(x.astype(np.float64), x2.astype(np.float64), y.astype(np.float64), keep_prob=0.8, masks=masks)
+        clipped, _ = orc.clip_by_global_norm(grads)
+        orc.adam_step(clipped, m, v, step, 0.002)
+        for name in wts:
+            got = eng.get_param(name)
+            assert np.abs(got - orc.w[name]).max() <= 2e-3 * 0.002 * step + 2e-6 * np.abs(orc.w[name]).max(), (step, name)
+    # slots follow the reference's checkpoint convention (<var>/Adam, <var>/Adam_1)
+    np.testing.assert_allclose(eng.get_adam_slot("CNN1/conv_W", 0), m["CNN1/conv_W"], rtol=0, atol=3e-3 * np.abs(m["CNN1/conv_W"]).max())
+    # the forward pass uses the updated weights (re-packed tensor-core operand images)
+    yy = eng.forward_host(x, x2)
+    ref = O.Oracle(cfg, {k: a.astype(np.float64) for k, a in orc.w.items()}, torch.float64).forward(x.astype(np.float64), x2.astype(np.float64))
+    assert np.abs(yy - ref).max() <= 5e-3
+    more = [eng.train_step_host(x, x2, y, lr=0.002, seed=200 + i)[1] for i in range(30)]
+    assert np.mean(more[-5:]) < losses[0]
+    eng.close()

@@ -351,10 +351,15 @@ class SuperResolution:
     # ------------------------------------------------------------------ training ----
     def train_batch(self):
         """DCSCN.py:415-425: one optimisation step on the current mini-batch."""
-        x = np.ascontiguousarray(np.stack(self.batch_input), dtype=np.float32)
-        x2 = np.ascontiguousarray(np.stack(self.batch_input_bicubic), dtype=np.float32)
-        y = np.ascontiguousarray(np.stack(self.batch_true), dtype=np.float32)
-        image_loss, mse = self.engine.train_step_host(x, x2, y, lr=self.lr, seed=self.step)
+        # data parallel: rank r of a torch.distributed job trains on patches r, r + world, ... of the mini-batch; the
+        # gradients meet in one flat all-reduce before the (identical) clip + Adam update on every rank
+        rank, world = _dist_rank_world()
+        x = np.ascontiguousarray(np.stack(self.batch_input[rank::world]), dtype=np.float32)
+        x2 = np.ascontiguousarray(np.stack(self.batch_input_bicubic[rank::world]), dtype=np.float32)
+        y = np.ascontiguousarray(np.stack(self.batch_true[rank::world]), dtype=np.float32)
+        if x.ndim == 3:
+            x, x2, y = x[..., None], x2[..., None], y[..., None]
+        image_loss, mse = self.engine.train_step_data_parallel(x, x2, y, lr=self.lr, seed=self.step * world + rank)
         self.training_loss_sum += image_loss
         self.training_psnr_sum += util.get_psnr(mse, max_value=self.max_value)
         self.training_step += 1

@@ -1513,6 +1513,20 @@ int dcscn_get_adam_slot(dcscn_handle* h, const char* name, int slot, float* host
   return 0;
 }
 
+int dcscn_grad_buffer(dcscn_handle* h, float** dev_ptr, int64_t* count) {
+  if (!h || !dev_ptr || !count) return fail("dcscn_grad_buffer: null argument");
+  if (!h->train || h->train->total == 0) return fail("dcscn_grad_buffer: no train step has run yet");
+  *dev_ptr = h->train->d_g;
+  *count = (int64_t)h->train->total;
+  return 0;
+}
+
+int dcscn_apply_gradients(dcscn_handle* h, float lr, void* stream) {
+  if (!h) return fail("dcscn_apply_gradients: null argument");
+  CUDA_TRY(cudaSetDevice(h->cfg.device_id));
+  return apply_gradients_impl(h, lr, true, (cudaStream_t)stream);
+}
+
 float dcscn_last_grad_norm(dcscn_handle* h) { return (h && h->train) ? h->train->last_norm : 0.f; }
 
 int dcscn_dropout_mask(dcscn_handle* h, const char* tensor, uint32_t seed, int n, int height, int width, uint8_t* mask, int64_t numel) {

@@ -53,7 +53,7 @@ EXPORTED_SYMBOLS = [
     "dcscn_set_param", "dcscn_get_param", "dcscn_forward", "dcscn_forward_host", "dcscn_get_activation",
     "dcscn_set_option", "dcscn_get_timings", "dcscn_launch_count", "dcscn_device_bytes",
     "dcscn_train_step", "dcscn_train_step_host", "dcscn_get_grad", "dcscn_get_adam_slot", "dcscn_last_grad_norm",
-    "dcscn_dropout_mask",
+    "dcscn_dropout_mask", "dcscn_grad_buffer", "dcscn_apply_gradients",
 ]
 
 _lib = None
@@ -95,6 +95,8 @@ def load_library(path=None):
     lib.dcscn_last_grad_norm.argtypes = [vp]
     lib.dcscn_last_grad_norm.restype = cf
     lib.dcscn_dropout_mask.argtypes = [vp, ctypes.c_char_p, u32, ci, ci, ci, ctypes.POINTER(ctypes.c_uint8), c64]
+    lib.dcscn_grad_buffer.argtypes = [vp, ctypes.POINTER(fp), ctypes.POINTER(c64)]
+    lib.dcscn_apply_gradients.argtypes = [vp, cf, vp]
     lib.dcscn_launch_count.argtypes = [vp]
     lib.dcscn_launch_count.restype = c64
     lib.dcscn_device_bytes.argtypes = [vp]
@@ -229,6 +231,41 @@ class Engine:
                                               int(seed) & 0xFFFFFFFF, int(bool(apply_update)), ctypes.byref(loss),
                                               ctypes.byref(mse), ctypes.c_void_p(st)))
         return float(loss.value), float(mse.value)
+
+    def grad_tensor(self):
+        """Zero-copy torch view of the flat device gradient buffer (for torch.distributed.all_reduce over NCCL)."""
+        import torch
+        ptr, cnt = ctypes.POINTER(ctypes.c_float)(), ctypes.c_int64()
+        self._check(self.lib.dcscn_grad_buffer(self.handle, ctypes.byref(ptr), ctypes.byref(cnt)))
+
+        class _Buf:
+            __cuda_array_interface__ = {"shape": (int(cnt.value),), "typestr": "<f4", "version": 2,
+                                        "data": (ctypes.cast(ptr, ctypes.c_void_p).value, False)}
+        return torch.as_tensor(_Buf(), device="cuda:%d" % self.config.device_id)
+
+    def apply_gradients(self, lr, stream=None):
+        import torch
+        st = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        self._check(self.lib.dcscn_apply_gradients(self.handle, float(lr), ctypes.c_void_p(st)))
+
+    def train_step_data_parallel(self, x, x2, y, lr, seed):
+        """One optimisation step with the mini-batch sharded over the ranks of the current torch.distributed job:
+        local gradients -> ONE flat all-reduce (mean) -> identical clip + Adam on every rank.  Returns the
+        job-wide (image_loss, mse)."""
+        import torch
+        import torch.distributed as dist
+        fn = self.train_step if hasattr(x, "is_cuda") and x.is_cuda else self.train_step_host
+        loss, mse = fn(x, x2, y, lr, seed, apply_update=False)
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            world = dist.get_world_size()
+            g = self.grad_tensor()
+            dist.all_reduce(g, op=dist.ReduceOp.SUM)
+            g.mul_(1.0 / world)
+            s = torch.tensor([loss, mse], dtype=torch.float64, device=g.device)
+            dist.all_reduce(s, op=dist.ReduceOp.SUM)
+            loss, mse = float(s[0]) / world, float(s[1]) / world
+        self.apply_gradients(lr)
+        return loss, mse
 
     def get_grad(self, name):
         a = np.empty(self.param_shapes()[name], dtype=np.float32)

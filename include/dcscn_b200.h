@@ -98,6 +98,12 @@ int dcscn_train_step_host(dcscn_handle* h, const float* x, const float* x2, cons
 int dcscn_get_grad(dcscn_handle* h, const char* name, float* host_data, int64_t numel);
 /* Adam slots of a variable ("<var>/Adam" = slot 0, "<var>/Adam_1" = slot 1 in the reference's checkpoints). */
 int dcscn_get_adam_slot(dcscn_handle* h, const char* name, int slot, float* host_data, int64_t numel);
+/* Data-parallel training: after dcscn_train_step(..., apply_update = 0) on every rank, all-reduce (average) the flat
+ * gradient buffer returned here (device pointer, `count` floats, every trainable in dcscn_param_info order) - e.g.
+ * ncclAllReduce over NVLink - then call dcscn_apply_gradients on every rank: global-norm clip of the averaged gradient
+ * + Adam, identically everywhere. */
+int dcscn_grad_buffer(dcscn_handle* h, float** dev_ptr, int64_t* count);
+int dcscn_apply_gradients(dcscn_handle* h, float lr, void* stream);
 /* Global gradient norm of the last train step (what clip_by_global_norm computed). */
 float dcscn_last_grad_norm(dcscn_handle* h);
 /* The keep mask (1 = kept) the train step with `seed` applies to `tensor` ("CNNi", "A1", "B1", "B2"), [n,h,w,C] uint8:

@@ -268,14 +268,86 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_secondary(args, rank, world, local_rank):
+    """Non-headline workloads of BASELINE.json (`--workload train` = configs[3], `--workload ds` = configs[4]); same JSON
+    shape, `config.workload` says which.  One process per GPU; the train step all-reduces one flat gradient buffer."""
+    import numpy as np
+    import torch
+    from helper import engine as E
+    from helper import tf_bundle
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def weights(model):
+        r = tf_bundle.BundleReader(os.path.join(ROOT, "tests", "golden", "models", model + ".ckpt"))
+        return {k: r.get_tensor(k) for k in r.keys()}
+
+    gen = torch.Generator().manual_seed(2 + rank)
+    if args.workload == "train":
+        per_gpu = 64
+        eng = E.Engine(E.make_config(scale=4, device_id=local_rank, dropout_keep=0.8))
+        eng.set_params(weights("dcscn_L12_F196to48_Sc4_NIN_A64_PS_R1F32"))
+        x = (torch.rand(per_gpu, 48, 48, 1, generator=gen) * 255).cuda()
+        x2 = (torch.rand(per_gpu, 192, 192, 1, generator=gen) * 255).cuda()
+        y = (torch.rand(per_gpu, 192, 192, 1, generator=gen) * 255).cuda()
+        step = lambda i: eng.train_step_data_parallel(x, x2, y, lr=0.002, seed=i * world + rank)
+        units, unit, metric = per_gpu * world, "patches/s", "training patches/sec DCSCN L12 x4 (48x48 -> 192x192)"
+        name = "DCSCN L12 F196->48 x4 train step, %d 48x48 patches per GPU, dropout keep 0.8, Adam (BASELINE.json configs[3])" % per_gpu
+    else:
+        eng = E.Engine(E.make_config(scale=4, layers=7, filters=32, min_filters=8, filters_decay_gamma=1.2, nin_filters=24,
+                                     nin_filters2=8, reconstruct_layers=0, pixel_shuffler_filters=1, depthwise_separable=True,
+                                     device_id=local_rank))
+        eng.set_params(weights("dcscn_L7_F32to8_G1.20_Sc4_NIN_A24_B8_PS_DS_R1F32"))
+        gen = torch.Generator().manual_seed(3 + rank)
+        x = (torch.rand(256, 48, 48, 1, generator=gen) * 255).cuda()
+        x2 = (torch.rand(256, 192, 192, 1, generator=gen) * 255).cuda()
+        yb = torch.empty_like(x2)
+        step = lambda i: eng.forward(x, x2, yb)
+        units, unit, metric = 256 * 192 * 192 * world / 1e6, "Mpixels/s", "output Mpixels/sec DS c-DCSCN L7 x4"
+        name = "depthwise-separable c-DCSCN L7 x4 inference, batch=256 synthetic 48x48 tiles per GPU (BASELINE.json configs[4])"
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = eng.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        step(100 + i)
+    ev1.record()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    if rank == 0:
+        print(json.dumps({
+            "metric": metric, "value": units * args.steps / (ms / 1e3), "unit": unit, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16x3 dgrad / fp32 wgrad" if args.workload == "train" else "f32",
+            "data": "synthetic", "config": {"workload": name}, "gpu_launches": int(eng.launch_count - l0)}))
+    eng.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="f16x3", choices=["f16x3", "f16x1"])
     ap.add_argument("--cpu-seconds", type=float, default=10.0, dest="cpu_seconds")
+    ap.add_argument("--workload", default="infer", choices=["infer", "train", "ds"],
+                    help="infer = headline (BASELINE configs[1]); train = configs[3]; ds = configs[4]")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -288,6 +360,9 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
                "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
+    if args.workload != "infer":
+        run_secondary(args, rank, world, local_rank)
+        return
     run_ours(args, rank, world, local_rank)
 
 

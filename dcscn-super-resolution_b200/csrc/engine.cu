@@ -368,8 +368,10 @@ static int pack_tc_layer(dcscn_handle* h, TcLayer& t) {
   // 16-byte chunk j of row r lands at chunk j ^ f(r)  (SW128: f = r & 7, SW64: f = (r >> 1) & 3)
   const int row_chunks = KC / 8;
   const size_t tile_elems = (size_t)t.n_pad * KC;
-  std::vector<__half> pack((size_t)t.n_tiles * taps * chunks * NPL * tile_elems);
-  for (int nt = 0; nt < t.n_tiles; ++nt)
+  const bool need_pair = (KC == 64) && h->pair && (h->sm_count % 2 == 0);
+  const bool need_single = !need_pair;   // the single-CTA kernel only runs when the CTA-pair kernels cannot
+  std::vector<__half> pack(need_single ? (size_t)t.n_tiles * taps * chunks * NPL * tile_elems : 0);
+  for (int nt = 0; need_single && nt < t.n_tiles; ++nt)
     for (int tp = 0; tp < taps; ++tp)
       for (int ch = 0; ch < chunks; ++ch) {
         __half* base = pack.data() + (((size_t)nt * taps + tp) * chunks + ch) * NPL * tile_elems;
@@ -390,7 +392,7 @@ static int pack_tc_layer(dcscn_handle* h, TcLayer& t) {
       }
   if (upload(&t.d_wpack, pack, h)) return 1;
   t.has_pair = false;
-  if (KC == 64) {
+  if (need_pair) {
     const int half_rows = t.n_pad / 2;
     const size_t half_elems = (size_t)half_rows * 64;
     std::vector<__half> pp((size_t)t.n_tiles * taps * chunks * 2 * NPL * half_elems);
@@ -1055,6 +1057,7 @@ static int launch_tc(dcscn_handle* h, const TcLaunch& L, cudaStream_t st) {
   if (h->pair && h->halo == 2 && L.halo1 && h->kc == 64) return npl == 2 ? launch_tc_halo1<2>(h, L, st) : launch_tc_halo1<1>(h, L, st);
   if (h->pair && h->halo && L.halo && h->kc == 64) return npl == 2 ? launch_tc_halo<2>(h, L, st) : launch_tc_halo<1>(h, L, st);
   if (h->pair && L.pair && h->kc == 64) return npl == 2 ? launch_tc_pair<2>(h, L, st) : launch_tc_pair<1>(h, L, st);
+  if (L.p.wpack == nullptr) return fail("internal: single-CTA weight image was not packed for this layer");
   if (h->kc == 64) return npl == 2 ? launch_tc_inst<64, 2>(h, L, st) : launch_tc_inst<64, 1>(h, L, st);
   return npl == 2 ? launch_tc_inst<32, 2>(h, L, st) : launch_tc_inst<32, 1>(h, L, st);
 }
@@ -1418,7 +1421,12 @@ int dcscn_set_option(dcscn_handle* h, const char* key, int64_t value) {
     if (value < 0 || value > 2) return fail("halo must be 0, 1 or 2");
     h->halo = (int)value;
   } else if (k == "pair") {
-    h->pair = value ? 1 : 0;
+    if (h->pair != (value ? 1 : 0)) {
+      h->pair = value ? 1 : 0;
+      h->params_dirty = true;   // the two kernels use different packed weight layouts
+      h->plans.clear();
+      h->last_plan = nullptr;
+    }
   } else if (k == "cluster") {
     if (value != 1 && value != 2 && value != 4) return fail("cluster must be 1, 2 or 4");
     h->cluster = (int)value;

@@ -22,7 +22,7 @@ def test_evaluate_cli_c_dcscn_set5(tmp_path):
     r = subprocess.run(cmd, cwd=str(tmp_path), capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     log = open(tmp_path / "log.txt").read()
-    m = re.search(r"Model Average \\[set5\\] PSNR:([0-9.]+), SSIM:([0-9.nan]+), Time \\(s\\): ([0-9.]+)", log)
+    m = re.search(r"Model Average \[set5\] PSNR:([0-9.]+), SSIM:([0-9.nan]+), Time \(s\): ([0-9.]+)", log)
     assert m, log
     assert abs(float(m.group(1)) - 37.148) <= 0.01
 

@@ -30,57 +30,137 @@ struct DsLayerParams {
   const float* add;         // null, or [N,H,W] tensor added to channel 0 (cout must be 1): tf.add(H[-1], x2)
 };
 
-constexpr int kDsPix = 64;      // pixels per CTA (one row segment)
+constexpr int kDsPix = 128;     // pixels per CTA (consecutive in the flattened N*H*W order; may span rows / images)
 constexpr int kDsThreads = 256;
 
-// One CTA: a run of kDsPix consecutive pixels of one image row.  Phase 1: depthwise outputs [pix][cin] into shared
-// memory (threads stride over (pixel, channel): channel fastest -> coalesced NHWC reads).  Phase 2: pointwise
-// [pix][cout] with the pointwise filter read through the read-only cache (warp-uniform per output channel).
-__global__ void __launch_bounds__(kDsThreads) ds_layer_kernel(const DsLayerParams p) {
-  extern __shared__ float s_dw[];  // [kDsPix][cin]
-  const int segs_per_row = (p.W + kDsPix - 1) / kDsPix;
-  const int seg = blockIdx.x % segs_per_row;
-  const int rowid = blockIdx.x / segs_per_row;      // img * H + y
-  const int y = rowid % p.H;
-  const int img = rowid / p.H;
-  const int x0 = seg * kDsPix;
-  const int npix = (p.W - x0) < kDsPix ? (p.W - x0) : kDsPix;
-  const int half = p.ksz >> 1;
-  const float* img_base = p.src + (size_t)img * p.H * p.W * p.src_pitch;
+__host__ __device__ inline int ds_cin_pad(int cin) {   // multiple of 4 with an odd number of float4 per row
+  int c = (cin + 3) & ~3;                              // -> consecutive pixel rows hit distinct bank groups
+  if (((c >> 2) & 1) == 0) c += 4;
+  return c;
+}
+__host__ __device__ inline int ds_cout_pad(int cout) { return (cout + 3) & ~3; }
+inline size_t ds_smem_bytes(int ksz, int cin, int cout) {
+  return ((size_t)kDsPix * ds_cin_pad(cin) + (size_t)ds_cin_pad(cin) * ds_cout_pad(cout) + (size_t)ksz * ksz * cin) * sizeof(float);
+}
 
-  for (int i = threadIdx.x; i < npix * p.cin; i += blockDim.x) {
-    const int c = i % p.cin, px = i / p.cin;
-    const int x = x0 + px;
-    float acc = 0.f;
-    for (int t = 0; t < p.ksz * p.ksz; ++t) {
-      const int yy = y + t / p.ksz - half, xx = x + t % p.ksz - half;
-      if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W)
-        acc = fmaf(__ldg(img_base + ((size_t)yy * p.W + xx) * p.src_pitch + c), __ldg(p.dw + t * p.cin + c), acc);
+// Pointwise contraction + bias + PReLU + store for PXT pixels x 4 output channels per thread (pixels pg + j * PG).
+template <int PXT>
+__device__ __forceinline__ void ds_pointwise(const DsLayerParams& p, const float* s_d, const float* s_w, int cin_p, int cout_p,
+                                             long long base, int npix) {
+  const int G = cout_p >> 2;
+  constexpr int PG = kDsPix / PXT;
+  for (int item = threadIdx.x; item < G * PG; item += kDsThreads) {
+    const int g = item % G, pg = item / G;
+    float acc[PXT][4];
+#pragma unroll
+    for (int j = 0; j < PXT; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[j][q] = 0.f;
+    const float* wcol = s_w + 4 * g;
+    for (int c4 = 0; c4 < cin_p; c4 += 4) {
+      const float4 w0 = *reinterpret_cast<const float4*>(wcol + (c4 + 0) * cout_p);
+      const float4 w1 = *reinterpret_cast<const float4*>(wcol + (c4 + 1) * cout_p);
+      const float4 w2 = *reinterpret_cast<const float4*>(wcol + (c4 + 2) * cout_p);
+      const float4 w3 = *reinterpret_cast<const float4*>(wcol + (c4 + 3) * cout_p);
+#pragma unroll
+      for (int j = 0; j < PXT; ++j) {
+        const float4 d = *reinterpret_cast<const float4*>(s_d + (pg + PG * j) * cin_p + c4);
+        acc[j][0] = fmaf(d.w, w3.x, fmaf(d.z, w2.x, fmaf(d.y, w1.x, fmaf(d.x, w0.x, acc[j][0]))));
+        acc[j][1] = fmaf(d.w, w3.y, fmaf(d.z, w2.y, fmaf(d.y, w1.y, fmaf(d.x, w0.y, acc[j][1]))));
+        acc[j][2] = fmaf(d.w, w3.z, fmaf(d.z, w2.z, fmaf(d.y, w1.z, fmaf(d.x, w0.z, acc[j][2]))));
+        acc[j][3] = fmaf(d.w, w3.w, fmaf(d.z, w2.w, fmaf(d.y, w1.w, fmaf(d.x, w0.w, acc[j][3]))));
+      }
     }
-    s_dw[px * p.cin + c] = acc;
+#pragma unroll
+    for (int j = 0; j < PXT; ++j) {
+      const int px = pg + PG * j;
+      if (px >= npix) continue;
+      const long long gp = base + px;
+      int x = 0, y = 0;
+      long long img = 0;
+      if (p.d2s_r != 0) {
+        x = (int)(gp % p.W);
+        const long long rowid = gp / p.W;
+        y = (int)(rowid % p.H);
+        img = rowid / p.H;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int co = 4 * g + q;
+        if (co >= p.cout) continue;
+        float v = acc[j][q];
+        if (p.bias) v += __ldg(p.bias + co);
+        if (p.alpha) v = v > 0.f ? v : __ldg(p.alpha + co) * v;
+        if (p.d2s_r == 0) {
+          if (p.add) v += __ldg(p.add + gp);
+          p.dst[(size_t)gp * p.dst_pitch + p.dst_off + co] = v;
+        } else {
+          // DCR: input channel (i*r + j)*C + c -> (y*r + i, x*r + j, c)   (tf.depth_to_space, tf_graph.py:248)
+          const int r = p.d2s_r, ij = co / p.d2s_cout, c = co - ij * p.d2s_cout;
+          const int ii = ij / r, jj = ij - ii * r;
+          const size_t o = (((size_t)img * p.H * r + (size_t)(y * r + ii)) * (p.W * r) + (size_t)(x * r + jj));
+          p.dst[o * p.dst_pitch + c] = v;
+        }
+      }
+    }
+  }
+}
+
+// One CTA: kDsPix consecutive pixels.  Phase 1: depthwise outputs [pix][cin_pad] into shared memory (a warp per
+// pixel, lanes over channels: coalesced NHWC reads).  Phase 2: the pointwise contraction as a register-tiled GEMM out
+// of shared memory: every thread owns 4 pixels x 4 output channels and reads float4s of the depthwise row and of the
+// (staged, zero-padded) pointwise filter: 8 LDS.128 per 64 FMA.
+__global__ void __launch_bounds__(kDsThreads) ds_layer_kernel(const DsLayerParams p) {
+  extern __shared__ float4 s_raw[];
+  const int cin_p = ds_cin_pad(p.cin), cout_p = ds_cout_pad(p.cout), kk = p.ksz * p.ksz;
+  float* s_d = reinterpret_cast<float*>(s_raw);       // [kDsPix][cin_p]
+  float* s_w = s_d + kDsPix * cin_p;                  // [cin_p][cout_p]
+  float* s_dw = s_w + cin_p * cout_p;                 // [k*k][cin]
+  const long long total = (long long)p.n_img * p.H * p.W;
+  const long long base = (long long)blockIdx.x * kDsPix;
+  const int npix = (int)((total - base) < kDsPix ? (total - base) : kDsPix);
+  const int half = p.ksz >> 1;
+
+  for (int i = threadIdx.x; i < cin_p * cout_p; i += kDsThreads) {
+    const int c = i / cout_p, co = i - c * cout_p;
+    s_w[i] = (c < p.cin && co < p.cout) ? __ldg(p.pw + (size_t)c * p.cout + co) : 0.f;
+  }
+  for (int i = threadIdx.x; i < kk * p.cin; i += kDsThreads) s_dw[i] = __ldg(p.dw + i);
+  __syncthreads();
+
+  // depthwise: LP lanes per pixel (smallest power of two >= cin_p, at most a warp), channels strided by LP
+  int LP = 1;
+  while (LP < cin_p && LP < 32) LP <<= 1;
+  const int px_per_pass = kDsThreads / LP;
+  for (int px = threadIdx.x / LP; px < kDsPix; px += px_per_pass) {
+    float* drow = s_d + px * cin_p;
+    const int l = threadIdx.x & (LP - 1);
+    if (px >= npix) {
+      for (int c = l; c < cin_p; c += LP) drow[c] = 0.f;
+      continue;
+    }
+    const long long gp = base + px;
+    const int x = (int)(gp % p.W);
+    const long long rowid = gp / p.W;
+    const int y = (int)(rowid % p.H);
+    const float* ctr = p.src + (size_t)gp * p.src_pitch;
+    for (int c = l; c < cin_p; c += LP) {
+      float acc = 0.f;
+      if (c < p.cin) {
+        for (int t = 0; t < kk; ++t) {
+          const int dy = t / p.ksz - half, dx = t % p.ksz - half;
+          if ((unsigned)(y + dy) < (unsigned)p.H && (unsigned)(x + dx) < (unsigned)p.W)
+            acc = fmaf(__ldg(ctr + ((long long)dy * p.W + dx) * p.src_pitch + c), s_dw[t * p.cin + c], acc);
+        }
+      }
+      drow[c] = acc;
+    }
   }
   __syncthreads();
 
-  for (int i = threadIdx.x; i < npix * p.cout; i += blockDim.x) {
-    const int co = i % p.cout, px = i / p.cout;
-    const float* d = s_dw + px * p.cin;
-    float acc = 0.f;
-    for (int c = 0; c < p.cin; ++c) acc = fmaf(d[c], __ldg(p.pw + (size_t)c * p.cout + co), acc);
-    if (p.bias) acc += __ldg(p.bias + co);
-    if (p.alpha) acc = acc > 0.f ? acc : __ldg(p.alpha + co) * acc;
-    const int x = x0 + px;
-    if (p.d2s_r == 0) {
-      const size_t o = (((size_t)img * p.H + y) * p.W + x);
-      if (p.add) acc += __ldg(p.add + o);
-      p.dst[o * p.dst_pitch + p.dst_off + co] = acc;
-    } else {
-      // DCR: input channel (i*r + j)*C + c -> (y*r + i, x*r + j, c)   (tf.depth_to_space, tf_graph.py:248)
-      const int r = p.d2s_r, ij = co / p.d2s_cout, c = co - ij * p.d2s_cout;
-      const int ii = ij / r, jj = ij - ii * r;
-      const size_t o = (((size_t)img * p.H * r + (size_t)(y * r + ii)) * (p.W * r) + (size_t)(x * r + jj));
-      p.dst[o * p.dst_pitch + c] = acc;
-    }
-  }
+  const int G = cout_p >> 2;               // float4 groups of output channels
+  if (G * (kDsPix / 4) >= kDsThreads) ds_pointwise<4>(p, s_d, s_w, cin_p, cout_p, base, npix);
+  else ds_pointwise<1>(p, s_d, s_w, cin_p, cout_p, base, npix);
 }
 
 }  // namespace dcscn

@@ -25,6 +25,8 @@
 #include "conv_tc_halo1.cuh"
 #include "conv_ds.cuh"
 #include "train.cuh"
+#include "wgrad_tc.cuh"
+#include "wgrad_tc.cuh"
 
 using namespace dcscn;
 
@@ -61,6 +63,7 @@ struct ParamDef {
   std::string name;
   std::vector<int64_t> shape;
   std::vector<float> host;
+  std::vector<float> shadow;    // flat index + 2 of every element (float-coded), see build_refresh_maps
   int64_t numel() const {
     int64_t n = 1;
     for (auto d : shape) n *= d;
@@ -89,6 +92,14 @@ struct TcLayer {
   __half* d_wpair = nullptr;    // CTA-pair layout [n_tile][tap][chunk][rank][plane][n_pad/2 x 64]
   CUtensorMap tm_w;             // 2-D map over d_wpair (rows of 128 bytes)
   bool has_pair = false;
+  int* d_pair_src = nullptr;    // training: flat parameter index behind every hi-plane element of d_wpair (-1 = zero)
+  size_t pair_src_n = 0;
+};
+
+struct GatherJob {   // training: dst[i] = d_w[map[i]] where map[i] >= 0 (biases, PReLU slopes, CNN1 / R-CNN1 filters)
+  float* dst;
+  int* map;
+  int n;
 };
 
 struct TcLaunch {
@@ -146,6 +157,11 @@ struct dcscn_handle {
   std::vector<TcLayer> tcl;          // CNN2..CNNL, A1+B1, B2, Up-PS [, Up-PS2]
   std::vector<TcLayer> bwd;          // data-gradient twins (transposed, flipped filters), see build_bwd_layers
   bool train_enabled = false;
+  int wgrad_impl = 0;                // 0 = tcgen05 (wgrad_tc.cuh), 1 = CUDA cores (validation)
+  int host_repack = 0;               // option: always re-pack on the host after an update (validation of the device path)
+  bool shadow_mode = false;          // P() returns index-coded shadows (build_refresh_maps)
+  bool refresh_ready = false;        // device-side weight refresh maps are valid for the current packing
+  std::vector<struct GatherJob> gather_jobs;
   struct TrainState* train = nullptr;
   float* d_first_w = nullptr;        // CNN1 [taps][n_pad]
   float* d_first_bias = nullptr;
@@ -278,7 +294,8 @@ static const LayerDef* find_layer(const dcscn_handle* h, const std::string& scop
   return nullptr;
 }
 static const std::vector<float>& P(const dcscn_handle* h, const std::string& name) {
-  return h->params[h->param_index.at(name)].host;
+  const ParamDef& p = h->params[h->param_index.at(name)];
+  return h->shadow_mode ? p.shadow : p.host;
 }
 
 // ------------------------------------------------------------------------------ weight packing ----
@@ -343,6 +360,36 @@ static void choose_tiling(int n_total_pad16, int* n_tiles, int* n_pad) {
   *n_pad = np;
 }
 
+// Values (unscaled fp32) of the CTA-pair operand image of a layer, one per hi-plane element, in image order:
+// [n_tile][tap][chunk][rank][n_pad/2 rows x 64 halves], each row 128-byte swizzled (16-byte chunk j of row r at j ^ (r & 7)).
+static void pair_image(const TcLayer& t, std::vector<float>& img) {
+  const int taps = t.ksz * t.ksz, chunks = (t.cin_pad + 63) / 64, n_total = t.n_tiles * t.n_pad;
+  std::vector<float> wq((size_t)taps * t.cin_pad * n_total, 0.f);   // dense, channel-position-indexed  Wq[tap][q][n]
+  for (int tp = 0; tp < taps; ++tp)
+    for (int ci = 0; ci < t.cin; ++ci) {
+      const int q = t.in_map[ci];
+      for (int co = 0; co < t.cout; ++co)
+        wq[((size_t)tp * t.cin_pad + q) * n_total + co] = t.w_host[((size_t)tp * t.cin + ci) * t.cout + co];
+    }
+  const int half_rows = t.n_pad / 2;
+  const size_t half_elems = (size_t)half_rows * 64;
+  img.assign((size_t)t.n_tiles * taps * chunks * 2 * half_elems, 0.f);
+  for (int nt = 0; nt < t.n_tiles; ++nt)
+    for (int tp = 0; tp < taps; ++tp)
+      for (int ch = 0; ch < chunks; ++ch)
+        for (int rk = 0; rk < 2; ++rk) {
+          float* base = img.data() + ((((size_t)nt * taps + tp) * chunks + ch) * 2 + rk) * half_elems;
+          for (int r = 0; r < half_rows; ++r) {
+            const int n = nt * t.n_pad + rk * half_rows + r;
+            const int sw = r & 7;
+            for (int kk = 0; kk < 64; ++kk) {
+              const int q = ch * 64 + kk;
+              if (q < t.cin_pad) base[(size_t)r * 64 + (size_t)((kk / 8) ^ sw) * 8 + (kk % 8)] = wq[((size_t)tp * t.cin_pad + q) * n_total + n];
+            }
+          }
+        }
+}
+
 static int pack_tc_layer(dcscn_handle* h, TcLayer& t) {
   const int KC = h->kc;
   const int NPL = planes(h);
@@ -355,9 +402,13 @@ static int pack_tc_layer(dcscn_handle* h, TcLayer& t) {
   t.wscale = 1.f;
   if (maxw > 0.f) t.wscale = std::ldexp(1.0f, (int)std::floor(std::log2(16384.0 / (double)maxw)));
 
+  const int row_chunks = KC / 8;
+  const size_t tile_elems = (size_t)t.n_pad * KC;
+  const bool need_pair = (KC == 64) && h->pair && (h->sm_count % 2 == 0);
+  const bool need_single = !need_pair;   // the single-CTA kernel only runs when the CTA-pair kernels cannot
   // dense, channel-position-indexed weights  Wq[tap][q][n]
-  std::vector<float> wq((size_t)taps * t.cin_pad * n_total, 0.f);
-  for (int tp = 0; tp < taps; ++tp)
+  std::vector<float> wq(need_single ? (size_t)taps * t.cin_pad * n_total : 0, 0.f);
+  for (int tp = 0; need_single && tp < taps; ++tp)
     for (int ci = 0; ci < t.cin; ++ci) {
       const int q = t.in_map[ci];
       for (int co = 0; co < t.cout; ++co)
@@ -366,10 +417,6 @@ static int pack_tc_layer(dcscn_handle* h, TcLayer& t) {
 
   // tiles in the shared-memory image of a K-major swizzled UMMA operand: row = output channel, KC halves per row,
   // 16-byte chunk j of row r lands at chunk j ^ f(r)  (SW128: f = r & 7, SW64: f = (r >> 1) & 3)
-  const int row_chunks = KC / 8;
-  const size_t tile_elems = (size_t)t.n_pad * KC;
-  const bool need_pair = (KC == 64) && h->pair && (h->sm_count % 2 == 0);
-  const bool need_single = !need_pair;   // the single-CTA kernel only runs when the CTA-pair kernels cannot
   std::vector<__half> pack(need_single ? (size_t)t.n_tiles * taps * chunks * NPL * tile_elems : 0);
   for (int nt = 0; need_single && nt < t.n_tiles; ++nt)
     for (int tp = 0; tp < taps; ++tp)
@@ -395,26 +442,16 @@ static int pack_tc_layer(dcscn_handle* h, TcLayer& t) {
   if (need_pair) {
     const int half_rows = t.n_pad / 2;
     const size_t half_elems = (size_t)half_rows * 64;
-    std::vector<__half> pp((size_t)t.n_tiles * taps * chunks * 2 * NPL * half_elems);
-    for (int nt = 0; nt < t.n_tiles; ++nt)
-      for (int tp = 0; tp < taps; ++tp)
-        for (int ch = 0; ch < chunks; ++ch)
-          for (int rk = 0; rk < 2; ++rk) {
-            __half* base = pp.data() + ((((size_t)nt * taps + tp) * chunks + ch) * 2 + rk) * NPL * half_elems;
-            for (int r = 0; r < half_rows; ++r) {
-              const int n = nt * t.n_pad + rk * half_rows + r;
-              const int sw = r & 7;
-              for (int kk = 0; kk < 64; ++kk) {
-                const int q = ch * 64 + kk;
-                float v = (q < t.cin_pad) ? wq[((size_t)tp * t.cin_pad + q) * n_total + n] : 0.f;
-                __half hi = __float2half_rn(v);
-                __half lo = __float2half_rn(v - __half2float(hi));
-                const size_t pos = (size_t)r * 64 + (size_t)((kk / 8) ^ sw) * 8 + (kk % 8);
-                base[pos] = hi;
-                if (NPL == 2) base[half_elems + pos] = lo;
-              }
-            }
-          }
+    std::vector<float> img;
+    pair_image(t, img);
+    std::vector<__half> pp(img.size() * NPL);
+    for (size_t i = 0; i < img.size(); ++i) {
+      const size_t blk = i / half_elems, pos = i - blk * half_elems;
+      const float v = img[i] * t.wscale;
+      const __half hi = __float2half_rn(v);
+      pp[blk * NPL * half_elems + pos] = hi;
+      if (NPL == 2) pp[blk * NPL * half_elems + half_elems + pos] = __float2half_rn(v - __half2float(hi));
+    }
     if (upload(&t.d_wpair, pp, h)) return 1;
     const size_t total_rows = pp.size() / 64;
     cuuint64_t dims[2] = {64, (cuuint64_t)total_rows};
@@ -458,6 +495,8 @@ static void free_tc(TcLayer& t) {
   dev_free(t.d_alpha);
   dev_free(t.d_wref);
   dev_free(t.d_in_map);
+  dev_free(t.d_pair_src);
+  t.d_pair_src = nullptr;
   t.d_wpack = t.d_wpair = nullptr;
   t.d_bias = t.d_alpha = t.d_wref = nullptr;
   t.d_in_map = nullptr;
@@ -465,7 +504,7 @@ static void free_tc(TcLayer& t) {
 
 static void adopt_tc(TcLayer& t, const TcLayer& old) {  // keep the device allocations of the previous packing
   t.d_wpack = old.d_wpack; t.d_wpair = old.d_wpair; t.d_bias = old.d_bias; t.d_alpha = old.d_alpha;
-  t.d_wref = old.d_wref; t.d_in_map = old.d_in_map;
+  t.d_wref = old.d_wref; t.d_in_map = old.d_in_map; t.d_pair_src = old.d_pair_src;
 }
 
 // (Re)builds every device-side weight image from the host fp32 parameters.
@@ -494,33 +533,30 @@ static int finalize_params_ds(dcscn_handle* h) {
 }
 
 static int build_bwd_layers(dcscn_handle* h);
+static int sync_host_params(dcscn_handle* h);   // train_engine.inc: device master copy -> host, when newer
 
-static int finalize_params(dcscn_handle* h) {
-  const dcscn_config& c = h->cfg;
-  if (c.depthwise_separable) return finalize_params_ds(h);
-  std::vector<TcLayer> old_tcl = std::move(h->tcl);
-  std::vector<TcLayer> old_bwd = std::move(h->bwd);
-  h->tcl.clear();
-  h->bwd.clear();
-  g_upload_realloc = false;
-  const int L = c.layers;
-
-  // CNN1 (CUDA cores)
-  {
-    const LayerDef* l = find_layer(h, "CNN1");
-    const int taps = l->k * l->k, np = h->feat_w[0];
-    std::vector<float> w((size_t)taps * np, 0.f), b(np, 0.f), a(np, 1.f);
-    const auto& W = P(h, "CNN1/conv_W");
-    for (int tp = 0; tp < taps; ++tp)
-      for (int co = 0; co < l->cout; ++co) w[(size_t)tp * np + co] = W[(size_t)tp * l->cout + co];
-    const auto& B = P(h, "CNN1/conv_B");
-    const auto& A = P(h, "CNN1/prelu/CNN1_prelu");
-    for (int co = 0; co < l->cout; ++co) {
-      b[co] = B[co];
-      a[co] = A[co];
-    }
-    if (upload(&h->d_first_w, w, h) || upload(&h->d_first_bias, b, h) || upload(&h->d_first_alpha, a, h)) return 1;
+// CNN1's device vectors (CUDA cores): filter [taps][n_pad], bias, PReLU slope, padded to the slot width.
+static void first_layer_vectors(const dcscn_handle* h, std::vector<float>& w, std::vector<float>& b, std::vector<float>& a) {
+  const LayerDef* l = find_layer(h, "CNN1");
+  const int taps = l->k * l->k, np = h->feat_w[0];
+  w.assign((size_t)taps * np, 0.f);
+  b.assign(np, 0.f);
+  a.assign(np, 1.f);
+  const auto& W = P(h, "CNN1/conv_W");
+  for (int tp = 0; tp < taps; ++tp)
+    for (int co = 0; co < l->cout; ++co) w[(size_t)tp * np + co] = W[(size_t)tp * l->cout + co];
+  const auto& B = P(h, "CNN1/conv_B");
+  const auto& A = P(h, "CNN1/prelu/CNN1_prelu");
+  for (int co = 0; co < l->cout; ++co) {
+    b[co] = B[co];
+    a[co] = A[co];
   }
+}
+
+// Fills h->tcl (forward tensor-core layers) and, when training, h->bwd (their dgrad twins) from the parameters P().
+static int construct_tc_layers(dcscn_handle* h) {
+  const dcscn_config& c = h->cfg;
+  const int L = c.layers;
   // CNN2..CNNL
   for (int i = 1; i < L; ++i) {
     const std::string scope = "CNN" + std::to_string(i + 1);
@@ -566,6 +602,25 @@ static int finalize_params(dcscn_handle* h) {
     }
   }
   if (h->train_enabled && build_bwd_layers(h)) return 1;
+  return 0;
+}
+
+static int finalize_params(dcscn_handle* h) {
+  const dcscn_config& c = h->cfg;
+  if (sync_host_params(h)) return 1;
+  if (c.depthwise_separable) return finalize_params_ds(h);
+  std::vector<TcLayer> old_tcl = std::move(h->tcl);
+  std::vector<TcLayer> old_bwd = std::move(h->bwd);
+  h->tcl.clear();
+  h->bwd.clear();
+  h->refresh_ready = false;
+  g_upload_realloc = false;
+  {
+    std::vector<float> w, b, a;
+    first_layer_vectors(h, w, b, a);
+    if (upload(&h->d_first_w, w, h) || upload(&h->d_first_bias, b, h) || upload(&h->d_first_alpha, a, h)) return 1;
+  }
+  if (construct_tc_layers(h)) return 1;
   for (size_t i = 0; i < h->tcl.size(); ++i) {
     if (i < old_tcl.size()) adopt_tc(h->tcl[i], old_tcl[i]);
     if (pack_tc_layer(h, h->tcl[i])) return 1;
@@ -1082,15 +1137,15 @@ static int launch_ds(dcscn_handle* h, const LayerDef& l, const dcscn_handle::DsD
   p.n_img = n; p.H = H; p.W = W; p.ksz = l.k; p.cin = l.cin; p.cout = l.cout;
   p.src = src; p.src_pitch = src_pitch; p.dw = d.dw; p.pw = d.pw; p.bias = d.bias; p.alpha = d.alpha;
   p.dst = dst; p.dst_pitch = dst_pitch; p.dst_off = dst_off; p.d2s_r = d2s_r; p.d2s_cout = d2s_cout; p.add = add;
-  const int segs = (W + kDsPix - 1) / kDsPix;
-  const size_t smem = (size_t)kDsPix * l.cin * sizeof(float);
-  if (smem > 200 * 1024) return fail("depthwise-separable layer %s: %d input channels exceed the kernel's shared memory", l.scope.c_str(), l.cin);
+  const size_t smem = ds_smem_bytes(l.k, l.cin, l.cout);
+  if (smem > 200 * 1024) return fail("depthwise-separable layer %s: %d -> %d channels exceed the kernel's shared memory", l.scope.c_str(), l.cin, l.cout);
   static bool attr_set = false;
   if (!attr_set) {
     CUDA_TRY(cudaFuncSetAttribute(ds_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
-  ds_layer_kernel<<<n * H * segs, kDsThreads, smem, st>>>(p);
+  const long long total = (long long)n * H * W;
+  ds_layer_kernel<<<(unsigned)((total + kDsPix - 1) / kDsPix), kDsThreads, smem, st>>>(p);
   CUDA_TRY(cudaGetLastError());
   h->launches++;
   return mark(h, st);
@@ -1277,6 +1332,7 @@ int dcscn_set_param(dcscn_handle* h, const char* name, const float* host_data, i
   if (!h || !name || !host_data) return fail("dcscn_set_param: null argument");
   auto it = h->param_index.find(name);
   if (it == h->param_index.end()) return fail("dcscn_set_param: unknown variable '%s'", name);
+  if (sync_host_params(h)) return 1;
   ParamDef& p = h->params[it->second];
   if (numel != p.numel()) return fail("dcscn_set_param: '%s' has %lld elements, got %lld", name, (long long)p.numel(), (long long)numel);
   memcpy(p.host.data(), host_data, (size_t)numel * sizeof(float));
@@ -1289,6 +1345,7 @@ int dcscn_get_param(dcscn_handle* h, const char* name, float* host_data, int64_t
   if (!h || !name || !host_data) return fail("dcscn_get_param: null argument");
   auto it = h->param_index.find(name);
   if (it == h->param_index.end()) return fail("dcscn_get_param: unknown variable '%s'", name);
+  if (sync_host_params(h)) return 1;
   const ParamDef& p = h->params[it->second];
   if (numel != p.numel()) return fail("dcscn_get_param: '%s' has %lld elements, got %lld", name, (long long)p.numel(), (long long)numel);
   memcpy(host_data, p.host.data(), (size_t)numel * sizeof(float));
@@ -1436,6 +1493,11 @@ int dcscn_set_option(dcscn_handle* h, const char* key, int64_t value) {
     h->fuse_last = value ? 1 : 0;
   } else if (k == "timing") {
     h->timing = value ? 1 : 0;
+  } else if (k == "wgrad_impl") {
+    if (value != 0 && value != 1) return fail("wgrad_impl must be 0 (tensor cores) or 1 (CUDA cores)");
+    h->wgrad_impl = (int)value;
+  } else if (k == "host_repack") {
+    h->host_repack = value ? 1 : 0;
   } else if (k == "seg_chunks") {
     if (value < 0 || value > 4096) return fail("seg_chunks must be >= 0 (0 = automatic)");
     h->seg_chunks = (int)value;

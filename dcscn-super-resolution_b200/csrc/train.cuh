@@ -345,4 +345,45 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamParams p) {
   }
 }
 
+
+// ---- device-side refresh of the packed operand images after an optimizer step -------------------------------------
+// dst = CTA-pair operand image (hi plane block, then lo plane block, per [n_tile][tap][chunk][rank]); map[i] = flat
+// index into the fp32 master weights behind hi-plane element i (-1 = structural zero).  Also records max |w * scale|
+// so the host can tell when the power-of-two scale has to be re-chosen.
+struct RepackParams {
+  const float* w;
+  const int* map;
+  __half* dst;
+  unsigned long long n;
+  int half_elems;
+  float wscale;
+  unsigned* wmax;     // float bits (values are non-negative, so unsigned order == float order)
+};
+
+__global__ void __launch_bounds__(256) repack_pair_kernel(const RepackParams p) {
+  float m = 0.f;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    const int idx = __ldg(p.map + i);
+    const float v = idx >= 0 ? __ldg(p.w + idx) * p.wscale : 0.f;
+    m = fmaxf(m, fabsf(v));
+    const __half hi = __float2half_rn(v);
+    const __half lo = __float2half_rn(v - __half2float(hi));
+    const unsigned long long blk = i / (unsigned)p.half_elems, pos = i - blk * (unsigned)p.half_elems;
+    p.dst[blk * 2ull * p.half_elems + pos] = hi;
+    p.dst[blk * 2ull * p.half_elems + p.half_elems + pos] = lo;
+  }
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(p.wmax, __float_as_uint(m));
+}
+
+__global__ void __launch_bounds__(256) gather_params_kernel(const float* __restrict__ w, const int* __restrict__ map,
+                                                            float* __restrict__ dst, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const int idx = map[i];
+    if (idx >= 0) dst[i] = w[idx];
+  }
+}
+
 }  // namespace dcscn

@@ -124,7 +124,9 @@ int dcscn_get_activation(dcscn_handle* h, const char* tensor, float* host_data, 
  *          "pair" 1 | 0 = CTA-pair kernel (tcgen05 cta_group::2, weight tiles split across two SMs; default 1);
  *          "cluster" 1 | 2 | 4 = CTAs per cluster multicasting weight tiles in the single-CTA kernel (default 1);
  *          "fuse_last" 1 | 0 = compute the per-pixel half of R-CNN1 inside the last Up-PS epilogue (default 1);
- *          "timing" 0 | 1 = record per-launch CUDA events (see dcscn_get_timings). */
+ *          "timing" 0 | 1 = record per-launch CUDA events (see dcscn_get_timings);
+ *          "host_repack" 0 | 1 = after an optimizer step rebuild the packed tensor-core weight images on the host
+ *          (validation of the default device-side refresh). */
 int dcscn_set_option(dcscn_handle* h, const char* key, int64_t value);
 /* With option "timing" = 1 every launch of a forward is bracketed by CUDA events on its stream; this returns the
  * device time in ms of each launch of the LAST forward (in launch order) and their comma-separated names. */

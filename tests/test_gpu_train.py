@@ -86,3 +86,57 @@ def test_adam_step_matches_oracle_and_loss_decreases():
     more = [eng.train_step_host(x, x2, y, lr=0.002, seed=200 + i)[1] for i in range(30)]
     assert np.mean(more[-5:]) < losses[0]
     eng.close()
+
+
+@pytest.mark.parametrize("kw", [SMALL, SMALL4], ids=["x2", "x4"])
+def test_device_refresh_equals_host_repack(kw):
+    """After an optimizer step the packed tensor-core weight images (forward layers and dgrad twins), fused bias / PReLU
+    vectors and the CNN1 / R-CNN1 filters are refreshed on the device through index maps derived from the host packing
+    code.  A fresh engine that packs the same weights on the host must give the same forward output and the same
+    gradients (only the power-of-two weight scale may differ, which is exact)."""
+    from helper import engine as E
+    cfg, wts, eng, x, x2, y = setup(kw, 0.8, 2, 12, 14, seed=3)
+    for i in range(4):
+        eng.train_step_host(x, x2, y, lr=0.01, seed=50 + i)
+    y_dev = eng.forward_host(x, x2)
+    eng.train_step_host(x, x2, y, lr=0.01, seed=99, apply_update=False)
+    params = {n: eng.get_param(n) for n in wts}
+    grads_dev = {n: eng.get_grad(n) for n in wts}
+    assert any(np.abs(params[n] - wts[n]).max() > 1e-3 for n in wts)      # the weights did move
+    fresh = E.Engine(E.make_config(dropout_keep=0.8, **kw))
+    fresh.set_params(params)
+    y_host = fresh.forward_host(x, x2)
+    fresh.train_step_host(x, x2, y, lr=0.01, seed=99, apply_update=False)
+    assert np.abs(y_dev - y_host).max() <= 1e-5
+    for n in wts:
+        g = fresh.get_grad(n)
+        assert np.abs(g - grads_dev[n]).max() <= 1e-4 * np.abs(g).max() + 1e-9, n   # fp32 atomics reorder sums
+    eng.close()
+    fresh.close()
+
+
+def test_tensor_core_wgrad_matches_cuda_core_wgrad_full_model():
+    """Filter gradients of the full L12 x2 model (196..48 filters, 1301-channel concat, 384-column Up-PS): the tcgen05
+    wgrad (transposed zero-bordered operands, K-split partial sums) against the straightforward CUDA-core kernel on the
+    same planes.  Both accumulate in fp32; 1e-4 of each tensor's max covers the different summation orders."""
+    from helper import engine as E, tf_bundle
+    import conftest
+    wts = conftest.load_golden_weights("dcscn_L12_F196to48_NIN_A64_PS_R1F32")
+    g = np.random.RandomState(11)
+    n, h, w = 3, 20, 28
+    x = (g.rand(n, h, w, 1) * 255).astype(np.float32)
+    x2 = (g.rand(n, 2 * h, 2 * w, 1) * 255).astype(np.float32)
+    y = np.clip(x2 + g.randn(n, 2 * h, 2 * w, 1) * 10, 0, 255).astype(np.float32)
+    grads = []
+    for impl in (1, 0):
+        eng = E.Engine(E.make_config(scale=2, dropout_keep=0.8))
+        eng.set_params(wts)
+        eng.set_option("wgrad_impl", impl)
+        eng.train_step_host(x, x2, y, lr=0.002, seed=5, apply_update=False)
+        grads.append({k: eng.get_grad(k) for k in wts})
+        eng.close()
+    for k in wts:
+        if not k.endswith("conv_W"):
+            continue
+        ref, got = grads[0][k], grads[1][k]
+        assert np.abs(got - ref).max() <= 1e-4 * np.abs(ref).max() + 1e-12, (k, float(np.abs(got - ref).max()), float(np.abs(ref).max()))

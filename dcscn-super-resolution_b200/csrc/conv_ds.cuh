@@ -30,7 +30,7 @@ struct DsLayerParams {
   const float* add;         // null, or [N,H,W] tensor added to channel 0 (cout must be 1): tf.add(H[-1], x2)
 };
 
-constexpr int kDsPix = 128;     // pixels per CTA (consecutive in the flattened N*H*W order; may span rows / images)
+constexpr int kDsPix = 64;      // pixels per CTA (consecutive in the flattened N*H*W order; may span rows / images)
 constexpr int kDsThreads = 256;
 
 __host__ __device__ inline int ds_cin_pad(int cin) {   // multiple of 4 with an odd number of float4 per row
@@ -110,16 +110,17 @@ __device__ __forceinline__ void ds_pointwise(const DsLayerParams& p, const float
 // pixel, lanes over channels: coalesced NHWC reads).  Phase 2: the pointwise contraction as a register-tiled GEMM out
 // of shared memory: every thread owns 4 pixels x 4 output channels and reads float4s of the depthwise row and of the
 // (staged, zero-padded) pointwise filter: 8 LDS.128 per 64 FMA.
+template <int KSZ>
 __global__ void __launch_bounds__(kDsThreads) ds_layer_kernel(const DsLayerParams p) {
   extern __shared__ float4 s_raw[];
-  const int cin_p = ds_cin_pad(p.cin), cout_p = ds_cout_pad(p.cout), kk = p.ksz * p.ksz;
+  constexpr int kk = KSZ * KSZ, half = KSZ >> 1;
+  const int cin_p = ds_cin_pad(p.cin), cout_p = ds_cout_pad(p.cout);
   float* s_d = reinterpret_cast<float*>(s_raw);       // [kDsPix][cin_p]
   float* s_w = s_d + kDsPix * cin_p;                  // [cin_p][cout_p]
   float* s_dw = s_w + cin_p * cout_p;                 // [k*k][cin]
   const long long total = (long long)p.n_img * p.H * p.W;
   const long long base = (long long)blockIdx.x * kDsPix;
   const int npix = (int)((total - base) < kDsPix ? (total - base) : kDsPix);
-  const int half = p.ksz >> 1;
 
   for (int i = threadIdx.x; i < cin_p * cout_p; i += kDsThreads) {
     const int c = i / cout_p, co = i - c * cout_p;
@@ -144,14 +145,24 @@ __global__ void __launch_bounds__(kDsThreads) ds_layer_kernel(const DsLayerParam
     const long long rowid = gp / p.W;
     const int y = (int)(rowid % p.H);
     const float* ctr = p.src + (size_t)gp * p.src_pitch;
+    // all taps of a channel are loaded before the first FMA (memory-level parallelism: this phase is latency-bound)
+    bool ok[kk];
+    long long toff[kk];
+#pragma unroll
+    for (int t = 0; t < kk; ++t) {
+      const int dy = t / KSZ - half, dx = t % KSZ - half;
+      ok[t] = (unsigned)(y + dy) < (unsigned)p.H && (unsigned)(x + dx) < (unsigned)p.W;
+      toff[t] = ((long long)dy * p.W + dx) * p.src_pitch;
+    }
+#pragma unroll 2
     for (int c = l; c < cin_p; c += LP) {
+      float v[kk];
+#pragma unroll
+      for (int t = 0; t < kk; ++t) v[t] = (c < p.cin && ok[t]) ? __ldg(ctr + toff[t] + c) : 0.f;
       float acc = 0.f;
       if (c < p.cin) {
-        for (int t = 0; t < kk; ++t) {
-          const int dy = t / p.ksz - half, dx = t % p.ksz - half;
-          if ((unsigned)(y + dy) < (unsigned)p.H && (unsigned)(x + dx) < (unsigned)p.W)
-            acc = fmaf(__ldg(ctr + ((long long)dy * p.W + dx) * p.src_pitch + c), s_dw[t * p.cin + c], acc);
-        }
+#pragma unroll
+        for (int t = 0; t < kk; ++t) acc = fmaf(v[t], s_dw[t * p.cin + c], acc);
       }
       drow[c] = acc;
     }
@@ -161,6 +172,32 @@ __global__ void __launch_bounds__(kDsThreads) ds_layer_kernel(const DsLayerParam
   const int G = cout_p >> 2;               // float4 groups of output channels
   if (G * (kDsPix / 4) >= kDsThreads) ds_pointwise<4>(p, s_d, s_w, cin_p, cout_p, base, npix);
   else ds_pointwise<1>(p, s_d, s_w, cin_p, cout_p, base, npix);
+}
+
+// cin == cout == 1 (R-CNN1 of a depthwise-separable graph at HR resolution): one thread per pixel.
+template <int KSZ>
+__global__ void __launch_bounds__(256) ds_single_kernel(const DsLayerParams p) {
+  constexpr int kk = KSZ * KSZ, half = KSZ >> 1;
+  const long long total = (long long)p.n_img * p.H * p.W;
+  float w[kk];
+#pragma unroll
+  for (int t = 0; t < kk; ++t) w[t] = __ldg(p.dw + t) * __ldg(p.pw);
+  const float bias = p.bias ? __ldg(p.bias) : 0.f;
+  for (long long gp = (long long)blockIdx.x * blockDim.x + threadIdx.x; gp < total; gp += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(gp % p.W);
+    const int y = (int)((gp / p.W) % p.H);
+    const float* ctr = p.src + (size_t)gp * p.src_pitch;
+    float acc = bias;
+#pragma unroll
+    for (int t = 0; t < kk; ++t) {
+      const int dy = t / KSZ - half, dx = t % KSZ - half;
+      if ((unsigned)(y + dy) < (unsigned)p.H && (unsigned)(x + dx) < (unsigned)p.W)
+        acc = fmaf(__ldg(ctr + ((long long)dy * p.W + dx) * p.src_pitch), w[t], acc);
+    }
+    if (p.alpha) acc = acc > 0.f ? acc : __ldg(p.alpha) * acc;
+    if (p.add) acc += __ldg(p.add + gp);
+    p.dst[(size_t)gp * p.dst_pitch + p.dst_off] = acc;
+  }
 }
 
 }  // namespace dcscn

@@ -1137,15 +1137,23 @@ static int launch_ds(dcscn_handle* h, const LayerDef& l, const dcscn_handle::DsD
   p.n_img = n; p.H = H; p.W = W; p.ksz = l.k; p.cin = l.cin; p.cout = l.cout;
   p.src = src; p.src_pitch = src_pitch; p.dw = d.dw; p.pw = d.pw; p.bias = d.bias; p.alpha = d.alpha;
   p.dst = dst; p.dst_pitch = dst_pitch; p.dst_off = dst_off; p.d2s_r = d2s_r; p.d2s_cout = d2s_cout; p.add = add;
-  const size_t smem = ds_smem_bytes(l.k, l.cin, l.cout);
-  if (smem > 200 * 1024) return fail("depthwise-separable layer %s: %d -> %d channels exceed the kernel's shared memory", l.scope.c_str(), l.cin, l.cout);
-  static bool attr_set = false;
-  if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(ds_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
+  if (l.k != 1 && l.k != 3) return fail("depthwise-separable layer %s: kernel size %d is not supported (1 or 3)", l.scope.c_str(), l.k);
   const long long total = (long long)n * H * W;
-  ds_layer_kernel<<<(unsigned)((total + kDsPix - 1) / kDsPix), kDsThreads, smem, st>>>(p);
+  if (l.cin == 1 && l.cout == 1 && d2s_r == 0) {
+    const int grid = (int)std::min<long long>((total + 255) / 256, (long long)h->sm_count * 16);
+    if (l.k == 3) ds_single_kernel<3><<<grid, 256, 0, st>>>(p); else ds_single_kernel<1><<<grid, 256, 0, st>>>(p);
+  } else {
+    const size_t smem = ds_smem_bytes(l.k, l.cin, l.cout);
+    if (smem > 200 * 1024) return fail("depthwise-separable layer %s: %d -> %d channels exceed the kernel's shared memory", l.scope.c_str(), l.cin, l.cout);
+    static size_t ds_smem_attr = 48 * 1024;   // current opt-in limit of the DS kernels (process-wide, only ever raised)
+    if (smem > ds_smem_attr) {   // raise the opt-in limit only as far as needed (keeps the L1 carve-out large)
+      CUDA_TRY(cudaFuncSetAttribute(ds_layer_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CUDA_TRY(cudaFuncSetAttribute(ds_layer_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      ds_smem_attr = smem;
+    }
+    const unsigned grid = (unsigned)((total + kDsPix - 1) / kDsPix);
+    if (l.k == 3) ds_layer_kernel<3><<<grid, kDsThreads, smem, st>>>(p); else ds_layer_kernel<1><<<grid, kDsThreads, smem, st>>>(p);
+  }
   CUDA_TRY(cudaGetLastError());
   h->launches++;
   return mark(h, st);

@@ -69,22 +69,45 @@ struct LastWgradParams {
   int px_per_block;
 };
 
-__global__ void __launch_bounds__(1024) last_wgrad_kernel(const LastWgradParams p) {
+// One thread per channel (lanes) x pixel row (threadIdx.y): hr[q'][c] is loaded once and multiplied with the up to
+// k*k values dY[q' - off(tap)] (warp-uniform, broadcast loads): k*k accumulators per thread, reduced over the block.
+constexpr int kLastWgMaxTaps = 25;
+__global__ void __launch_bounds__(256) last_wgrad_kernel(const LastWgradParams p) {
+  extern __shared__ float s_red[];                 // [blockDim.y][taps * CP]
   const int taps = p.ksz * p.ksz, half = p.ksz >> 1;
+  const int CP = blockDim.x, R = blockDim.y;
   const size_t total = (size_t)p.n_img * p.H * p.W;
   const size_t q0 = (size_t)blockIdx.x * p.px_per_block;
   const size_t q1 = q0 + p.px_per_block < total ? q0 + p.px_per_block : total;
-  for (int tc = threadIdx.x; tc < taps * p.C; tc += blockDim.x) {
-    const int tap = tc / p.C, c = tc - tap * p.C;
-    const int dy = tap / p.ksz - half, dx = tap % p.ksz - half;
-    float acc = 0.f;
-    for (size_t q = q0; q < q1; ++q) {
+  for (int c0 = 0; c0 < p.C; c0 += CP) {
+    const int c = c0 + threadIdx.x;
+    float acc[kLastWgMaxTaps];
+#pragma unroll
+    for (int t = 0; t < kLastWgMaxTaps; ++t) acc[t] = 0.f;
+    for (size_t q = q0 + threadIdx.y; q < q1; q += R) {
       const int x = (int)(q % p.W), y = (int)((q / p.W) % p.H);
-      const int yy = y + dy, xx = x + dx;
-      if (yy < 0 || yy >= p.H || xx < 0 || xx >= p.W) continue;
-      acc = fmaf(__ldg(p.hr + (q + (ptrdiff_t)dy * p.W + dx) * p.pitch + c), __ldg(p.dY + q), acc);
+      const float hv = c < p.C ? __ldg(p.hr + q * p.pitch + c) : 0.f;
+#pragma unroll
+      for (int t = 0; t < kLastWgMaxTaps; ++t) {
+        if (t < taps) {
+          const int dy = t / p.ksz - half, dx = t % p.ksz - half;   // hr[q] is the (dy,dx) neighbour of pixel q - off
+          const int yy = y - dy, xx = x - dx;
+          if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W)
+            acc[t] = fmaf(hv, __ldg(p.dY + (ptrdiff_t)q - ((ptrdiff_t)dy * p.W + dx)), acc[t]);
+        }
+      }
     }
-    atomicAdd(p.dW + tc, acc);
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < kLastWgMaxTaps; ++t)
+      if (t < taps) s_red[((size_t)threadIdx.y * taps + t) * CP + threadIdx.x] = acc[t];
+    __syncthreads();
+    for (int i = threadIdx.y * CP + threadIdx.x; i < taps * CP; i += CP * R) {
+      const int t = i / CP, cc = i - t * CP;
+      float sum = 0.f;
+      for (int r = 0; r < R; ++r) sum += s_red[((size_t)r * taps + t) * CP + cc];
+      if (c0 + cc < p.C) atomicAdd(p.dW + t * p.C + c0 + cc, sum);
+    }
   }
 }
 
@@ -101,23 +124,53 @@ struct LastDgradParams {
   int pitch;
 };
 
+// One thread per HR pixel: its k*k dY neighbours are loaded once, then every channel is k*k FMAs against the filter in
+// shared memory (broadcast reads) and the C results go out as contiguous fp16 hi/lo runs of the LR pixel's
+// (i*r + j)*C + c column block.
 __global__ void __launch_bounds__(256) last_dgrad_s2d_kernel(const LastDgradParams p) {
-  const int cols = p.r * p.r * p.C, half = p.ksz >> 1;
+  extern __shared__ float s_w[];                   // [taps][C]
+  const int taps = p.ksz * p.ksz, half = p.ksz >> 1;
+  for (int i = threadIdx.x; i < taps * p.C; i += blockDim.x) s_w[i] = __ldg(p.w + i);
+  __syncthreads();
   const int HH = p.H * p.r, WW = p.W * p.r;
-  const size_t total = (size_t)p.n_img * p.H * p.W * cols;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-    const int col = (int)(idx % cols);
-    const size_t pix = idx / cols;
-    const int x = (int)(pix % p.W), y = (int)((pix / p.W) % p.H), img = (int)(pix / ((size_t)p.W * p.H));
-    const int ij = col / p.C, c = col - ij * p.C, i = ij / p.r, j = ij - i * p.r;
-    const int Y = y * p.r + i, X = x * p.r + j;
-    float acc = 0.f;
-    for (int tap = 0; tap < p.ksz * p.ksz; ++tap) {
-      const int yy = Y - (tap / p.ksz - half), xx = X - (tap % p.ksz - half);
-      if (yy < 0 || yy >= HH || xx < 0 || xx >= WW) continue;
-      acc = fmaf(__ldg(p.w + tap * p.C + c), __ldg(p.dY + ((size_t)img * HH + yy) * WW + xx), acc);
+  const size_t total = (size_t)p.n_img * HH * WW;
+  for (size_t Q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; Q < total; Q += (size_t)gridDim.x * blockDim.x) {
+    const int X = (int)(Q % WW), Y = (int)((Q / WW) % HH);
+    const size_t img = Q / ((size_t)WW * HH);
+    float dy[kLastWgMaxTaps];
+#pragma unroll
+    for (int t = 0; t < kLastWgMaxTaps; ++t) {
+      dy[t] = 0.f;
+      if (t < taps) {
+        const int yy = Y - (t / p.ksz - half), xx = X - (t % p.ksz - half);
+        if (yy >= 0 && yy < HH && xx >= 0 && xx < WW) dy[t] = __ldg(p.dY + (img * HH + yy) * WW + xx);
+      }
     }
-    store_planes(p.dz_hi, p.dz_lo, pix * p.pitch + col, acc);
+    const int y = Y / p.r, i = Y - y * p.r, x = X / p.r, j = X - x * p.r;
+    const size_t o = ((img * p.H + y) * p.W + x) * p.pitch + (size_t)(i * p.r + j) * p.C;
+    for (int c = 0; c < p.C; c += 2) {
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int t = 0; t < kLastWgMaxTaps; ++t)
+        if (t < taps) {
+          a0 = fmaf(s_w[t * p.C + c], dy[t], a0);
+          if (c + 1 < p.C) a1 = fmaf(s_w[t * p.C + c + 1], dy[t], a1);
+        }
+      __half h0, l0, h1, l1;
+      split_f16(a0, h0, l0);
+      split_f16(a1, h1, l1);
+      if (((o + c) & 1) == 0 && c + 1 < p.C) {
+        *reinterpret_cast<__half2*>(p.dz_hi + o + c) = __halves2half2(h0, h1);
+        if (p.dz_lo != nullptr) *reinterpret_cast<__half2*>(p.dz_lo + o + c) = __halves2half2(l0, l1);
+      } else {
+        p.dz_hi[o + c] = h0;
+        if (p.dz_lo != nullptr) p.dz_lo[o + c] = l0;
+        if (c + 1 < p.C) {
+          p.dz_hi[o + c + 1] = h1;
+          if (p.dz_lo != nullptr) p.dz_lo[o + c + 1] = l1;
+        }
+      }
+    }
   }
 }
 
@@ -168,35 +221,87 @@ struct ActGradParams {
   int px_per_block;
 };
 
+// blockDim = (channel pairs rounded up to a warp multiple, pixel rows): a thread keeps its channel pair and strides
+// over the block's pixels (half2 loads, two pixels in flight); bias / alpha sums are reduced over the rows in shared
+// memory, one atomic per channel per CTA.
+__device__ __forceinline__ float2 load_planes2(const __half* hi, const __half* lo, size_t i) {
+  float2 v = __half22float2(*reinterpret_cast<const __half2*>(hi + i));
+  if (lo != nullptr) {
+    const float2 l = __half22float2(*reinterpret_cast<const __half2*>(lo + i));
+    v.x += l.x;
+    v.y += l.y;
+  }
+  return v;
+}
+
 __global__ void __launch_bounds__(256) act_grad_kernel(const ActGradParams p) {
+  extern __shared__ float s_sum[];                 // [2][rows][2 * PP]
+  const int PP = blockDim.x, R = blockDim.y;
   const size_t q0 = (size_t)blockIdx.x * p.px_per_block;
   const size_t q1 = q0 + p.px_per_block < p.pixels ? q0 + p.px_per_block : p.pixels;
   const float inv_keep = 1.0f / p.keep;
-  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
-    const float a = p.alpha ? __ldg(p.alpha + c) : 1.f;
-    float sb = 0.f, sa = 0.f;
-    for (size_t q = q0; q < q1; ++q) {
-      float g = load_planes(p.g1_hi, p.g1_lo, q * p.g1_pitch + c);
-      if (p.g2_hi != nullptr) g += load_planes(p.g2_hi, p.g2_lo, q * p.g2_pitch + c);
-      float dz = g;
+  const int c = 2 * threadIdx.x;
+  const bool v0 = c < p.C, v1 = c + 1 < p.C;
+  float a0 = 1.f, a1 = 1.f;
+  if (p.alpha) {
+    if (v0) a0 = __ldg(p.alpha + c);
+    if (v1) a1 = __ldg(p.alpha + c + 1);
+  }
+  float sb0 = 0.f, sb1 = 0.f, sa0 = 0.f, sa1 = 0.f;
+  if (v0) {
+#pragma unroll 2
+    for (size_t q = q0 + threadIdx.y; q < q1; q += R) {
+      float2 g = load_planes2(p.g1_hi, p.g1_lo, q * p.g1_pitch + c);
+      if (p.g2_hi != nullptr) {
+        const float2 g2 = load_planes2(p.g2_hi, p.g2_lo, q * p.g2_pitch + c);
+        g.x += g2.x;
+        g.y += g2.y;
+      }
+      float2 dz = g;
       if (p.alpha != nullptr) {
         if (p.keep < 1.0f) {
-          const bool kept = dropout_keep(p.seed, p.layer, (uint64_t)q * (uint64_t)p.n_total + p.col0 + c, p.keep);
-          g = kept ? g * inv_keep : 0.f;
+          const uint64_t e = (uint64_t)q * (uint64_t)p.n_total + p.col0 + c;
+          g.x = dropout_keep(p.seed, p.layer, e, p.keep) ? g.x * inv_keep : 0.f;
+          g.y = dropout_keep(p.seed, p.layer, e + 1, p.keep) ? g.y * inv_keep : 0.f;
         }
-        const float out = load_planes(p.out_hi, p.out_lo, q * p.out_pitch + c);
-        if (out < 0.f) {
-          sa = fmaf(g, out * p.keep / a, sa);
-          dz = g * a;
-        } else {
-          dz = g;
+        const float2 out = load_planes2(p.out_hi, p.out_lo, q * p.out_pitch + c);
+        dz = g;
+        if (out.x < 0.f) {
+          sa0 = fmaf(g.x, out.x * p.keep / a0, sa0);
+          dz.x = g.x * a0;
+        }
+        if (out.y < 0.f) {
+          sa1 = fmaf(g.y, out.y * p.keep / a1, sa1);
+          dz.y = g.y * a1;
         }
       }
-      sb += dz;
-      store_planes(p.dz_hi, p.dz_lo, q * p.dz_pitch + c, dz);
+      if (!v1) dz.y = 0.f;                          // pad channels of the result stay zero
+      sb0 += dz.x;
+      sb1 += dz.y;
+      __half h0, l0, h1, l1;
+      split_f16(dz.x, h0, l0);
+      split_f16(dz.y, h1, l1);
+      *reinterpret_cast<__half2*>(p.dz_hi + q * p.dz_pitch + c) = __halves2half2(h0, h1);
+      if (p.dz_lo != nullptr) *reinterpret_cast<__half2*>(p.dz_lo + q * p.dz_pitch + c) = __halves2half2(l0, l1);
     }
-    if (p.dbias != nullptr) atomicAdd(p.dbias + c, sb);
-    if (p.dalpha != nullptr) atomicAdd(p.dalpha + c, sa);
+  }
+  if (p.dbias == nullptr && p.dalpha == nullptr) return;
+  float* sb = s_sum;
+  float* sa = s_sum + (size_t)R * 2 * PP;
+  sb[(size_t)threadIdx.y * 2 * PP + c] = sb0;
+  sb[(size_t)threadIdx.y * 2 * PP + c + 1] = sb1;
+  sa[(size_t)threadIdx.y * 2 * PP + c] = sa0;
+  sa[(size_t)threadIdx.y * 2 * PP + c + 1] = sa1;
+  __syncthreads();
+  for (int i = threadIdx.y * PP + threadIdx.x; i < 2 * PP; i += PP * R) {
+    if (i >= p.C) continue;
+    float tb = 0.f, ta = 0.f;
+    for (int r = 0; r < R; ++r) {
+      tb += sb[(size_t)r * 2 * PP + i];
+      ta += sa[(size_t)r * 2 * PP + i];
+    }
+    if (p.dbias != nullptr) atomicAdd(p.dbias + i, tb);
+    if (p.dalpha != nullptr) atomicAdd(p.dalpha + i, ta);
   }
 }
 
@@ -283,6 +388,56 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WgradParams p) {
       const int ci = ci0 + tci + i, co = co0 + tco + j;
       if (ci < p.cin && co < p.cout && acc[i][j] != 0.f) atomicAdd(p.dW + ((size_t)tap * p.cin + ci) * p.cout + co, acc[i][j]);
     }
+}
+
+// cin == 1 (CNN1: the input is the fp32 LR image): dW[tap][0][co] = sum_q x[q + off(tap)] * dZ[q][co].  One thread per
+// output channel x pixel row; dZ[q][co] is loaded once and meets the k*k neighbours of x (broadcast loads).
+struct FirstWgradParams {
+  int n_img, H, W, ksz, cout;
+  const float* x;               // [N,H,W]
+  const __half *dz_hi, *dz_lo;  // [pixels][dz_pitch]
+  int dz_pitch;
+  float* dW;                    // [taps][1][cout]
+  int px_per_block;
+};
+
+__global__ void __launch_bounds__(256) first_wgrad_kernel(const FirstWgradParams p) {
+  extern __shared__ float s_red[];                 // [blockDim.y][taps * CP]
+  const int taps = p.ksz * p.ksz, half = p.ksz >> 1;
+  const int CP = blockDim.x, R = blockDim.y;
+  const size_t total = (size_t)p.n_img * p.H * p.W;
+  const size_t q0 = (size_t)blockIdx.x * p.px_per_block;
+  const size_t q1 = q0 + p.px_per_block < total ? q0 + p.px_per_block : total;
+  for (int c0 = 0; c0 < p.cout; c0 += CP) {
+    const int c = c0 + threadIdx.x;
+    float acc[kLastWgMaxTaps];
+#pragma unroll
+    for (int t = 0; t < kLastWgMaxTaps; ++t) acc[t] = 0.f;
+    for (size_t q = q0 + threadIdx.y; q < q1; q += R) {
+      const int x = (int)(q % p.W), y = (int)((q / p.W) % p.H);
+      const float zv = c < p.cout ? load_planes(p.dz_hi, p.dz_lo, q * p.dz_pitch + c) : 0.f;
+#pragma unroll
+      for (int t = 0; t < kLastWgMaxTaps; ++t) {
+        if (t < taps) {
+          const int dy = t / p.ksz - half, dx = t % p.ksz - half;
+          const int yy = y + dy, xx = x + dx;
+          if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W)
+            acc[t] = fmaf(zv, __ldg(p.x + (ptrdiff_t)q + ((ptrdiff_t)dy * p.W + dx)), acc[t]);
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < kLastWgMaxTaps; ++t)
+      if (t < taps) s_red[((size_t)threadIdx.y * taps + t) * CP + threadIdx.x] = acc[t];
+    __syncthreads();
+    for (int i = threadIdx.y * CP + threadIdx.x; i < taps * CP; i += CP * R) {
+      const int t = i / CP, cc = i - t * CP;
+      float sum = 0.f;
+      for (int r = 0; r < R; ++r) sum += s_red[((size_t)r * taps + t) * CP + cc];
+      if (c0 + cc < p.cout) atomicAdd(p.dW + (size_t)t * p.cout + c0 + cc, sum);
+    }
+  }
 }
 
 // per-channel sum of a plane tensor (bias gradient of layers without activation)

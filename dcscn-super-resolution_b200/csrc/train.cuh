@@ -69,45 +69,75 @@ struct LastWgradParams {
   int px_per_block;
 };
 
-// One thread per channel (lanes) x pixel row (threadIdx.y): hr[q'][c] is loaded once and multiplied with the up to
-// k*k values dY[q' - off(tap)] (warp-uniform, broadcast loads): k*k accumulators per thread, reduced over the block.
+// Thread = (pixel slot, channel quad): hr[q'][4 channels] is one 16-byte load and meets the up to k*k values
+// dY[q' - off(tap)]; k*k x 4 accumulators per thread, reduced over the block's pixel slots in shared memory, one atomic
+// per (tap, channel) per CTA.  Needs C % 4 == 0 and pitch % 4 == 0 (else `last_wgrad_scalar_kernel`).
 constexpr int kLastWgMaxTaps = 25;
+template <int TAPS>
 __global__ void __launch_bounds__(256) last_wgrad_kernel(const LastWgradParams p) {
-  extern __shared__ float s_red[];                 // [blockDim.y][taps * CP]
+  extern __shared__ float s_red[];                 // [slots][TAPS][C]
+  constexpr int KS = TAPS == 9 ? 3 : (TAPS == 25 ? 5 : 1), half = KS >> 1;
+  const int quads = p.C >> 2;                      // threads per pixel
+  const int slots = blockDim.x / quads;            // pixels in flight per CTA
+  const int cq = threadIdx.x % quads, slot = threadIdx.x / quads;
+  const long long total = (long long)p.n_img * p.H * p.W;
+  const long long q0 = (long long)blockIdx.x * p.px_per_block;
+  const long long q1 = q0 + p.px_per_block < total ? q0 + p.px_per_block : total;
+  float acc[TAPS][4];
+#pragma unroll
+  for (int t = 0; t < TAPS; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
+  if (slot < slots) {
+    long long q = q0 + slot;
+    int x = (int)(q % p.W), y = (int)((q / p.W) % p.H);
+    for (; q < q1; q += slots) {
+      const float4 hv = __ldg(reinterpret_cast<const float4*>(p.hr + q * p.pitch) + cq);
+#pragma unroll
+      for (int t = 0; t < TAPS; ++t) {
+        const int dy = t / KS - half, dx = t % KS - half;   // hr[q] is the (dy,dx) neighbour of pixel q - off
+        const int yy = y - dy, xx = x - dx;
+        if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W) {
+          const float d = __ldg(p.dY + q - ((long long)dy * p.W + dx));
+          acc[t][0] = fmaf(hv.x, d, acc[t][0]);
+          acc[t][1] = fmaf(hv.y, d, acc[t][1]);
+          acc[t][2] = fmaf(hv.z, d, acc[t][2]);
+          acc[t][3] = fmaf(hv.w, d, acc[t][3]);
+        }
+      }
+      x += slots;
+      while (x >= p.W) {
+        x -= p.W;
+        if (++y == p.H) y = 0;
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < TAPS; ++t)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) s_red[((size_t)slot * TAPS + t) * p.C + 4 * cq + i] = acc[t][i];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < TAPS * p.C; i += blockDim.x) {
+    float sum = 0.f;
+    for (int r = 0; r < slots; ++r) sum += s_red[(size_t)r * TAPS * p.C + i];
+    atomicAdd(p.dW + i, sum);
+  }
+}
+
+__global__ void __launch_bounds__(256) last_wgrad_scalar_kernel(const LastWgradParams p) {
   const int taps = p.ksz * p.ksz, half = p.ksz >> 1;
-  const int CP = blockDim.x, R = blockDim.y;
   const size_t total = (size_t)p.n_img * p.H * p.W;
   const size_t q0 = (size_t)blockIdx.x * p.px_per_block;
   const size_t q1 = q0 + p.px_per_block < total ? q0 + p.px_per_block : total;
-  for (int c0 = 0; c0 < p.C; c0 += CP) {
-    const int c = c0 + threadIdx.x;
-    float acc[kLastWgMaxTaps];
-#pragma unroll
-    for (int t = 0; t < kLastWgMaxTaps; ++t) acc[t] = 0.f;
-    for (size_t q = q0 + threadIdx.y; q < q1; q += R) {
+  for (int tc = threadIdx.x; tc < taps * p.C; tc += blockDim.x) {
+    const int tap = tc / p.C, c = tc - tap * p.C;
+    const int dy = tap / p.ksz - half, dx = tap % p.ksz - half;
+    float acc = 0.f;
+    for (size_t q = q0; q < q1; ++q) {
       const int x = (int)(q % p.W), y = (int)((q / p.W) % p.H);
-      const float hv = c < p.C ? __ldg(p.hr + q * p.pitch + c) : 0.f;
-#pragma unroll
-      for (int t = 0; t < kLastWgMaxTaps; ++t) {
-        if (t < taps) {
-          const int dy = t / p.ksz - half, dx = t % p.ksz - half;   // hr[q] is the (dy,dx) neighbour of pixel q - off
-          const int yy = y - dy, xx = x - dx;
-          if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W)
-            acc[t] = fmaf(hv, __ldg(p.dY + (ptrdiff_t)q - ((ptrdiff_t)dy * p.W + dx)), acc[t]);
-        }
-      }
+      const int yy = y + dy, xx = x + dx;
+      if (yy < 0 || yy >= p.H || xx < 0 || xx >= p.W) continue;
+      acc = fmaf(__ldg(p.hr + (q + (ptrdiff_t)dy * p.W + dx) * p.pitch + c), __ldg(p.dY + q), acc);
     }
-    __syncthreads();
-#pragma unroll
-    for (int t = 0; t < kLastWgMaxTaps; ++t)
-      if (t < taps) s_red[((size_t)threadIdx.y * taps + t) * CP + threadIdx.x] = acc[t];
-    __syncthreads();
-    for (int i = threadIdx.y * CP + threadIdx.x; i < taps * CP; i += CP * R) {
-      const int t = i / CP, cc = i - t * CP;
-      float sum = 0.f;
-      for (int r = 0; r < R; ++r) sum += s_red[((size_t)r * taps + t) * CP + cc];
-      if (c0 + cc < p.C) atomicAdd(p.dW + t * p.C + c0 + cc, sum);
-    }
+    atomicAdd(p.dW + tc, acc);
   }
 }
 
@@ -148,28 +178,36 @@ __global__ void __launch_bounds__(256) last_dgrad_s2d_kernel(const LastDgradPara
     }
     const int y = Y / p.r, i = Y - y * p.r, x = X / p.r, j = X - x * p.r;
     const size_t o = ((img * p.H + y) * p.W + x) * p.pitch + (size_t)(i * p.r + j) * p.C;
-    for (int c = 0; c < p.C; c += 2) {
-      float a0 = 0.f, a1 = 0.f;
+    if ((p.C & 7) == 0 && (p.pitch & 7) == 0) {     // 8 channels -> one 16-byte store per plane
+      for (int c = 0; c < p.C; c += 8) {
+        uint32_t ph[4], pl[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+          for (int t = 0; t < kLastWgMaxTaps; ++t)
+            if (t < taps) {
+              const float2 w2 = *reinterpret_cast<const float2*>(s_w + t * p.C + c + 2 * k);
+              a0 = fmaf(w2.x, dy[t], a0);
+              a1 = fmaf(w2.y, dy[t], a1);
+            }
+          __half h0, l0, h1, l1;
+          split_f16(a0, h0, l0);
+          split_f16(a1, h1, l1);
+          ph[k] = pack_h2(h0, h1);
+          pl[k] = pack_h2(l0, l1);
+        }
+        *reinterpret_cast<uint4*>(p.dz_hi + o + c) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+        if (p.dz_lo != nullptr) *reinterpret_cast<uint4*>(p.dz_lo + o + c) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+      }
+      continue;
+    }
+    for (int c = 0; c < p.C; ++c) {
+      float a0 = 0.f;
 #pragma unroll
       for (int t = 0; t < kLastWgMaxTaps; ++t)
-        if (t < taps) {
-          a0 = fmaf(s_w[t * p.C + c], dy[t], a0);
-          if (c + 1 < p.C) a1 = fmaf(s_w[t * p.C + c + 1], dy[t], a1);
-        }
-      __half h0, l0, h1, l1;
-      split_f16(a0, h0, l0);
-      split_f16(a1, h1, l1);
-      if (((o + c) & 1) == 0 && c + 1 < p.C) {
-        *reinterpret_cast<__half2*>(p.dz_hi + o + c) = __halves2half2(h0, h1);
-        if (p.dz_lo != nullptr) *reinterpret_cast<__half2*>(p.dz_lo + o + c) = __halves2half2(l0, l1);
-      } else {
-        p.dz_hi[o + c] = h0;
-        if (p.dz_lo != nullptr) p.dz_lo[o + c] = l0;
-        if (c + 1 < p.C) {
-          p.dz_hi[o + c + 1] = h1;
-          if (p.dz_lo != nullptr) p.dz_lo[o + c + 1] = l1;
-        }
-      }
+        if (t < taps) a0 = fmaf(s_w[t * p.C + c], dy[t], a0);
+      store_planes(p.dz_hi, p.dz_lo, o + c, a0);
     }
   }
 }
@@ -184,7 +222,26 @@ struct S2dParams {
 };
 
 __global__ void __launch_bounds__(256) s2d_planes_kernel(const S2dParams p) {
-  const int cols = p.r * p.r * p.C;
+  const int rr = p.r * p.r;
+  if ((p.C & 7) == 0 && (p.src_pitch & 7) == 0 && (p.dst_pitch & 7) == 0) {   // 16-byte moves of 8 channels
+    const int g8 = p.C >> 3;
+    const size_t total = (size_t)p.n_img * p.H * p.W * rr * g8;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+      const int g = (int)(idx % g8);
+      size_t r1 = idx / g8;
+      const int ij = (int)(r1 % rr);
+      const size_t pix = r1 / rr;
+      const int i = ij / p.r, j = ij - i * p.r;
+      const int x = (int)(pix % p.W), y = (int)((pix / p.W) % p.H);
+      const size_t img = pix / ((size_t)p.W * p.H);
+      const size_t s = ((img * p.H * p.r + (size_t)(y * p.r + i)) * (p.W * p.r) + (size_t)(x * p.r + j)) * p.src_pitch + 8 * g;
+      const size_t d = pix * p.dst_pitch + (size_t)ij * p.C + 8 * g;
+      *reinterpret_cast<uint4*>(p.dst_hi + d) = __ldg(reinterpret_cast<const uint4*>(p.src_hi + s));
+      if (p.dst_lo != nullptr) *reinterpret_cast<uint4*>(p.dst_lo + d) = __ldg(reinterpret_cast<const uint4*>(p.src_lo + s));
+    }
+    return;
+  }
+  const int cols = rr * p.C;
   const size_t total = (size_t)p.n_img * p.H * p.W * cols;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     const int col = (int)(idx % cols);
@@ -445,12 +502,26 @@ struct ColSumParams {
   size_t pixels; int C; const __half *hi, *lo; int pitch; float* out; int px_per_block;
 };
 __global__ void __launch_bounds__(256) colsum_kernel(const ColSumParams p) {
+  // blockDim = (channel lanes, pixel rows); per-thread partial sums, reduced over the rows in shared memory
+  extern __shared__ float s_cs[];                  // [rows][lanes]
+  const int CP = blockDim.x, R = blockDim.y;
   const size_t q0 = (size_t)blockIdx.x * p.px_per_block;
   const size_t q1 = q0 + p.px_per_block < p.pixels ? q0 + p.px_per_block : p.pixels;
-  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
-    float s = 0.f;
-    for (size_t q = q0; q < q1; ++q) s += load_planes(p.hi, p.lo, q * p.pitch + c);
-    atomicAdd(p.out + c, s);
+  for (int c0 = 0; c0 < p.C; c0 += CP) {
+    const int c = c0 + threadIdx.x;
+    float sum = 0.f;
+    if (c < p.C) {
+#pragma unroll 4
+      for (size_t q = q0 + threadIdx.y; q < q1; q += R) sum += load_planes(p.hi, p.lo, q * p.pitch + c);
+    }
+    __syncthreads();
+    s_cs[threadIdx.y * CP + threadIdx.x] = sum;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < p.C) {
+      float tot = 0.f;
+      for (int r = 0; r < R; ++r) tot += s_cs[r * CP + threadIdx.x];
+      atomicAdd(p.out + c, tot);
+    }
   }
 }
 

@@ -196,33 +196,40 @@ __global__ void __launch_bounds__(256) conv_last_kernel(const ConvLastParams p) 
   }
 }
 
-// Same layer straight from global memory (used by the train step, where the HR feature map is materialised anyway):
-// one thread per output pixel, 16-byte loads of the 9 neighbours' channel vectors (L1 hits), filter in shared memory
-// (broadcast float4 reads).  Needs C % 4 == 0 and pitch % 4 == 0.
+// Same layer straight from global memory (used by the train step, where the HR feature map is materialised anyway).
+// Thread = (pixel, channel quad): a warp's 16-byte loads cover whole 128-byte lines of consecutive pixels; the quads
+// of a pixel are summed with shuffles.  Needs C % 4 == 0, pitch % 4 == 0 and C / 4 a power of two <= 32.
 __global__ void __launch_bounds__(256) conv_last_direct_kernel(const ConvLastParams p) {
   extern __shared__ float4 s_w4[];                 // [taps][C / 4]
-  const int taps = p.ksz * p.ksz, half = p.ksz >> 1, c4n = p.C >> 2;
-  for (int i = threadIdx.x; i < taps * c4n; i += blockDim.x) s_w4[i] = __ldg(reinterpret_cast<const float4*>(p.w) + i);
+  const int taps = p.ksz * p.ksz, half = p.ksz >> 1, quads = p.C >> 2;
+  for (int i = threadIdx.x; i < taps * quads; i += blockDim.x) s_w4[i] = __ldg(reinterpret_cast<const float4*>(p.w) + i);
   __syncthreads();
+  const int cq = threadIdx.x % quads;
+  const int ppb = blockDim.x / quads;               // pixels per CTA pass
   const long long total = (long long)p.n_img * p.H * p.W;
-  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(q % p.W), y = (int)((q / p.W) % p.H);
-    float a0 = p.bias, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    for (int t = 0; t < taps; ++t) {
-      const int dy = t / p.ksz - half, dx = t % p.ksz - half;
-      if ((unsigned)(y + dy) >= (unsigned)p.H || (unsigned)(x + dx) >= (unsigned)p.W) continue;
-      const float4* src = reinterpret_cast<const float4*>(p.src + (q + (long long)dy * p.W + dx) * p.pitch);
-      const float4* w = s_w4 + t * c4n;
-#pragma unroll 8
-      for (int c = 0; c < c4n; ++c) {
-        const float4 v = __ldg(src + c), ww = w[c];
-        a0 = fmaf(v.x, ww.x, a0);
-        a1 = fmaf(v.y, ww.y, a1);
-        a2 = fmaf(v.z, ww.z, a2);
-        a3 = fmaf(v.w, ww.w, a3);
+  const long long rounds = (total + ppb - 1) / ppb;
+  for (long long rd = blockIdx.x; rd < rounds; rd += gridDim.x) {
+    const long long q = rd * ppb + threadIdx.x / quads;
+    float acc = 0.f;
+    if (q < total) {
+      const int x = (int)(q % p.W), y = (int)((q / p.W) % p.H);
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 9
+      for (int t = 0; t < taps; ++t) {
+        const int dy = t / p.ksz - half, dx = t % p.ksz - half;
+        if ((unsigned)(y + dy) < (unsigned)p.H && (unsigned)(x + dx) < (unsigned)p.W) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(p.src + (q + (long long)dy * p.W + dx) * p.pitch) + cq);
+          const float4 ww = s_w4[t * quads + cq];
+          a0 = fmaf(v.x, ww.x, a0);
+          a1 = fmaf(v.y, ww.y, a1);
+          a2 = fmaf(v.z, ww.z, a2);
+          a3 = fmaf(v.w, ww.w, a3);
+        }
       }
+      acc = (a0 + a1) + (a2 + a3);
     }
-    p.y[q] = (a0 + a1) + (a2 + a3) + __ldg(p.x2 + q);
+    for (int o = quads >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (cq == 0 && q < total) p.y[q] = acc + p.bias + __ldg(p.x2 + q);
   }
 }
 

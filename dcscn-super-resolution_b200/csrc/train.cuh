@@ -154,17 +154,21 @@ struct LastDgradParams {
   int pitch;
 };
 
-// One thread per HR pixel: its k*k dY neighbours are loaded once, then every channel is k*k FMAs against the filter in
-// shared memory (broadcast reads) and the C results go out as contiguous fp16 hi/lo runs of the LR pixel's
-// (i*r + j)*C + c column block.
+// Thread = (HR pixel, 8-channel group): the pixel's k*k dY neighbours are loaded (shared by the lanes of the pixel),
+// 8 channels are k*k FMAs each against the filter in shared memory and leave as one 16-byte store per plane, so a warp
+// writes whole lines of the LR pixel's (i*r + j)*C + c column block.  Other channel counts: one thread per pixel.
 __global__ void __launch_bounds__(256) last_dgrad_s2d_kernel(const LastDgradParams p) {
   extern __shared__ float s_w[];                   // [taps][C]
   const int taps = p.ksz * p.ksz, half = p.ksz >> 1;
   for (int i = threadIdx.x; i < taps * p.C; i += blockDim.x) s_w[i] = __ldg(p.w + i);
   __syncthreads();
   const int HH = p.H * p.r, WW = p.W * p.r;
-  const size_t total = (size_t)p.n_img * HH * WW;
-  for (size_t Q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; Q < total; Q += (size_t)gridDim.x * blockDim.x) {
+  const bool vec = (p.C & 7) == 0 && (p.pitch & 7) == 0;
+  const int groups = vec ? p.C >> 3 : 1;
+  const size_t total = (size_t)p.n_img * HH * WW * groups;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % groups);
+    const size_t Q = idx / groups;
     const int X = (int)(Q % WW), Y = (int)((Q / WW) % HH);
     const size_t img = Q / ((size_t)WW * HH);
     float dy[kLastWgMaxTaps];
@@ -178,28 +182,27 @@ __global__ void __launch_bounds__(256) last_dgrad_s2d_kernel(const LastDgradPara
     }
     const int y = Y / p.r, i = Y - y * p.r, x = X / p.r, j = X - x * p.r;
     const size_t o = ((img * p.H + y) * p.W + x) * p.pitch + (size_t)(i * p.r + j) * p.C;
-    if ((p.C & 7) == 0 && (p.pitch & 7) == 0) {     // 8 channels -> one 16-byte store per plane
-      for (int c = 0; c < p.C; c += 8) {
-        uint32_t ph[4], pl[4];
+    if (vec) {
+      const int c = 8 * g;
+      uint32_t ph[4], pl[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          float a0 = 0.f, a1 = 0.f;
+      for (int k = 0; k < 4; ++k) {
+        float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-          for (int t = 0; t < kLastWgMaxTaps; ++t)
-            if (t < taps) {
-              const float2 w2 = *reinterpret_cast<const float2*>(s_w + t * p.C + c + 2 * k);
-              a0 = fmaf(w2.x, dy[t], a0);
-              a1 = fmaf(w2.y, dy[t], a1);
-            }
-          __half h0, l0, h1, l1;
-          split_f16(a0, h0, l0);
-          split_f16(a1, h1, l1);
-          ph[k] = pack_h2(h0, h1);
-          pl[k] = pack_h2(l0, l1);
-        }
-        *reinterpret_cast<uint4*>(p.dz_hi + o + c) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-        if (p.dz_lo != nullptr) *reinterpret_cast<uint4*>(p.dz_lo + o + c) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+        for (int t = 0; t < kLastWgMaxTaps; ++t)
+          if (t < taps) {
+            const float2 w2 = *reinterpret_cast<const float2*>(s_w + t * p.C + c + 2 * k);
+            a0 = fmaf(w2.x, dy[t], a0);
+            a1 = fmaf(w2.y, dy[t], a1);
+          }
+        __half h0, l0, h1, l1;
+        split_f16(a0, h0, l0);
+        split_f16(a1, h1, l1);
+        ph[k] = pack_h2(h0, h1);
+        pl[k] = pack_h2(l0, l1);
       }
+      *reinterpret_cast<uint4*>(p.dz_hi + o + c) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+      if (p.dz_lo != nullptr) *reinterpret_cast<uint4*>(p.dz_lo + o + c) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
       continue;
     }
     for (int c = 0; c < p.C; ++c) {
@@ -502,25 +505,31 @@ struct ColSumParams {
   size_t pixels; int C; const __half *hi, *lo; int pitch; float* out; int px_per_block;
 };
 __global__ void __launch_bounds__(256) colsum_kernel(const ColSumParams p) {
-  // blockDim = (channel lanes, pixel rows); per-thread partial sums, reduced over the rows in shared memory
-  extern __shared__ float s_cs[];                  // [rows][lanes]
+  // blockDim = (channel-pair lanes, pixel rows); half2 loads, per-thread partial sums reduced over the rows in smem
+  extern __shared__ float s_cs[];                  // [rows][2 * lanes]
   const int CP = blockDim.x, R = blockDim.y;
   const size_t q0 = (size_t)blockIdx.x * p.px_per_block;
   const size_t q1 = q0 + p.px_per_block < p.pixels ? q0 + p.px_per_block : p.pixels;
-  for (int c0 = 0; c0 < p.C; c0 += CP) {
-    const int c = c0 + threadIdx.x;
-    float sum = 0.f;
-    if (c < p.C) {
+  for (int c0 = 0; c0 < p.C; c0 += 2 * CP) {
+    const int c = c0 + 2 * threadIdx.x;
+    float s0 = 0.f, s1 = 0.f;
+    if (c < p.C) {                                  // pitch is even and >= C rounded up to 2: the pair is in bounds
 #pragma unroll 4
-      for (size_t q = q0 + threadIdx.y; q < q1; q += R) sum += load_planes(p.hi, p.lo, q * p.pitch + c);
+      for (size_t q = q0 + threadIdx.y; q < q1; q += R) {
+        const float2 v = load_planes2(p.hi, p.lo, q * p.pitch + c);
+        s0 += v.x;
+        s1 += v.y;
+      }
     }
     __syncthreads();
-    s_cs[threadIdx.y * CP + threadIdx.x] = sum;
+    s_cs[threadIdx.y * 2 * CP + 2 * threadIdx.x] = s0;
+    s_cs[threadIdx.y * 2 * CP + 2 * threadIdx.x + 1] = s1;
     __syncthreads();
-    if (threadIdx.y == 0 && c < p.C) {
+    for (int i = threadIdx.y * CP + threadIdx.x; i < 2 * CP; i += CP * R) {
+      if (c0 + i >= p.C) continue;
       float tot = 0.f;
-      for (int r = 0; r < R; ++r) tot += s_cs[r * CP + threadIdx.x];
-      atomicAdd(p.out + c, tot);
+      for (int r = 0; r < R; ++r) tot += s_cs[r * 2 * CP + i];
+      atomicAdd(p.out + c0 + i, tot);
     }
   }
 }

@@ -198,20 +198,23 @@ __global__ void __launch_bounds__(256) conv_last_kernel(const ConvLastParams p) 
 
 // Same layer straight from global memory (used by the train step, where the HR feature map is materialised anyway).
 // Thread = (pixel, channel quad): a warp's 16-byte loads cover whole 128-byte lines of consecutive pixels; the quads
-// of a pixel are summed with shuffles.  Needs C % 4 == 0, pitch % 4 == 0 and C / 4 a power of two <= 32.
+// of a pixel (a power-of-two lane group, the lanes beyond C / 4 idle) are summed with shuffles.  Needs C % 4 == 0,
+// pitch % 4 == 0 and C <= 128.
 __global__ void __launch_bounds__(256) conv_last_direct_kernel(const ConvLastParams p) {
   extern __shared__ float4 s_w4[];                 // [taps][C / 4]
   const int taps = p.ksz * p.ksz, half = p.ksz >> 1, quads = p.C >> 2;
   for (int i = threadIdx.x; i < taps * quads; i += blockDim.x) s_w4[i] = __ldg(reinterpret_cast<const float4*>(p.w) + i);
   __syncthreads();
-  const int cq = threadIdx.x % quads;
-  const int ppb = blockDim.x / quads;               // pixels per CTA pass
+  int lpp = 1;                                      // lanes per pixel
+  while (lpp < quads) lpp <<= 1;
+  const int cq = threadIdx.x % lpp;
+  const int ppb = blockDim.x / lpp;                 // pixels per CTA pass
   const long long total = (long long)p.n_img * p.H * p.W;
   const long long rounds = (total + ppb - 1) / ppb;
   for (long long rd = blockIdx.x; rd < rounds; rd += gridDim.x) {
-    const long long q = rd * ppb + threadIdx.x / quads;
+    const long long q = rd * ppb + threadIdx.x / lpp;
     float acc = 0.f;
-    if (q < total) {
+    if (q < total && cq < quads) {
       const int x = (int)(q % p.W), y = (int)((q / p.W) % p.H);
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll 9
@@ -228,7 +231,7 @@ __global__ void __launch_bounds__(256) conv_last_direct_kernel(const ConvLastPar
       }
       acc = (a0 + a1) + (a2 + a3);
     }
-    for (int o = quads >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    for (int o = lpp >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (cq == 0 && q < total) p.y[q] = acc + p.bias + __ldg(p.x2 + q);
   }
 }

@@ -96,42 +96,73 @@ __global__ void __launch_bounds__(256) conv_first3x3_kernel(const ConvFirstParam
   const long long total = (long long)p.g.n_img * p.g.H * p.g.W;
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (long long pix = warp0; pix < total; pix += nwarps) {
-    const int x = (int)(pix % p.g.W);
-    const int y = (int)((pix / p.g.W) % p.g.H);
-    const float* row = p.x + (pix - x);            // start of this image row
-    float acc[8];
+  constexpr int RUN = 32;                          // consecutive pixels per warp visit: a sliding 3x3 window, 3 loads / pixel
+  const int W = p.g.W, H = p.g.H;
+  for (long long pix0 = warp0 * RUN; pix0 < total; pix0 += nwarps * RUN) {
+    const long long pix1 = pix0 + RUN < total ? pix0 + RUN : total;
+    int x = (int)(pix0 % W);
+    int y = (int)((pix0 / W) % H);
+    float c0v[3], c1v[3], c2v[3];                  // window columns x-1, x, x+1 (rows y-1, y, y+1)
+    auto load_col = [&](long long pix, int yy0, int xx, float (&col)[3]) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-#pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      const int dy = t / 3 - 1, dx = t % 3 - 1;
-      const int yy = y + dy, xx = x + dx;
-      const float v = (yy >= 0 && yy < p.g.H && xx >= 0 && xx < p.g.W) ? __ldg(row + (long long)dy * p.g.W + xx) : 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = fmaf(v, w[t][i], acc[i]);
-    }
-    uint32_t ph[4], pl[4];
-#pragma unroll
-    for (int i = 0; i < 8; i += 2) {
-      float t0 = acc[i] + bias[i], t1 = acc[i + 1] + bias[i + 1];
-      t0 = t0 > 0.f ? t0 : alpha[i] * t0;
-      t1 = t1 > 0.f ? t1 : alpha[i + 1] * t1;
-      if (keep < 1.0f) {
-        const uint64_t base = (uint64_t)pix * (uint64_t)p.n_pad + c0 + i;
-        t0 = dropout_keep(p.epi.drop_seed, p.epi.drop_layer, base, keep) ? t0 * inv_keep : 0.f;
-        t1 = dropout_keep(p.epi.drop_seed, p.epi.drop_layer, base + 1, keep) ? t1 * inv_keep : 0.f;
+      for (int r = 0; r < 3; ++r) {
+        const int yy = yy0 + r - 1;
+        col[r] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(p.x + pix + (long long)(r - 1) * W + (xx - x)) : 0.f;
       }
-      __half h0, l0, h1, l1;
-      split_f16(t0, h0, l0);
-      split_f16(t1, h1, l1);
-      ph[i >> 1] = pack_h2(h0, h1);
-      pl[i >> 1] = pack_h2(l0, l1);
-    }
-    if (active) {
-      const size_t off = (size_t)pix * seg.pitch + c0;
-      *reinterpret_cast<uint4*>(seg.dst_hi + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-      if (seg.dst_lo != nullptr) *reinterpret_cast<uint4*>(seg.dst_lo + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+    };
+    load_col(pix0, y, x - 1, c0v);
+    load_col(pix0, y, x, c1v);
+    for (long long pix = pix0; pix < pix1; ++pix) {
+      load_col(pix, y, x + 1, c2v);
+      float acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          acc[i] = fmaf(c0v[r], w[3 * r + 0][i], acc[i]);
+          acc[i] = fmaf(c1v[r], w[3 * r + 1][i], acc[i]);
+          acc[i] = fmaf(c2v[r], w[3 * r + 2][i], acc[i]);
+        }
+      }
+      uint32_t ph[4], pl[4];
+#pragma unroll
+      for (int i = 0; i < 8; i += 2) {
+        float t0 = acc[i] + bias[i], t1 = acc[i + 1] + bias[i + 1];
+        t0 = t0 > 0.f ? t0 : alpha[i] * t0;
+        t1 = t1 > 0.f ? t1 : alpha[i + 1] * t1;
+        if (keep < 1.0f) {
+          const uint64_t base = (uint64_t)pix * (uint64_t)p.n_pad + c0 + i;
+          t0 = dropout_keep(p.epi.drop_seed, p.epi.drop_layer, base, keep) ? t0 * inv_keep : 0.f;
+          t1 = dropout_keep(p.epi.drop_seed, p.epi.drop_layer, base + 1, keep) ? t1 * inv_keep : 0.f;
+        }
+        __half h0, l0, h1, l1;
+        split_f16(t0, h0, l0);
+        split_f16(t1, h1, l1);
+        ph[i >> 1] = pack_h2(h0, h1);
+        pl[i >> 1] = pack_h2(l0, l1);
+      }
+      if (active) {
+        const size_t off = (size_t)pix * seg.pitch + c0;
+        *reinterpret_cast<uint4*>(seg.dst_hi + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+        if (seg.dst_lo != nullptr) *reinterpret_cast<uint4*>(seg.dst_lo + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+      }
+      if (++x == W) {                                // next image row (or next image): rebuild the window
+        x = 0;
+        if (++y == H) y = 0;
+        if (pix + 1 < pix1) {
+#pragma unroll
+          for (int r = 0; r < 3; ++r) c0v[r] = 0.f;
+          load_col(pix + 1, y, 0, c1v);
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          c0v[r] = c1v[r];
+          c1v[r] = c2v[r];
+        }
+      }
     }
   }
 }

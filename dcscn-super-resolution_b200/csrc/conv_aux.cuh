@@ -246,7 +246,8 @@ __global__ void __launch_bounds__(256) conv_last_direct_kernel(const ConvLastPar
     const long long q = rd * ppb + threadIdx.x / lpp;
     float acc = 0.f;
     if (q < total && cq < quads) {
-      const int x = (int)(q % p.W), y = (int)((q / p.W) % p.H);
+      const unsigned q32 = (unsigned)q, row32 = q32 / (unsigned)p.W;   // < 2^32 pixels (launcher)
+      const int x = (int)(q32 - row32 * (unsigned)p.W), y = (int)(row32 % (unsigned)p.H);
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll 9
       for (int t = 0; t < taps; ++t) {

@@ -45,8 +45,8 @@ inline size_t ds_smem_bytes(int ksz, int cin, int cout) {
 
 // Pointwise contraction + bias + PReLU + store for PXT pixels x 4 output channels per thread (pixels pg + j * PG).
 template <int PXT>
-__device__ __forceinline__ void ds_pointwise(const DsLayerParams& p, const float* s_d, const float* s_w, int cin_p, int cout_p,
-                                             long long base, int npix) {
+__device__ __forceinline__ void ds_pointwise(const DsLayerParams& p, const float* s_d, const float* s_w, const int* s_x,
+                                             const int* s_y, int cin_p, int cout_p, long long base, int npix) {
   const int G = cout_p >> 2;
   constexpr int PG = kDsPix / PXT;
   for (int item = threadIdx.x; item < G * PG; item += kDsThreads) {
@@ -76,14 +76,9 @@ __device__ __forceinline__ void ds_pointwise(const DsLayerParams& p, const float
       const int px = pg + PG * j;
       if (px >= npix) continue;
       const long long gp = base + px;
-      int x = 0, y = 0;
-      long long img = 0;
-      if (p.d2s_r != 0) {
-        x = (int)(gp % p.W);
-        const long long rowid = gp / p.W;
-        y = (int)(rowid % p.H);
-        img = rowid / p.H;
-      }
+      const int x = s_x[px], y = s_y[px];
+      // first pixel of this image row block in the r-times larger output: (img*H*W) * r*r, then (y*r + i, x*r + j)
+      const long long img_px = gp - ((long long)y * p.W + x);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int co = 4 * g + q;
@@ -98,7 +93,7 @@ __device__ __forceinline__ void ds_pointwise(const DsLayerParams& p, const float
           // DCR: input channel (i*r + j)*C + c -> (y*r + i, x*r + j, c)   (tf.depth_to_space, tf_graph.py:248)
           const int r = p.d2s_r, ij = co / p.d2s_cout, c = co - ij * p.d2s_cout;
           const int ii = ij / r, jj = ij - ii * r;
-          const size_t o = (((size_t)img * p.H * r + (size_t)(y * r + ii)) * (p.W * r) + (size_t)(x * r + jj));
+          const size_t o = (size_t)img_px * r * r + (size_t)(y * r + ii) * (p.W * r) + (size_t)(x * r + jj);
           p.dst[o * p.dst_pitch + c] = v;
         }
       }
@@ -122,6 +117,12 @@ __global__ void __launch_bounds__(kDsThreads) ds_layer_kernel(const DsLayerParam
   const long long base = (long long)blockIdx.x * kDsPix;
   const int npix = (int)((total - base) < kDsPix ? (total - base) : kDsPix);
 
+  __shared__ int s_x[kDsPix], s_y[kDsPix];        // pixel coordinates, computed once (64-bit divisions are expensive)
+  if (threadIdx.x < kDsPix) {
+    const long long gp = base + threadIdx.x;
+    s_x[threadIdx.x] = (int)(gp % p.W);
+    s_y[threadIdx.x] = (int)((gp / p.W) % p.H);
+  }
   for (int i = threadIdx.x; i < cin_p * cout_p; i += kDsThreads) {
     const int c = i / cout_p, co = i - c * cout_p;
     s_w[i] = (c < p.cin && co < p.cout) ? __ldg(p.pw + (size_t)c * p.cout + co) : 0.f;
@@ -141,9 +142,7 @@ __global__ void __launch_bounds__(kDsThreads) ds_layer_kernel(const DsLayerParam
       continue;
     }
     const long long gp = base + px;
-    const int x = (int)(gp % p.W);
-    const long long rowid = gp / p.W;
-    const int y = (int)(rowid % p.H);
+    const int x = s_x[px], y = s_y[px];
     const float* ctr = p.src + (size_t)gp * p.src_pitch;
     // all taps of a channel are loaded before the first FMA (memory-level parallelism: this phase is latency-bound)
     bool ok[kk];
@@ -170,8 +169,8 @@ __global__ void __launch_bounds__(kDsThreads) ds_layer_kernel(const DsLayerParam
   __syncthreads();
 
   const int G = cout_p >> 2;               // float4 groups of output channels
-  if (G * (kDsPix / 4) >= kDsThreads) ds_pointwise<4>(p, s_d, s_w, cin_p, cout_p, base, npix);
-  else ds_pointwise<1>(p, s_d, s_w, cin_p, cout_p, base, npix);
+  if (G * (kDsPix / 4) >= kDsThreads) ds_pointwise<4>(p, s_d, s_w, s_x, s_y, cin_p, cout_p, base, npix);
+  else ds_pointwise<1>(p, s_d, s_w, s_x, s_y, cin_p, cout_p, base, npix);
 }
 
 // cin == cout == 1 (R-CNN1 of a depthwise-separable graph at HR resolution): one thread per pixel.
@@ -184,8 +183,10 @@ __global__ void __launch_bounds__(256) ds_single_kernel(const DsLayerParams p) {
   for (int t = 0; t < kk; ++t) w[t] = __ldg(p.dw + t) * __ldg(p.pw);
   const float bias = p.bias ? __ldg(p.bias) : 0.f;
   for (long long gp = (long long)blockIdx.x * blockDim.x + threadIdx.x; gp < total; gp += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(gp % p.W);
-    const int y = (int)((gp / p.W) % p.H);
+    const unsigned g32 = (unsigned)gp;                     // total < 2^32 pixels (checked by the launcher)
+    const unsigned row = g32 / (unsigned)p.W;
+    const int x = (int)(g32 - row * (unsigned)p.W);
+    const int y = (int)(row % (unsigned)p.H);
     const float* ctr = p.src + (size_t)gp * p.src_pitch;
     float acc = bias;
 #pragma unroll

@@ -1139,7 +1139,7 @@ static int launch_ds(dcscn_handle* h, const LayerDef& l, const dcscn_handle::DsD
   p.dst = dst; p.dst_pitch = dst_pitch; p.dst_off = dst_off; p.d2s_r = d2s_r; p.d2s_cout = d2s_cout; p.add = add;
   if (l.k != 1 && l.k != 3) return fail("depthwise-separable layer %s: kernel size %d is not supported (1 or 3)", l.scope.c_str(), l.k);
   const long long total = (long long)n * H * W;
-  if (l.cin == 1 && l.cout == 1 && d2s_r == 0) {
+  if (l.cin == 1 && l.cout == 1 && d2s_r == 0 && total < (1ll << 32)) {
     const int grid = (int)std::min<long long>((total + 255) / 256, (long long)h->sm_count * 16);
     if (l.k == 3) ds_single_kernel<3><<<grid, 256, 0, st>>>(p); else ds_single_kernel<1><<<grid, 256, 0, st>>>(p);
   } else {

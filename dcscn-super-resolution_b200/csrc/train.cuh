@@ -167,10 +167,14 @@ __global__ void __launch_bounds__(256) last_dgrad_s2d_kernel(const LastDgradPara
   const int groups = vec ? p.C >> 3 : 1;
   const size_t total = (size_t)p.n_img * HH * WW * groups;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-    const int g = (int)(idx % groups);
-    const size_t Q = idx / groups;
-    const int X = (int)(Q % WW), Y = (int)((Q / WW) % HH);
-    const size_t img = Q / ((size_t)WW * HH);
+    // 32-bit index math (the launcher guarantees fewer than 2^32 elements; 64-bit divisions dominate otherwise)
+    const unsigned i32 = (unsigned)idx;
+    const unsigned Q32 = i32 / (unsigned)groups;
+    const int g = (int)(i32 - Q32 * (unsigned)groups);
+    const size_t Q = Q32;
+    const unsigned R32 = Q32 / (unsigned)WW;
+    const int X = (int)(Q32 - R32 * (unsigned)WW), Y = (int)(R32 % (unsigned)HH);
+    const size_t img = R32 / (unsigned)HH;
     float dy[kLastWgMaxTaps];
 #pragma unroll
     for (int t = 0; t < kLastWgMaxTaps; ++t) {
@@ -230,13 +234,16 @@ __global__ void __launch_bounds__(256) s2d_planes_kernel(const S2dParams p) {
     const int g8 = p.C >> 3;
     const size_t total = (size_t)p.n_img * p.H * p.W * rr * g8;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-      const int g = (int)(idx % g8);
-      size_t r1 = idx / g8;
-      const int ij = (int)(r1 % rr);
-      const size_t pix = r1 / rr;
+      const unsigned i32 = (unsigned)idx;           // < 2^32 elements (launcher)
+      const unsigned r1 = i32 / (unsigned)g8;
+      const int g = (int)(i32 - r1 * (unsigned)g8);
+      const unsigned pix32 = r1 / (unsigned)rr;
+      const int ij = (int)(r1 - pix32 * (unsigned)rr);
+      const size_t pix = pix32;
       const int i = ij / p.r, j = ij - i * p.r;
-      const int x = (int)(pix % p.W), y = (int)((pix / p.W) % p.H);
-      const size_t img = pix / ((size_t)p.W * p.H);
+      const unsigned row32 = pix32 / (unsigned)p.W;
+      const int x = (int)(pix32 - row32 * (unsigned)p.W), y = (int)(row32 % (unsigned)p.H);
+      const size_t img = row32 / (unsigned)p.H;
       const size_t s = ((img * p.H * p.r + (size_t)(y * p.r + i)) * (p.W * p.r) + (size_t)(x * p.r + j)) * p.src_pitch + 8 * g;
       const size_t d = pix * p.dst_pitch + (size_t)ij * p.C + 8 * g;
       *reinterpret_cast<uint4*>(p.dst_hi + d) = __ldg(reinterpret_cast<const uint4*>(p.src_hi + s));

@@ -93,6 +93,17 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def ncu_traffic():
+    """DRAM bytes (read + write) of the same tcgen05 conv launches of one step, from the committed `ncu --set full`
+    capture (profiles/r1d_traffic.json, made from profiles/r1d_conv_tc_ncu_summary.csv); None if it is missing."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1d_traffic.json")) as f:
+            t = json.load(f)
+        return int(t["dram_bytes_read"] + t["dram_bytes_write"]), t["source"]
+    except (OSError, KeyError, ValueError):
+        return None, None
+
+
 def cpu_oracle_rate(seconds_target, tiles_per_call=32):
     """Oracle (torch-CPU fp32) throughput in output Mpixels/s on a bounded sample of the same workload."""
     import numpy as np
@@ -237,7 +248,8 @@ def run_ours(args, rank, world, local_rank):
             "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (%s)" % how,
             "mma_passes": passes, "frac_of_issued_mma": achieved * passes / sustained,
-            "traffic": None,
+            "traffic": ncu_traffic()[0], "traffic_unit": "DRAM bytes (read + write) of the same launches of one step",
+            "traffic_source": ncu_traffic()[1],
             "hbm_gbs_model": 24700.0 * lr_px / (ms / args.steps / 1e3) / 1e9,
             "launch_ms": {k: round(v, 4) for k, v in per.items()},
         }

@@ -285,8 +285,10 @@ class SuperResolution:
             return self.checkpoint_dir + "/" + name + "_" + str(trial) + ".ckpt"
         return self.checkpoint_dir + "/" + name + ".ckpt"
 
-    def load_model(self, name="", trial=0, output_log=False):
-        """tf_graph.py:263-280: restore from the TF V2 bundle `<checkpoint_dir>/<name>.ckpt`."""
+    def load_model(self, name="", trial=0, output_log=False, restore_optimizer=False):
+        """tf_graph.py:263-280: restore from the TF V2 bundle `<checkpoint_dir>/<name>.ckpt`.  With
+        `restore_optimizer` (train.py resuming a run) the Adam slots `<var>/Adam`, `<var>/Adam_1` and the update count
+        behind `beta1_power` are restored too, as tf.train.Saver.restore does for the graph train.py builds."""
         filename = self._ckpt_filename(name, trial)
         if not os.path.isfile(filename + ".index"):
             print("Error. [%s] is not exist!" % filename)
@@ -299,15 +301,35 @@ class SuperResolution:
                                       % (filename, var))
             weights[var] = reader.get_tensor(var)
         self.engine.set_params(weights)
+        if restore_optimizer and not self.depthwise_separable and reader.has_tensor("beta1_power"):
+            for var in weights:
+                for slot, suffix in enumerate(("/Adam", "/Adam_1")):
+                    if reader.has_tensor(var + suffix):
+                        self.engine.set_adam_slot(var, slot, reader.get_tensor(var + suffix))
+            b1p = float(np.asarray(reader.get_tensor("beta1_power")).reshape(-1)[0])
+            if 0.0 < b1p < 1.0 and 0.0 < self.beta1 < 1.0:
+                self.engine.adam_step = max(0, int(round(math.log(b1p) / math.log(self.beta1))) - 1)
+            elif b1p <= 0.0:
+                self.engine.adam_step = 10 ** 6       # the power underflowed in a long run: bias correction is 1
         if output_log:
             logging.info("Model restored [ %s ]." % filename)
         else:
             print("Model restored [ %s ]." % filename)
 
     def save_model(self, name="", trial=0, output_log=False):
-        """tf_graph.py:282-296: write `<name>.ckpt.index` + `.data-00000-of-00001` (TF V2 bundle)."""
+        """tf_graph.py:282-296: write `<name>.ckpt.index` + `.data-00000-of-00001` (TF V2 bundle) with everything the
+        reference's tf.train.Saver() writes: the trainables, their Adam slots and beta1_power / beta2_power - so the
+        file restores in the reference's sr.py / train.py graphs (which build the optimizer) as well as here."""
         filename = self._ckpt_filename(name, trial)
-        tensors = {var: self.engine.get_param(var) for var in self.engine.param_shapes()}
+        shapes = self.engine.param_shapes()
+        tensors = {var: self.engine.get_param(var) for var in shapes}
+        steps = 0 if self.depthwise_separable else self.engine.adam_step
+        for var, shape in shapes.items():
+            for slot, suffix in enumerate(("/Adam", "/Adam_1")):
+                tensors[var + suffix] = (self.engine.get_adam_slot(var, slot) if steps > 0
+                                         else np.zeros(shape, dtype=np.float32))
+        tensors["beta1_power"] = np.asarray(self.beta1 ** (steps + 1), dtype=np.float32)
+        tensors["beta2_power"] = np.asarray(self.beta2 ** (steps + 1), dtype=np.float32)
         tf_bundle.write_bundle(filename, tensors)
         if output_log:
             logging.info("Model saved [%s]." % filename)

@@ -1591,6 +1591,33 @@ int dcscn_get_adam_slot(dcscn_handle* h, const char* name, int slot, float* host
   return 0;
 }
 
+int dcscn_set_adam_slot(dcscn_handle* h, const char* name, int slot, const float* host_data, int64_t numel) {
+  if (!h || !name || !host_data) return fail("dcscn_set_adam_slot: null argument");
+  CUDA_TRY(cudaSetDevice(h->cfg.device_id));
+  if (train_init(h)) return 1;
+  auto it = h->param_index.find(name);
+  if (it == h->param_index.end()) return fail("dcscn_set_adam_slot: unknown variable '%s'", name);
+  const ParamDef& p = h->params[it->second];
+  if (numel != p.numel() || (slot != 0 && slot != 1)) return fail("dcscn_set_adam_slot: bad size or slot");
+  float* dst = (slot == 0 ? h->train->d_m : h->train->d_v) + h->train->off[it->second];
+  CUDA_TRY(cudaMemcpy(dst, host_data, (size_t)numel * sizeof(float), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int dcscn_get_adam_step(dcscn_handle* h, int64_t* step) {
+  if (!h || !step) return fail("dcscn_get_adam_step: null argument");
+  *step = h->train ? h->train->step : 0;
+  return 0;
+}
+
+int dcscn_set_adam_step(dcscn_handle* h, int64_t step) {
+  if (!h || step < 0) return fail("dcscn_set_adam_step: bad argument");
+  CUDA_TRY(cudaSetDevice(h->cfg.device_id));
+  if (train_init(h)) return 1;
+  h->train->step = step;
+  return 0;
+}
+
 int dcscn_grad_buffer(dcscn_handle* h, float** dev_ptr, int64_t* count) {
   if (!h || !dev_ptr || !count) return fail("dcscn_grad_buffer: null argument");
   if (!h->train || h->train->total == 0) return fail("dcscn_grad_buffer: no train step has run yet");

@@ -52,7 +52,8 @@ EXPORTED_SYMBOLS = [
     "dcscn_create", "dcscn_destroy", "dcscn_last_error", "dcscn_num_params", "dcscn_param_info",
     "dcscn_set_param", "dcscn_get_param", "dcscn_forward", "dcscn_forward_host", "dcscn_get_activation",
     "dcscn_set_option", "dcscn_get_timings", "dcscn_launch_count", "dcscn_device_bytes",
-    "dcscn_train_step", "dcscn_train_step_host", "dcscn_get_grad", "dcscn_get_adam_slot", "dcscn_last_grad_norm",
+    "dcscn_train_step", "dcscn_train_step_host", "dcscn_get_grad", "dcscn_get_adam_slot", "dcscn_set_adam_slot", "dcscn_get_adam_step",
+    "dcscn_set_adam_step", "dcscn_last_grad_norm",
     "dcscn_dropout_mask", "dcscn_grad_buffer", "dcscn_apply_gradients",
 ]
 
@@ -92,6 +93,9 @@ def load_library(path=None):
     lib.dcscn_train_step_host.argtypes = [vp, vp, vp, vp, ci, ci, ci, cf, u32, ci, fp, fp]
     lib.dcscn_get_grad.argtypes = [vp, ctypes.c_char_p, fp, c64]
     lib.dcscn_get_adam_slot.argtypes = [vp, ctypes.c_char_p, ci, fp, c64]
+    lib.dcscn_set_adam_slot.argtypes = [vp, ctypes.c_char_p, ci, fp, c64]
+    lib.dcscn_get_adam_step.argtypes = [vp, ctypes.POINTER(c64)]
+    lib.dcscn_set_adam_step.argtypes = [vp, c64]
     lib.dcscn_last_grad_norm.argtypes = [vp]
     lib.dcscn_last_grad_norm.restype = cf
     lib.dcscn_dropout_mask.argtypes = [vp, ctypes.c_char_p, u32, ci, ci, ci, ctypes.POINTER(ctypes.c_uint8), c64]
@@ -277,6 +281,22 @@ class Engine:
         self._check(self.lib.dcscn_get_adam_slot(self.handle, name.encode(), slot,
                                                  a.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), a.size))
         return a
+
+    def set_adam_slot(self, name, slot, value):
+        a = np.ascontiguousarray(value, dtype=np.float32)
+        self._check(self.lib.dcscn_set_adam_slot(self.handle, name.encode(), slot,
+                                                 a.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), a.size))
+
+    @property
+    def adam_step(self):
+        """Number of optimizer updates applied so far (TF stores beta^(t+1) as beta1_power / beta2_power)."""
+        t = ctypes.c_int64()
+        self._check(self.lib.dcscn_get_adam_step(self.handle, ctypes.byref(t)))
+        return int(t.value)
+
+    @adam_step.setter
+    def adam_step(self, t):
+        self._check(self.lib.dcscn_set_adam_step(self.handle, int(t)))
 
     @property
     def last_grad_norm(self):

@@ -306,11 +306,12 @@ def write_bundle(prefix, tensors, block_size=4096):
     offset = 0
     with open(prefix + ".data-00000-of-00001", "wb") as f:
         for name in names:
-            arr = np.ascontiguousarray(np.asarray(tensors[name], dtype="<f4"))
-            raw = arr.tobytes()
+            src = np.asarray(tensors[name], dtype="<f4")
+            shape = src.shape                      # () for scalars such as beta1_power (ascontiguousarray would make it (1,))
+            raw = np.ascontiguousarray(src).tobytes()
             f.write(raw)
             entries.append((name.encode("utf-8"),
-                            _encode_entry(arr.shape, offset, len(raw), masked_crc32c(raw))))
+                            _encode_entry(shape, offset, len(raw), masked_crc32c(raw))))
             offset += len(raw)
 
     # BundleHeaderProto: num_shards=1, endianness=LITTLE(0, omitted), version{producer=1}

@@ -31,7 +31,7 @@ def train(model, flags, trial):
 
     model.init_all_variables()
     if flags.load_model_name != "":
-        model.load_model(flags.load_model_name, output_log=True)
+        model.load_model(flags.load_model_name, output_log=True, restore_optimizer=True)
     model.init_train_step()
     model.init_epoch_index()
     model_updated = True

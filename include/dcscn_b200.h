@@ -98,6 +98,12 @@ int dcscn_train_step_host(dcscn_handle* h, const float* x, const float* x2, cons
 int dcscn_get_grad(dcscn_handle* h, const char* name, float* host_data, int64_t numel);
 /* Adam slots of a variable ("<var>/Adam" = slot 0, "<var>/Adam_1" = slot 1 in the reference's checkpoints). */
 int dcscn_get_adam_slot(dcscn_handle* h, const char* name, int slot, float* host_data, int64_t numel);
+/* Restoring optimizer state from a checkpoint (what tf.train.Saver.restore does for the graph sr.py / train.py build,
+ * helper/tf_graph.py:263-280): the slots, and the number of applied updates t (the reference stores it as
+ * beta1_power = beta1^(t+1), beta2_power = beta2^(t+1)). */
+int dcscn_set_adam_slot(dcscn_handle* h, const char* name, int slot, const float* host_data, int64_t numel);
+int dcscn_get_adam_step(dcscn_handle* h, int64_t* step);
+int dcscn_set_adam_step(dcscn_handle* h, int64_t step);
 /* Data-parallel training: after dcscn_train_step(..., apply_update = 0) on every rank, all-reduce (average) the flat
  * gradient buffer returned here (device pointer, `count` floats, every trainable in dcscn_param_info order) - e.g.
  * ncclAllReduce over NVLink - then call dcscn_apply_gradients on every rank: global-norm clip of the averaged gradient

@@ -93,3 +93,34 @@ def test_save_and_reload_checkpoint(tmp_path):
     m.load_model()
     p1, _ = m.do_for_evaluate(f)
     assert p1 == p0
+
+
+def test_checkpoint_carries_optimizer_state(tmp_path):
+    """save_model writes what the reference's tf.train.Saver() writes (trainables, `<var>/Adam`, `<var>/Adam_1`,
+    beta1_power, beta2_power); load_model(restore_optimizer=True) brings the Adam state back, so a resumed run takes
+    exactly the step the uninterrupted run would have taken."""
+    from helper import tf_bundle
+    m = build_model(tmp_path, CD, 1)
+    g = np.random.RandomState(0)
+    x = (g.rand(4, 16, 16, 1) * 255).astype(np.float32)
+    x2 = (g.rand(4, 32, 32, 1) * 255).astype(np.float32)
+    y = (g.rand(4, 32, 32, 1) * 255).astype(np.float32)
+    for i in range(3):
+        m.engine.train_step_host(x, x2, y, lr=1e-3, seed=i)
+    m.checkpoint_dir = str(tmp_path / "ckpt")
+    m.save_model()
+    r = tf_bundle.BundleReader(os.path.join(m.checkpoint_dir, m.name + ".ckpt"))
+    names = set(r.keys())
+    shapes = m.engine.param_shapes()
+    assert names == set(shapes) | {v + s for v in shapes for s in ("/Adam", "/Adam_1")} | {"beta1_power", "beta2_power"}
+    assert float(r.get_tensor("beta1_power")) == pytest.approx(m.beta1 ** 4, rel=1e-6)
+    m.engine.train_step_host(x, x2, y, lr=1e-3, seed=7)          # the uninterrupted run's 4th step
+    want = {v: m.engine.get_param(v) for v in shapes}
+
+    m2 = build_model(tmp_path, CD, 1)
+    m2.checkpoint_dir = m.checkpoint_dir
+    m2.load_model(restore_optimizer=True)
+    assert m2.engine.adam_step == 3
+    m2.engine.train_step_host(x, x2, y, lr=1e-3, seed=7)
+    for v in shapes:
+        assert np.abs(m2.engine.get_param(v) - want[v]).max() <= 1e-5, v   # one Adam step moves a weight by <= lr = 1e-3; fp32 atomics reorder a few small sums

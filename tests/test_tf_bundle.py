@@ -76,3 +76,14 @@ def test_errors(tmp_path):
     open(p, "wb").write(bytes(raw))
     with pytest.raises(ValueError):
         tf_bundle.BundleReader(prefix).get_tensor("w", verify_crc=True)
+
+
+def test_scalar_tensors_round_trip_with_empty_shape(tmp_path):
+    """beta1_power / beta2_power are rank-0 in the reference's checkpoints (shape proto without dims)."""
+    from helper import tf_bundle
+    prefix = str(tmp_path / "m.ckpt")
+    tf_bundle.write_bundle(prefix, {"beta1_power": np.asarray(0.9 ** 5, dtype=np.float32), "w": np.ones((2, 3), np.float32)})
+    r = tf_bundle.BundleReader(prefix)
+    assert r.shape("beta1_power") == [] and r.get_tensor("beta1_power").shape == ()
+    assert float(r.get_tensor("beta1_power")) == pytest.approx(0.9 ** 5, rel=1e-6)
+    assert r.shape("w") == [2, 3]

@@ -31,13 +31,16 @@ struct WgradTcParams {
   int m_tiles;            // 128-channel tiles of the input
   int n_tiles, n_pad;     // column tiles of dZ, n_pad channels each (multiple of 16, <= 256)
   int n_groups;           // 64-channel boxes per dZ tile = ceil(n_pad / 64)
-  int ksplit;             // CTAs sharing one (tap, m_tile, n_tile): contiguous ranges of the chunk index
+  int tap_group;          // filter taps per CTA: they share the dZ tile of a chunk, one TMEM accumulator each
+  int ksplit;             // CTAs sharing one (tap group, m_tile, n_tile): contiguous ranges of the chunk index
   int chunks;             // n_img * tiles_y * tiles_x
   float* partial;         // [ksplit][taps][m_tiles * 128][n_tiles * n_pad]
   uint32_t tmem_cols;     // power of two >= max(32, n_pad)
 };
 
-__host__ __device__ inline size_t wgrad_tc_stage_bytes(int n_groups) { return (size_t)(4 + 2 * n_groups) * kWgBoxBytes; }
+__host__ __device__ inline size_t wgrad_tc_stage_bytes(int n_groups, int tap_group) {
+  return (size_t)(4 * tap_group + 2 * n_groups) * kWgBoxBytes;
+}
 
 // MN-major, 128-byte swizzle: LBO (bits [16,30)) = bytes between 64-channel groups, SBO (bits [32,46)) = bytes
 // between 8-pixel groups, descriptor version 1 (bit 46), layout type SWIZZLE_128B = 2 (bits [61,64)).
@@ -53,8 +56,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                 const WgradTcParams p, const int num_stages) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const uint32_t STAGE_BYTES = (uint32_t)wgrad_tc_stage_bytes(p.n_groups);
-  const uint32_t Z_OFF = 4u * kWgBoxBytes, ZP_BYTES = (uint32_t)p.n_groups * kWgBoxBytes;
+  const uint32_t STAGE_BYTES = (uint32_t)wgrad_tc_stage_bytes(p.n_groups, p.tap_group);
+  const uint32_t Z_OFF = 4u * (uint32_t)p.tap_group * kWgBoxBytes, ZP_BYTES = (uint32_t)p.n_groups * kWgBoxBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)num_stages * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + num_stages;
   uint64_t* done_bar = empty_bar + num_stages;
@@ -66,10 +69,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
   const int ks = b % p.ksplit; b /= p.ksplit;
   const int nt = b % p.n_tiles; b /= p.n_tiles;
   const int mt = b % p.m_tiles;
-  const int tap = b / p.m_tiles;
+  const int tap0 = (b / p.m_tiles) * p.tap_group;                    // this CTA's taps: [tap0, tap0 + ntap)
+  const int ntap = (taps - tap0) < p.tap_group ? (taps - tap0) : p.tap_group;
   const int c_begin = (int)((long long)ks * p.chunks / p.ksplit);
   const int c_end = (int)((long long)(ks + 1) * p.chunks / p.ksplit);
-  const int dy = tap / p.ksz - half, dx = tap % p.ksz - half;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < num_stages; ++i) {
@@ -102,10 +105,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         const int y0 = (r / p.tiles_x) * kWgTH, x0 = (r % p.tiles_x) * kWgTW;
         ptx::mbar_wait(&empty_bar[st], ph ^ 1);
         uint8_t* s = smem + (size_t)st * STAGE_BYTES;
-        ptx::mbar_arrive_expect_tx(&full_bar[st], STAGE_BYTES);
-        for (int g = 0; g < 2; ++g) {
-          ptx::tma_load_4d(s + g * kWgBoxBytes, &tm_a_hi, &full_bar[st], mt * 128 + g * 64, x0 + dx, y0 + dy, img);
-          ptx::tma_load_4d(s + (2 + g) * kWgBoxBytes, &tm_a_lo, &full_bar[st], mt * 128 + g * 64, x0 + dx, y0 + dy, img);
+        ptx::mbar_arrive_expect_tx(&full_bar[st], (uint32_t)(4 * ntap + 2 * p.n_groups) * kWgBoxBytes);
+        for (int j = 0; j < ntap; ++j) {
+          const int tap = tap0 + j;
+          const int dy = tap / p.ksz - half, dx = tap % p.ksz - half;
+          uint8_t* sa = s + (size_t)j * 4 * kWgBoxBytes;
+          for (int g = 0; g < 2; ++g) {
+            ptx::tma_load_4d(sa + g * kWgBoxBytes, &tm_a_hi, &full_bar[st], mt * 128 + g * 64, x0 + dx, y0 + dy, img);
+            ptx::tma_load_4d(sa + (2 + g) * kWgBoxBytes, &tm_a_lo, &full_bar[st], mt * 128 + g * 64, x0 + dx, y0 + dy, img);
+          }
         }
         for (int g = 0; g < p.n_groups; ++g) {
           ptx::tma_load_4d(s + Z_OFF + g * kWgBoxBytes, &tm_z_hi, &full_bar[st], nt * p.n_pad + g * 64, x0, y0, img);
@@ -120,27 +128,26 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     const uint32_t smem_base_u32 = ptx::smem_u32(smem);
     int st = 0;
     uint32_t ph = 0;
-    uint32_t accumulate = 0;
     for (int c = c_begin; c < c_end; ++c) {
       ptx::mbar_wait(&full_bar[st], ph);
       ptx::tc_fence_after();
       const uint32_t st_addr = smem_base_u32 + (uint32_t)st * STAGE_BYTES;
-      const uint32_t a_hi = st_addr, a_lo = st_addr + 2u * kWgBoxBytes;
       const uint32_t z_hi = st_addr + Z_OFF, z_lo = z_hi + ZP_BYTES;
+      const uint32_t keep = (c == c_begin) ? 0u : 1u;      // every tap's accumulator starts from zero in the first chunk
       if (ptx::elect_one()) {
-#pragma unroll
-        for (uint32_t k = 0; k < 2; ++k) {   // 16 pixels (rows of 128 bytes) per UMMA; small products first
-          const uint32_t ko = k * 2048u;
-          ptx::mma_f16_ss(tmem_base, make_desc_mn(a_lo + ko), make_desc_mn(z_hi + ko), idesc, accumulate);
-          ptx::mma_f16_ss(tmem_base, make_desc_mn(a_hi + ko), make_desc_mn(z_lo + ko), idesc, 1);
-          accumulate = 1;
+        for (int j = 0; j < ntap; ++j) {
+          const uint32_t a_hi = st_addr + (uint32_t)j * 4u * kWgBoxBytes, a_lo = a_hi + 2u * kWgBoxBytes;
+          const uint32_t d = tmem_base + (uint32_t)(j * p.n_pad);
+          // 16 pixels (rows of 128 bytes) per UMMA; the two small products first, the dominant one last
+          ptx::mma_f16_ss(d, make_desc_mn(a_lo), make_desc_mn(z_hi), idesc, keep);
+          ptx::mma_f16_ss(d, make_desc_mn(a_hi), make_desc_mn(z_lo), idesc, 1);
+          ptx::mma_f16_ss(d, make_desc_mn(a_lo + 2048u), make_desc_mn(z_hi + 2048u), idesc, 1);
+          ptx::mma_f16_ss(d, make_desc_mn(a_hi + 2048u), make_desc_mn(z_lo + 2048u), idesc, 1);
+          ptx::mma_f16_ss(d, make_desc_mn(a_hi), make_desc_mn(z_hi), idesc, 1);
+          ptx::mma_f16_ss(d, make_desc_mn(a_hi + 2048u), make_desc_mn(z_hi + 2048u), idesc, 1);
         }
-#pragma unroll
-        for (uint32_t k = 0; k < 2; ++k)
-          ptx::mma_f16_ss(tmem_base, make_desc_mn(a_hi + k * 2048u), make_desc_mn(z_hi + k * 2048u), idesc, 1);
         ptx::mma_commit(&empty_bar[st]);
       }
-      accumulate = 1;
       __syncwarp();
       if (++st == num_stages) { st = 0; ph ^= 1; }
     }
@@ -150,20 +157,22 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
     const int quad = warp & 3;                       // TMEM lanes [32 * quad, +32) are this warp's
     const int m = quad * 32 + lane;
     const size_t m_total = (size_t)p.m_tiles * 128, n_total = (size_t)p.n_tiles * p.n_pad;
-    float* out = p.partial + (((size_t)ks * taps + tap) * m_total + (size_t)mt * 128 + m) * n_total + (size_t)nt * p.n_pad;
     ptx::mbar_wait(done_bar, 0);
     ptx::tc_fence_after();
-    for (int col = 0; col < p.n_pad; col += 16) {
-      float v[16];
-      if (c_end > c_begin) {
-        ptx::tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)col, v);
-      } else {
+    for (int j = 0; j < ntap; ++j) {
+      float* out = p.partial + (((size_t)ks * taps + tap0 + j) * m_total + (size_t)mt * 128 + m) * n_total + (size_t)nt * p.n_pad;
+      for (int col = 0; col < p.n_pad; col += 16) {
+        float v[16];
+        if (c_end > c_begin) {
+          ptx::tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(j * p.n_pad + col), v);
+        } else {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = 0.f;
+          for (int i = 0; i < 16; ++i) v[i] = 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; i += 4)
+          *reinterpret_cast<float4*>(out + col + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
       }
-#pragma unroll
-      for (int i = 0; i < 16; i += 4)
-        *reinterpret_cast<float4*>(out + col + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
     }
     ptx::tc_fence_before();
   }

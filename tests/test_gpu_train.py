@@ -140,3 +140,32 @@ def test_tensor_core_wgrad_matches_cuda_core_wgrad_full_model():
             continue
         ref, got = grads[0][k], grads[1][k]
         assert np.abs(got - ref).max() <= 1e-4 * np.abs(ref).max() + 1e-12, (k, float(np.abs(got - ref).max()), float(np.abs(ref).max()))
+
+
+def test_full_size_batch_gradient_is_mean_of_half_batch_gradients():
+    """BASELINE configs[3] size (L12 x4, 64 patches of 48x48 -> 192x192), where the CPU oracle would take minutes:
+    with dropout off the loss is a mean over patches, so every gradient of the full batch must equal the mean of the
+    gradients of its two halves (L2 term included in both)."""
+    from helper import engine as E
+    import conftest
+    wts = conftest.load_golden_weights("dcscn_L12_F196to48_Sc4_NIN_A64_PS_R1F32")
+    g = np.random.RandomState(5)
+    n = 64
+    x = (g.rand(n, 48, 48, 1) * 255).astype(np.float32)
+    x2 = (g.rand(n, 192, 192, 1) * 255).astype(np.float32)
+    y = np.clip(x2 + g.randn(n, 192, 192, 1) * 10, 0, 255).astype(np.float32)
+    eng = E.Engine(E.make_config(scale=4, dropout_keep=1.0))
+    eng.set_params(wts)
+
+    def grads(sl):
+        loss, mse = eng.train_step_host(x[sl], x2[sl], y[sl], lr=0.002, seed=1, apply_update=False)
+        return mse, {k: eng.get_grad(k) for k in wts}
+
+    m_all, g_all = grads(slice(0, n))
+    m_a, g_a = grads(slice(0, n // 2))
+    m_b, g_b = grads(slice(n // 2, n))
+    assert m_all == pytest.approx(0.5 * (m_a + m_b), rel=1e-5)
+    for k in wts:
+        want = 0.5 * (g_a[k] + g_b[k])
+        assert np.abs(g_all[k] - want).max() <= 2e-4 * np.abs(want).max() + 1e-9, (k, float(np.abs(g_all[k] - want).max()), float(np.abs(want).max()))
+    eng.close()

@@ -23,6 +23,8 @@ namespace dcscn {
 
 constexpr int kWgTW = 16, kWgTH = 2;                 // pixel patch of one K chunk (32 pixels)
 constexpr int kWgBoxBytes = kWgTW * kWgTH * 128;     // one TMA box: 32 rows of 64 fp16
+constexpr int kWgHaloRows = (kWgTW + 2) * kWgTH;   // halo box: 18 x 2 pixels serve the three dx taps of one filter row
+constexpr int kWgHaloStride = 5 * 1024;            // bytes between halo boxes (36 rows of 128 B, padded to the swizzle period)
 constexpr int kWgTcThreads = 192;                    // warp 0: TMA, warp 1: UMMA issue, warps 2-5: drain (one TMEM lane quadrant each)
 
 struct WgradTcParams {
@@ -31,6 +33,7 @@ struct WgradTcParams {
   int m_tiles;            // 128-channel tiles of the input
   int n_tiles, n_pad;     // column tiles of dZ, n_pad channels each (multiple of 16, <= 256)
   int n_groups;           // 64-channel boxes per dZ tile = ceil(n_pad / 64)
+  int halo;               // 1: tap_group == ksz == 3 and the three dx taps of a filter row read ONE 18-pixel-wide A box
   int tap_group;          // filter taps per CTA: they share the dZ tile of a chunk, one TMEM accumulator each
   int ksplit;             // CTAs sharing one (tap group, m_tile, n_tile): contiguous ranges of the chunk index
   int chunks;             // n_img * tiles_y * tiles_x
@@ -38,14 +41,14 @@ struct WgradTcParams {
   uint32_t tmem_cols;     // power of two >= max(32, n_pad)
 };
 
-__host__ __device__ inline size_t wgrad_tc_stage_bytes(int n_groups, int tap_group) {
-  return (size_t)(4 * tap_group + 2 * n_groups) * kWgBoxBytes;
+__host__ __device__ inline size_t wgrad_tc_stage_bytes(int n_groups, int tap_group, int halo) {
+  return (halo ? (size_t)4 * kWgHaloStride : (size_t)4 * tap_group * kWgBoxBytes) + (size_t)2 * n_groups * kWgBoxBytes;
 }
 
 // MN-major, 128-byte swizzle: LBO (bits [16,30)) = bytes between 64-channel groups, SBO (bits [32,46)) = bytes
 // between 8-pixel groups, descriptor version 1 (bit 46), layout type SWIZZLE_128B = 2 (bits [61,64)).
-__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
-  const uint32_t lo = ((saddr & 0x3FFFFu) >> 4) | ((uint32_t)(kWgBoxBytes >> 4) << 16);
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo = kWgBoxBytes) {
+  const uint32_t lo = ((saddr & 0x3FFFFu) >> 4) | ((lbo >> 4) << 16);
   constexpr uint32_t hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
   return ((uint64_t)hi << 32) | (uint64_t)lo;
 }
@@ -56,8 +59,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
                 const WgradTcParams p, const int num_stages) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const uint32_t STAGE_BYTES = (uint32_t)wgrad_tc_stage_bytes(p.n_groups, p.tap_group);
-  const uint32_t Z_OFF = 4u * (uint32_t)p.tap_group * kWgBoxBytes, ZP_BYTES = (uint32_t)p.n_groups * kWgBoxBytes;
+  const uint32_t STAGE_BYTES = (uint32_t)wgrad_tc_stage_bytes(p.n_groups, p.tap_group, p.halo);
+  const uint32_t Z_OFF = p.halo ? 4u * kWgHaloStride : 4u * (uint32_t)p.tap_group * kWgBoxBytes;
+  const uint32_t ZP_BYTES = (uint32_t)p.n_groups * kWgBoxBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)num_stages * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + num_stages;
   uint64_t* done_bar = empty_bar + num_stages;
@@ -105,14 +109,23 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
         const int y0 = (r / p.tiles_x) * kWgTH, x0 = (r % p.tiles_x) * kWgTW;
         ptx::mbar_wait(&empty_bar[st], ph ^ 1);
         uint8_t* s = smem + (size_t)st * STAGE_BYTES;
-        ptx::mbar_arrive_expect_tx(&full_bar[st], (uint32_t)(4 * ntap + 2 * p.n_groups) * kWgBoxBytes);
-        for (int j = 0; j < ntap; ++j) {
-          const int tap = tap0 + j;
-          const int dy = tap / p.ksz - half, dx = tap % p.ksz - half;
-          uint8_t* sa = s + (size_t)j * 4 * kWgBoxBytes;
+        if (p.halo) {   // one 18 x 2 box per plane and channel group; origin = left neighbour column of the filter row
+          const int dy = tap0 / p.ksz - half;
+          ptx::mbar_arrive_expect_tx(&full_bar[st], (uint32_t)(4 * kWgHaloRows * 128 + 2 * p.n_groups * kWgBoxBytes));
           for (int g = 0; g < 2; ++g) {
-            ptx::tma_load_4d(sa + g * kWgBoxBytes, &tm_a_hi, &full_bar[st], mt * 128 + g * 64, x0 + dx, y0 + dy, img);
-            ptx::tma_load_4d(sa + (2 + g) * kWgBoxBytes, &tm_a_lo, &full_bar[st], mt * 128 + g * 64, x0 + dx, y0 + dy, img);
+            ptx::tma_load_4d(s + g * kWgHaloStride, &tm_a_hi, &full_bar[st], mt * 128 + g * 64, x0 - half, y0 + dy, img);
+            ptx::tma_load_4d(s + (2 + g) * kWgHaloStride, &tm_a_lo, &full_bar[st], mt * 128 + g * 64, x0 - half, y0 + dy, img);
+          }
+        } else {
+          ptx::mbar_arrive_expect_tx(&full_bar[st], (uint32_t)(4 * ntap + 2 * p.n_groups) * kWgBoxBytes);
+          for (int j = 0; j < ntap; ++j) {
+            const int tap = tap0 + j;
+            const int dy = tap / p.ksz - half, dx = tap % p.ksz - half;
+            uint8_t* sa = s + (size_t)j * 4 * kWgBoxBytes;
+            for (int g = 0; g < 2; ++g) {
+              ptx::tma_load_4d(sa + g * kWgBoxBytes, &tm_a_hi, &full_bar[st], mt * 128 + g * 64, x0 + dx, y0 + dy, img);
+              ptx::tma_load_4d(sa + (2 + g) * kWgBoxBytes, &tm_a_lo, &full_bar[st], mt * 128 + g * 64, x0 + dx, y0 + dy, img);
+            }
           }
         }
         for (int g = 0; g < p.n_groups; ++g) {
@@ -136,15 +149,28 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
       const uint32_t keep = (c == c_begin) ? 0u : 1u;      // every tap's accumulator starts from zero in the first chunk
       if (ptx::elect_one()) {
         for (int j = 0; j < ntap; ++j) {
-          const uint32_t a_hi = st_addr + (uint32_t)j * 4u * kWgBoxBytes, a_lo = a_hi + 2u * kWgBoxBytes;
           const uint32_t d = tmem_base + (uint32_t)(j * p.n_pad);
           // 16 pixels (rows of 128 bytes) per UMMA; the two small products first, the dominant one last
-          ptx::mma_f16_ss(d, make_desc_mn(a_lo), make_desc_mn(z_hi), idesc, keep);
-          ptx::mma_f16_ss(d, make_desc_mn(a_hi), make_desc_mn(z_lo), idesc, 1);
-          ptx::mma_f16_ss(d, make_desc_mn(a_lo + 2048u), make_desc_mn(z_hi + 2048u), idesc, 1);
-          ptx::mma_f16_ss(d, make_desc_mn(a_hi + 2048u), make_desc_mn(z_lo + 2048u), idesc, 1);
-          ptx::mma_f16_ss(d, make_desc_mn(a_hi), make_desc_mn(z_hi), idesc, 1);
-          ptx::mma_f16_ss(d, make_desc_mn(a_hi + 2048u), make_desc_mn(z_hi + 2048u), idesc, 1);
+          if (p.halo) {
+            // tap dx = j - 1 starts j rows into each 18-row line of the halo box; the swizzle XOR follows absolute
+            // shared-memory address bits, so a start on any 128-byte row is legal
+            const uint32_t a_hi = st_addr + (uint32_t)j * 128u, a_lo = a_hi + 2u * kWgHaloStride;
+            const uint32_t l1 = (uint32_t)(kWgTW + 2) * 128u;      // second image row of the patch
+            ptx::mma_f16_ss(d, make_desc_mn(a_lo, kWgHaloStride), make_desc_mn(z_hi), idesc, keep);
+            ptx::mma_f16_ss(d, make_desc_mn(a_hi, kWgHaloStride), make_desc_mn(z_lo), idesc, 1);
+            ptx::mma_f16_ss(d, make_desc_mn(a_lo + l1, kWgHaloStride), make_desc_mn(z_hi + 2048u), idesc, 1);
+            ptx::mma_f16_ss(d, make_desc_mn(a_hi + l1, kWgHaloStride), make_desc_mn(z_lo + 2048u), idesc, 1);
+            ptx::mma_f16_ss(d, make_desc_mn(a_hi, kWgHaloStride), make_desc_mn(z_hi), idesc, 1);
+            ptx::mma_f16_ss(d, make_desc_mn(a_hi + l1, kWgHaloStride), make_desc_mn(z_hi + 2048u), idesc, 1);
+          } else {
+            const uint32_t a_hi = st_addr + (uint32_t)j * 4u * kWgBoxBytes, a_lo = a_hi + 2u * kWgBoxBytes;
+            ptx::mma_f16_ss(d, make_desc_mn(a_lo), make_desc_mn(z_hi), idesc, keep);
+            ptx::mma_f16_ss(d, make_desc_mn(a_hi), make_desc_mn(z_lo), idesc, 1);
+            ptx::mma_f16_ss(d, make_desc_mn(a_lo + 2048u), make_desc_mn(z_hi + 2048u), idesc, 1);
+            ptx::mma_f16_ss(d, make_desc_mn(a_hi + 2048u), make_desc_mn(z_lo + 2048u), idesc, 1);
+            ptx::mma_f16_ss(d, make_desc_mn(a_hi), make_desc_mn(z_hi), idesc, 1);
+            ptx::mma_f16_ss(d, make_desc_mn(a_hi + 2048u), make_desc_mn(z_hi + 2048u), idesc, 1);
+          }
         }
         ptx::mma_commit(&empty_bar[st]);
       }

@@ -228,43 +228,66 @@ __global__ void __launch_bounds__(256) conv_last_kernel(const ConvLastParams p) 
 }
 
 // Same layer straight from global memory (used by the train step, where the HR feature map is materialised anyway).
-// Thread = (pixel, channel quad): a warp's 16-byte loads cover whole 128-byte lines of consecutive pixels; the quads
-// of a pixel (a power-of-two lane group, the lanes beyond C / 4 idle) are summed with shuffles.  Needs C % 4 == 0,
-// pitch % 4 == 0 and C <= 128.
+// Lane = channel quad (filter taps of its 4 channels in registers), a warp walks a run of consecutive pixels of an image
+// row with a sliding 3x3 window of float4 (three 16-byte loads per pixel, no index divisions in the loop) and reduces
+// the lanes' partial dot products with shuffles.  Needs ksz == 3, C % 4 == 0, pitch % 4 == 0 and C <= 128.
+constexpr int kLastRun = 32;
 __global__ void __launch_bounds__(256) conv_last_direct_kernel(const ConvLastParams p) {
-  extern __shared__ float4 s_w4[];                 // [taps][C / 4]
-  const int taps = p.ksz * p.ksz, half = p.ksz >> 1, quads = p.C >> 2;
-  for (int i = threadIdx.x; i < taps * quads; i += blockDim.x) s_w4[i] = __ldg(reinterpret_cast<const float4*>(p.w) + i);
-  __syncthreads();
-  int lpp = 1;                                      // lanes per pixel
-  while (lpp < quads) lpp <<= 1;
-  const int cq = threadIdx.x % lpp;
-  const int ppb = blockDim.x / lpp;                 // pixels per CTA pass
+  const int lane = threadIdx.x & 31, quads = p.C >> 2;
+  const bool active = lane < quads;
+  float4 w[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) w[t] = active ? __ldg(reinterpret_cast<const float4*>(p.w + t * p.C) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
   const long long total = (long long)p.n_img * p.H * p.W;
-  const long long rounds = (total + ppb - 1) / ppb;
-  for (long long rd = blockIdx.x; rd < rounds; rd += gridDim.x) {
-    const long long q = rd * ppb + threadIdx.x / lpp;
-    float acc = 0.f;
-    if (q < total && cq < quads) {
-      const unsigned q32 = (unsigned)q, row32 = q32 / (unsigned)p.W;   // < 2^32 pixels (launcher)
-      const int x = (int)(q32 - row32 * (unsigned)p.W), y = (int)(row32 % (unsigned)p.H);
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int W = p.W, H = p.H;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long q0 = warp0 * kLastRun; q0 < total; q0 += nwarps * kLastRun) {
+    const long long q1 = q0 + kLastRun < total ? q0 + kLastRun : total;
+    int x = (int)(q0 % W), y = (int)((q0 / W) % H);
+    float4 c0v[3], c1v[3], c2v[3];                 // window columns x-1, x, x+1 (rows y-1, y, y+1) of this lane's 4 channels
+    auto load_col = [&](long long q, int xx, float4 (&col)[3]) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int yy = y + r - 1;
+        col[r] = (active && yy >= 0 && yy < H && xx >= 0 && xx < W)
+                     ? __ldg(reinterpret_cast<const float4*>(p.src + (q + (long long)(r - 1) * W + (xx - x)) * p.pitch) + lane) : zero4;
+      }
+    };
+    load_col(q0, x - 1, c0v);
+    load_col(q0, x, c1v);
+    for (long long q = q0; q < q1; ++q) {
+      load_col(q, x + 1, c2v);
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 9
-      for (int t = 0; t < taps; ++t) {
-        const int dy = t / p.ksz - half, dx = t % p.ksz - half;
-        if ((unsigned)(y + dy) < (unsigned)p.H && (unsigned)(x + dx) < (unsigned)p.W) {
-          const float4 v = __ldg(reinterpret_cast<const float4*>(p.src + (q + (long long)dy * p.W + dx) * p.pitch) + cq);
-          const float4 ww = s_w4[t * quads + cq];
-          a0 = fmaf(v.x, ww.x, a0);
-          a1 = fmaf(v.y, ww.y, a1);
-          a2 = fmaf(v.z, ww.z, a2);
-          a3 = fmaf(v.w, ww.w, a3);
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const float4 w0 = w[3 * r], w1 = w[3 * r + 1], w2 = w[3 * r + 2];
+        a0 = fmaf(c0v[r].x, w0.x, fmaf(c1v[r].x, w1.x, fmaf(c2v[r].x, w2.x, a0)));
+        a1 = fmaf(c0v[r].y, w0.y, fmaf(c1v[r].y, w1.y, fmaf(c2v[r].y, w2.y, a1)));
+        a2 = fmaf(c0v[r].z, w0.z, fmaf(c1v[r].z, w1.z, fmaf(c2v[r].z, w2.z, a2)));
+        a3 = fmaf(c0v[r].w, w0.w, fmaf(c1v[r].w, w1.w, fmaf(c2v[r].w, w2.w, a3)));
+      }
+      float acc = (a0 + a1) + (a2 + a3);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) p.y[q] = acc + p.bias + __ldg(p.x2 + q);
+      if (++x == W) {                                // next image row (or next image): rebuild the window
+        x = 0;
+        if (++y == H) y = 0;
+        if (q + 1 < q1) {
+#pragma unroll
+          for (int r = 0; r < 3; ++r) c0v[r] = zero4;
+          load_col(q + 1, 0, c1v);
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          c0v[r] = c1v[r];
+          c1v[r] = c2v[r];
         }
       }
-      acc = (a0 + a1) + (a2 + a3);
     }
-    for (int o = lpp >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (cq == 0 && q < total) p.y[q] = acc + p.bias + __ldg(p.x2 + q);
   }
 }
 

@@ -219,6 +219,81 @@ __global__ void __launch_bounds__(256) last_dgrad_s2d_kernel(const LastDgradPara
   }
 }
 
+// Row-walking form of the same kernel for 3x3 filters and C % 4 == 0, C <= 128 (the reference's R-CNN1): lane = channel
+// quad with its 9 x 4 filter values in registers, a warp walks a run of HR pixels of one image row with a sliding 3x3
+// window of dY (three broadcast loads per pixel, no index divisions in the loop) and writes 8 bytes per plane per lane:
+// a pixel's C channels leave as one contiguous run of the LR pixel's (i*r + j)*C column block.
+constexpr int kDgradRun = 32;
+__global__ void __launch_bounds__(256) last_dgrad_s2d_rows_kernel(const LastDgradParams p) {
+  const int lane = threadIdx.x & 31, quads = p.C >> 2;
+  const bool active = lane < quads;
+  float4 w[9];                                     // scalar loads: p.w points into the flat parameter buffer (4-byte aligned)
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const float* wt = p.w + t * p.C + 4 * lane;
+    w[t] = active ? make_float4(__ldg(wt), __ldg(wt + 1), __ldg(wt + 2), __ldg(wt + 3)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const int HH = p.H * p.r, WW = p.W * p.r;
+  const long long total = (long long)p.n_img * HH * WW;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long q0 = warp0 * kDgradRun; q0 < total; q0 += nwarps * kDgradRun) {
+    const long long q1 = q0 + kDgradRun < total ? q0 + kDgradRun : total;
+    int X = (int)(q0 % WW), Y = (int)((q0 / WW) % HH);
+    long long img = q0 / ((long long)WW * HH);
+    // d hr[q] = sum_tap w[tap] * dY[q - off(tap)]: window columns X+1, X, X-1 pair with filter columns dx = -1, 0, +1
+    float l[3], m[3], r3[3];                        // dY columns X-1, X, X+1 (rows Y-1, Y, Y+1)
+    auto load_col = [&](long long q, int XX, float (&col)[3]) {
+#pragma unroll
+      for (int rr = 0; rr < 3; ++rr) {
+        const int YY = Y + rr - 1;
+        col[rr] = (YY >= 0 && YY < HH && XX >= 0 && XX < WW) ? __ldg(p.dY + q + (long long)(rr - 1) * WW + (XX - X)) : 0.f;
+      }
+    };
+    load_col(q0, X - 1, l);
+    load_col(q0, X, m);
+    for (long long q = q0; q < q1; ++q) {
+      load_col(q, X + 1, r3);
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+      for (int rr = 0; rr < 3; ++rr) {
+        // filter row ky = 2 - rr pairs with dY row Y + (rr - 1): tap (dy, dx) meets dY[Y - dy][X - dx]
+        const float4 wl = w[3 * (2 - rr) + 2], wm = w[3 * (2 - rr) + 1], wr = w[3 * (2 - rr) + 0];
+        a0 = fmaf(wl.x, l[rr], fmaf(wm.x, m[rr], fmaf(wr.x, r3[rr], a0)));
+        a1 = fmaf(wl.y, l[rr], fmaf(wm.y, m[rr], fmaf(wr.y, r3[rr], a1)));
+        a2 = fmaf(wl.z, l[rr], fmaf(wm.z, m[rr], fmaf(wr.z, r3[rr], a2)));
+        a3 = fmaf(wl.w, l[rr], fmaf(wm.w, m[rr], fmaf(wr.w, r3[rr], a3)));
+      }
+      if (active) {
+        const int y = Y / p.r, i = Y - y * p.r, x = X / p.r, j = X - x * p.r;
+        const size_t o = (((size_t)img * p.H + y) * p.W + x) * p.pitch + (size_t)(i * p.r + j) * p.C + 4 * lane;
+        __half h0, l0, h1, l1, h2, l2, h3, l3;
+        split_f16(a0, h0, l0);
+        split_f16(a1, h1, l1);
+        split_f16(a2, h2, l2);
+        split_f16(a3, h3, l3);
+        *reinterpret_cast<uint2*>(p.dz_hi + o) = make_uint2(pack_h2(h0, h1), pack_h2(h2, h3));
+        if (p.dz_lo != nullptr) *reinterpret_cast<uint2*>(p.dz_lo + o) = make_uint2(pack_h2(l0, l1), pack_h2(l2, l3));
+      }
+      if (++X == WW) {
+        X = 0;
+        if (++Y == HH) { Y = 0; ++img; }
+        if (q + 1 < q1) {
+#pragma unroll
+          for (int rr = 0; rr < 3; ++rr) l[rr] = 0.f;
+          load_col(q + 1, 0, m);
+        }
+      } else {
+#pragma unroll
+        for (int rr = 0; rr < 3; ++rr) {
+          l[rr] = m[rr];
+          m[rr] = r3[rr];
+        }
+      }
+    }
+  }
+}
+
 // space_to_depth of a plane tensor (gradient of the first depth_to_space of the x4 graph, DCSCN.py:298-301).
 struct S2dParams {
   int n_img, H, W, r, C;   // LR-side size; src is [N, r*H, r*W, src_pitch]
@@ -469,41 +544,58 @@ struct FirstWgradParams {
 };
 
 __global__ void __launch_bounds__(256) first_wgrad_kernel(const FirstWgradParams p) {
-  extern __shared__ float s_red[];                 // [blockDim.y][taps * CP]
-  const int taps = p.ksz * p.ksz, half = p.ksz >> 1;
-  const int CP = blockDim.x, R = blockDim.y;
-  const size_t total = (size_t)p.n_img * p.H * p.W;
-  const size_t q0 = (size_t)blockIdx.x * p.px_per_block;
-  const size_t q1 = q0 + p.px_per_block < total ? q0 + p.px_per_block : total;
-  for (int c0 = 0; c0 < p.cout; c0 += CP) {
-    const int c = c0 + threadIdx.x;
-    float acc[kLastWgMaxTaps];
+  // Thread = one output channel (all warps walk the SAME pixel run of the CTA, each with its own 32 channels); the 3x3
+  // neighbourhood of x slides along the row (three broadcast loads per pixel, no divisions in the loop); k*k partial
+  // sums per thread, one atomic per (tap, channel) per CTA.  Only ksz == 3 takes this path.
+  const int c = threadIdx.x;
+  const bool active = c < p.cout;
+  const long long total = (long long)p.n_img * p.H * p.W;
+  const long long q0 = (long long)blockIdx.x * p.px_per_block;
+  const long long q1 = q0 + p.px_per_block < total ? q0 + p.px_per_block : total;
+  if (q0 >= total) return;
+  const int W = p.W, H = p.H;
+  int x = (int)(q0 % W), y = (int)((q0 / W) % H);
+  float acc[9];
 #pragma unroll
-    for (int t = 0; t < kLastWgMaxTaps; ++t) acc[t] = 0.f;
-    for (size_t q = q0 + threadIdx.y; q < q1; q += R) {
-      const int x = (int)(q % p.W), y = (int)((q / p.W) % p.H);
-      const float zv = c < p.cout ? load_planes(p.dz_hi, p.dz_lo, q * p.dz_pitch + c) : 0.f;
+  for (int t = 0; t < 9; ++t) acc[t] = 0.f;
+  float l[3], m[3], r3[3];
+  auto load_col = [&](long long q, int xx, float (&col)[3]) {
 #pragma unroll
-      for (int t = 0; t < kLastWgMaxTaps; ++t) {
-        if (t < taps) {
-          const int dy = t / p.ksz - half, dx = t % p.ksz - half;
-          const int yy = y + dy, xx = x + dx;
-          if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W)
-            acc[t] = fmaf(zv, __ldg(p.x + (ptrdiff_t)q + ((ptrdiff_t)dy * p.W + dx)), acc[t]);
-        }
+    for (int rr = 0; rr < 3; ++rr) {
+      const int yy = y + rr - 1;
+      col[rr] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(p.x + q + (long long)(rr - 1) * W + (xx - x)) : 0.f;
+    }
+  };
+  load_col(q0, x - 1, l);
+  load_col(q0, x, m);
+  for (long long q = q0; q < q1; ++q) {
+    load_col(q, x + 1, r3);
+    const float zv = active ? load_planes(p.dz_hi, p.dz_lo, (size_t)q * p.dz_pitch + c) : 0.f;
+#pragma unroll
+    for (int rr = 0; rr < 3; ++rr) {               // tap (dy, dx) = (rr - 1, -1 | 0 | +1) meets x[q + off]
+      acc[3 * rr + 0] = fmaf(zv, l[rr], acc[3 * rr + 0]);
+      acc[3 * rr + 1] = fmaf(zv, m[rr], acc[3 * rr + 1]);
+      acc[3 * rr + 2] = fmaf(zv, r3[rr], acc[3 * rr + 2]);
+    }
+    if (++x == W) {
+      x = 0;
+      if (++y == H) y = 0;
+      if (q + 1 < q1) {
+#pragma unroll
+        for (int rr = 0; rr < 3; ++rr) l[rr] = 0.f;
+        load_col(q + 1, 0, m);
+      }
+    } else {
+#pragma unroll
+      for (int rr = 0; rr < 3; ++rr) {
+        l[rr] = m[rr];
+        m[rr] = r3[rr];
       }
     }
-    __syncthreads();
+  }
+  if (active) {
 #pragma unroll
-    for (int t = 0; t < kLastWgMaxTaps; ++t)
-      if (t < taps) s_red[((size_t)threadIdx.y * taps + t) * CP + threadIdx.x] = acc[t];
-    __syncthreads();
-    for (int i = threadIdx.y * CP + threadIdx.x; i < taps * CP; i += CP * R) {
-      const int t = i / CP, cc = i - t * CP;
-      float sum = 0.f;
-      for (int r = 0; r < R; ++r) sum += s_red[((size_t)r * taps + t) * CP + cc];
-      if (c0 + cc < p.cout) atomicAdd(p.dW + (size_t)t * p.cout + c0 + cc, sum);
-    }
+    for (int t = 0; t < 9; ++t) atomicAdd(p.dW + (size_t)t * p.cout + c, acc[t]);
   }
 }
 
@@ -512,30 +604,40 @@ struct ColSumParams {
   size_t pixels; int C; const __half *hi, *lo; int pitch; float* out; int px_per_block;
 };
 __global__ void __launch_bounds__(256) colsum_kernel(const ColSumParams p) {
-  // blockDim = (channel-pair lanes, pixel rows); half2 loads, per-thread partial sums reduced over the rows in smem
-  extern __shared__ float s_cs[];                  // [rows][2 * lanes]
+  // blockDim = (8-channel lanes, pixel rows); 16-byte loads, per-thread partial sums reduced over the rows in smem.
+  // Needs pitch % 8 == 0 (true for every plane tensor: pitches are multiples of 16).
+  extern __shared__ float s_cs[];                  // [rows][8 * lanes]
   const int CP = blockDim.x, R = blockDim.y;
   const size_t q0 = (size_t)blockIdx.x * p.px_per_block;
   const size_t q1 = q0 + p.px_per_block < p.pixels ? q0 + p.px_per_block : p.pixels;
-  for (int c0 = 0; c0 < p.C; c0 += 2 * CP) {
-    const int c = c0 + 2 * threadIdx.x;
-    float s0 = 0.f, s1 = 0.f;
-    if (c < p.C) {                                  // pitch is even and >= C rounded up to 2: the pair is in bounds
-#pragma unroll 4
+  for (int c0 = 0; c0 < p.C; c0 += 8 * CP) {
+    const int c = c0 + 8 * threadIdx.x;
+    float sum[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sum[i] = 0.f;
+    if (c < p.C) {
+#pragma unroll 2
       for (size_t q = q0 + threadIdx.y; q < q1; q += R) {
-        const float2 v = load_planes2(p.hi, p.lo, q * p.pitch + c);
-        s0 += v.x;
-        s1 += v.y;
+        const uint4 vh = __ldg(reinterpret_cast<const uint4*>(p.hi + q * p.pitch + c));
+        const uint4 vl = p.lo ? __ldg(reinterpret_cast<const uint4*>(p.lo + q * p.pitch + c)) : make_uint4(0, 0, 0, 0);
+        const uint32_t hh[4] = {vh.x, vh.y, vh.z, vh.w}, ll[4] = {vl.x, vl.y, vl.z, vl.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hh[i]));
+          const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&ll[i]));
+          sum[2 * i] += a.x + b.x;
+          sum[2 * i + 1] += a.y + b.y;
+        }
       }
     }
     __syncthreads();
-    s_cs[threadIdx.y * 2 * CP + 2 * threadIdx.x] = s0;
-    s_cs[threadIdx.y * 2 * CP + 2 * threadIdx.x + 1] = s1;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s_cs[threadIdx.y * 8 * CP + 8 * threadIdx.x + i] = sum[i];
     __syncthreads();
-    for (int i = threadIdx.y * CP + threadIdx.x; i < 2 * CP; i += CP * R) {
+    for (int i = threadIdx.y * CP + threadIdx.x; i < 8 * CP; i += CP * R) {
       if (c0 + i >= p.C) continue;
       float tot = 0.f;
-      for (int r = 0; r < R; ++r) tot += s_cs[r * 2 * CP + i];
+      for (int r = 0; r < R; ++r) tot += s_cs[r * 8 * CP + i];
       atomicAdd(p.out + c0 + i, tot);
     }
   }

@@ -108,7 +108,7 @@ __device__ __forceinline__ void ds_pointwise(const DsLayerParams& p, const float
 template <int KSZ>
 __global__ void __launch_bounds__(kDsThreads) ds_layer_kernel(const DsLayerParams p) {
   extern __shared__ float4 s_raw[];
-  constexpr int kk = KSZ * KSZ, half = KSZ >> 1;
+  constexpr int kk = KSZ * KSZ;
   const int cin_p = ds_cin_pad(p.cin), cout_p = ds_cout_pad(p.cout);
   float* s_d = reinterpret_cast<float*>(s_raw);       // [kDsPix][cin_p]
   float* s_w = s_d + kDsPix * cin_p;                  // [cin_p][cout_p]
@@ -130,40 +130,68 @@ __global__ void __launch_bounds__(kDsThreads) ds_layer_kernel(const DsLayerParam
   for (int i = threadIdx.x; i < kk * p.cin; i += kDsThreads) s_dw[i] = __ldg(p.dw + i);
   __syncthreads();
 
-  // depthwise: LP lanes per pixel (smallest power of two >= cin_p, at most a warp), channels strided by LP
-  int LP = 1;
-  while (LP < cin_p && LP < 32) LP <<= 1;
-  const int px_per_pass = kDsThreads / LP;
-  for (int px = threadIdx.x / LP; px < kDsPix; px += px_per_pass) {
-    float* drow = s_d + px * cin_p;
-    const int l = threadIdx.x & (LP - 1);
-    if (px >= npix) {
-      for (int c = l; c < cin_p; c += LP) drow[c] = 0.f;
-      continue;
-    }
-    const long long gp = base + px;
-    const int x = s_x[px], y = s_y[px];
-    const float* ctr = p.src + (size_t)gp * p.src_pitch;
-    // all taps of a channel are loaded before the first FMA (memory-level parallelism: this phase is latency-bound)
-    bool ok[kk];
-    long long toff[kk];
+  // depthwise.  3x3: a warp walks kDsPix / 8 consecutive pixels with lane = channel and a sliding 3x3 window (three
+  // coalesced loads per pixel and channel, filter taps in registers, no per-element index arithmetic).
+  // 1x1 (A1 / B1 of a depthwise-separable graph): a per-channel scale, one load per (pixel, channel).
+  if (KSZ == 3) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int PPW = kDsPix / (kDsThreads / 32);
+    const int px0 = warp * PPW;
+    const int px1 = (px0 + PPW) < npix ? (px0 + PPW) : npix;
+    const int W = p.W, H = p.H;
+    for (int c0 = 0; c0 < p.cin && px0 < npix; c0 += 32) {
+      const int c = c0 + lane;
+      const bool act = c < p.cin;
+      float wd[9];
 #pragma unroll
-    for (int t = 0; t < kk; ++t) {
-      const int dy = t / KSZ - half, dx = t % KSZ - half;
-      ok[t] = (unsigned)(y + dy) < (unsigned)p.H && (unsigned)(x + dx) < (unsigned)p.W;
-      toff[t] = ((long long)dy * p.W + dx) * p.src_pitch;
-    }
-#pragma unroll 2
-    for (int c = l; c < cin_p; c += LP) {
-      float v[kk];
+      for (int t = 0; t < 9; ++t) wd[t] = act ? s_dw[t * p.cin + c] : 0.f;
+      int x = s_x[px0], y = s_y[px0];
+      const float* ctr = p.src + (size_t)(base + px0) * p.src_pitch + c;   // centre pixel, this lane's channel
+      float l[3], m[3], r[3];
+      auto load_col = [&](int xx, float (&col)[3]) {
 #pragma unroll
-      for (int t = 0; t < kk; ++t) v[t] = (c < p.cin && ok[t]) ? __ldg(ctr + toff[t] + c) : 0.f;
-      float acc = 0.f;
-      if (c < p.cin) {
+        for (int rr = 0; rr < 3; ++rr) {
+          const int yy = y + rr - 1;
+          col[rr] = (act && yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(ctr + ((long long)(rr - 1) * W + (xx - x)) * p.src_pitch) : 0.f;
+        }
+      };
+      load_col(x - 1, l);
+      load_col(x, m);
+      for (int px = px0; px < px1; ++px) {
+        load_col(x + 1, r);
+        float acc = 0.f;
 #pragma unroll
-        for (int t = 0; t < kk; ++t) acc = fmaf(v[t], s_dw[t * p.cin + c], acc);
+        for (int rr = 0; rr < 3; ++rr)
+          acc = fmaf(l[rr], wd[3 * rr], fmaf(m[rr], wd[3 * rr + 1], fmaf(r[rr], wd[3 * rr + 2], acc)));
+        if (act) s_d[px * cin_p + c] = acc;
+        ctr += p.src_pitch;
+        if (++x == W) {                              // next image row (or image): rebuild the window
+          x = 0;
+          if (++y == H) y = 0;
+          if (px + 1 < px1) {
+#pragma unroll
+            for (int rr = 0; rr < 3; ++rr) l[rr] = 0.f;
+            load_col(0, m);
+          }
+        } else {
+#pragma unroll
+          for (int rr = 0; rr < 3; ++rr) {
+            l[rr] = m[rr];
+            m[rr] = r[rr];
+          }
+        }
       }
-      drow[c] = acc;
+    }
+    // zero padding: channels [cin, cin_p) of every row and the rows past the last pixel
+    const int padc = cin_p - p.cin;
+    for (int i = threadIdx.x; i < kDsPix * padc; i += kDsThreads) s_d[(i / padc) * cin_p + p.cin + i % padc] = 0.f;
+    for (int i = threadIdx.x + npix * cin_p; i < kDsPix * cin_p; i += kDsThreads) s_d[i] = 0.f;
+  } else {
+    for (int i = threadIdx.x; i < kDsPix * cin_p; i += kDsThreads) {
+      const int px = i / cin_p, c = i - px * cin_p;
+      float v = 0.f;
+      if (px < npix && c < p.cin) v = __ldg(p.src + (size_t)(base + px) * p.src_pitch + c) * s_dw[c];
+      s_d[i] = v;
     }
   }
   __syncthreads();

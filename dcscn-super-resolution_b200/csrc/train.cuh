@@ -171,7 +171,6 @@ __global__ void __launch_bounds__(256) last_dgrad_s2d_kernel(const LastDgradPara
     const unsigned i32 = (unsigned)idx;
     const unsigned Q32 = i32 / (unsigned)groups;
     const int g = (int)(i32 - Q32 * (unsigned)groups);
-    const size_t Q = Q32;
     const unsigned R32 = Q32 / (unsigned)WW;
     const int X = (int)(Q32 - R32 * (unsigned)WW), Y = (int)(R32 % (unsigned)HH);
     const size_t img = R32 / (unsigned)HH;

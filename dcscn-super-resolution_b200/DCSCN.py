@@ -192,8 +192,6 @@ class SuperResolution:
             problems.append("--reconstruct_layers=%d" % self.reconstruct_layers)
         if self.optimizer != "adam":
             problems.append("--optimizer=%s (only adam)" % self.optimizer)
-        if self.use_l1_loss:
-            problems.append("--use_l1_loss")
         if problems:
             raise NotImplementedError("not supported by the B200 engine: " + ", ".join(problems))
 
@@ -247,6 +245,8 @@ class SuperResolution:
     def build_optimizer(self):
         """DCSCN.py:334-369: the loss / clip / Adam step lives inside the engine's train_step."""
         self.optimizer_built = True
+        if self.use_l1_loss:
+            self.engine.set_option("l1_loss", 1)
         util.print_num_of_total_parameters(self, output_detail=True)
 
     def build_summary_saver(self, with_saver=True):

@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const ConvFirstParams p
 // 3x3 fast path: lane = 8 consecutive output channels (weights, bias, alpha live in registers for the whole kernel),
 // warp = one pixel at a time, so each pixel's 2 x n_pad fp16 values leave the SM as two contiguous, fully coalesced
 // rows.  HBM-write-bound by construction (CNN1 writes 2 x 208 fp16 per LR pixel and reads 4 bytes).
-__global__ void __launch_bounds__(256) conv_first3x3_kernel(const ConvFirstParams p) {
+__global__ void __launch_bounds__(256, 2) conv_first3x3_kernel(const ConvFirstParams p) {
   const int lane = threadIdx.x & 31;
   const int lanes_used = p.n_pad >> 3;
   const bool active = lane < lanes_used;

@@ -157,6 +157,7 @@ struct dcscn_handle {
   std::vector<TcLayer> tcl;          // CNN2..CNNL, A1+B1, B2, Up-PS [, Up-PS2]
   std::vector<TcLayer> bwd;          // data-gradient twins (transposed, flipped filters), see build_bwd_layers
   bool train_enabled = false;
+  int l1_loss = 0;                   // --use_l1_loss: image_loss = mean |y_ - y| (DCSCN.py:342-344)
   int wgrad_halo = 1;                // the three dx taps of a filter row share one 18-pixel-wide A box
   int wgrad_taps = 0;                // 0 = automatic (up to 3 filter taps per wgrad CTA), else the cap
   int wgrad_impl = 0;                // 0 = tcgen05 (wgrad_tc.cuh), 1 = CUDA cores (validation)
@@ -1506,6 +1507,8 @@ int dcscn_set_option(dcscn_handle* h, const char* key, int64_t value) {
   } else if (k == "wgrad_impl") {
     if (value != 0 && value != 1) return fail("wgrad_impl must be 0 (tensor cores) or 1 (CUDA cores)");
     h->wgrad_impl = (int)value;
+  } else if (k == "l1_loss") {
+    h->l1_loss = value ? 1 : 0;
   } else if (k == "wgrad_halo") {
     h->wgrad_halo = value ? 1 : 0;
   } else if (k == "wgrad_taps") {

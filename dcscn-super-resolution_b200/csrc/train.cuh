@@ -31,31 +31,43 @@ __device__ __forceinline__ void store_planes(__half* hi, __half* lo, size_t i, f
 }
 
 // ------------------------------------------------------------------------------------------------ loss ----
-// diff = y_ - y; mse = mean(diff^2) (DCSCN.py:340-347); dY = dL/dy_ * grad_scale = diff * (2 * grad_scale / count).
+// diff = y_ - y; mse = mean(diff^2) (DCSCN.py:340-347).  image_loss = mse, or mean|diff| with --use_l1_loss
+// (DCSCN.py:342-344).  dY = d image_loss / d y_ * grad_scale: diff * dscale (dscale = 2 * grad_scale / count), or
+// sign(diff) * dscale (dscale = grad_scale / count) for the L1 loss.
 struct LossParams {
   const float* y_pred;
   const float* y_true;
   float* dY;
   size_t count;
-  float dscale;        // 2 * grad_scale / count
-  double* sq_sum;      // sum of diff^2 (one double)
+  float dscale;
+  double* sq_sum;      // sum of diff^2
+  double* abs_sum;     // sum of |diff|
+  int l1;
 };
 
 __global__ void __launch_bounds__(256) loss_kernel(const LossParams p) {
-  double acc = 0.0;
+  double acc = 0.0, acc1 = 0.0;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.count; i += (size_t)gridDim.x * blockDim.x) {
     const float d = p.y_pred[i] - p.y_true[i];
-    p.dY[i] = d * p.dscale;
+    p.dY[i] = p.l1 ? (d > 0.f ? p.dscale : (d < 0.f ? -p.dscale : 0.f)) : d * p.dscale;   // tf.abs has gradient sign(x)
     acc += (double)d * (double)d;
+    acc1 += (double)fabsf(d);
   }
-  __shared__ double s[256];
+  __shared__ double s[256], s1[256];
   s[threadIdx.x] = acc;
+  s1[threadIdx.x] = acc1;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
-    if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+    if (threadIdx.x < o) {
+      s[threadIdx.x] += s[threadIdx.x + o];
+      s1[threadIdx.x] += s1[threadIdx.x + o];
+    }
     __syncthreads();
   }
-  if (threadIdx.x == 0) atomicAdd(p.sq_sum, s[0]);
+  if (threadIdx.x == 0) {
+    atomicAdd(p.sq_sum, s[0]);
+    atomicAdd(p.abs_sum, s1[0]);
+  }
 }
 
 // --------------------------------------------------------------------------------------- R-CNN1 backward ----

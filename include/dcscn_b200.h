@@ -131,6 +131,8 @@ int dcscn_get_activation(dcscn_handle* h, const char* tensor, float* host_data, 
  *          "cluster" 1 | 2 | 4 = CTAs per cluster multicasting weight tiles in the single-CTA kernel (default 1);
  *          "fuse_last" 1 | 0 = compute the per-pixel half of R-CNN1 inside the last Up-PS epilogue (default 1);
  *          "timing" 0 | 1 = record per-launch CUDA events (see dcscn_get_timings);
+ *          "l1_loss" 0 | 1 = image_loss of the train step is mean |y_ - y| instead of the MSE (--use_l1_loss,
+ *          DCSCN.py:342-344; the returned mse stays the MSE);
  *          "wgrad_impl" 0 | 1 = filter gradients on tcgen05 (default) or on CUDA cores (cross-check);
  *          "wgrad_taps" 0..3 = filter taps per wgrad CTA (0 = automatic);
  *          "host_repack" 0 | 1 = after an optimizer step rebuild the packed tensor-core weight images on the host

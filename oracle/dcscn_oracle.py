@@ -284,8 +284,9 @@ class Oracle:
         the dead conv_W, tf_graph.py:183,212)."""
         return [scope + "/conv_W" for scope, *_ in self.table]
 
-    def loss_and_grads(self, x_nhwc, x2_nhwc, y_nhwc, keep_prob=1.0, masks=None):
-        """mse, loss = mse + l2_decay*sum(sum(W^2)/2), d loss / d trainables (DCSCN.py:340-357,399)."""
+    def loss_and_grads(self, x_nhwc, x2_nhwc, y_nhwc, keep_prob=1.0, masks=None, use_l1_loss=False):
+        """mse, loss = image_loss + l2_decay*sum(sum(W^2)/2), d loss / d trainables (DCSCN.py:340-357,399);
+        image_loss = mse, or mean|diff| with use_l1_loss (DCSCN.py:342-347)."""
         cfg = self.cfg
         params = {n: _t(self.w[n], self.dtype).clone().requires_grad_(True) for n in self.trainable_names()}
         x = _t(x_nhwc, self.dtype).permute(0, 3, 1, 2).contiguous()
@@ -294,10 +295,10 @@ class Oracle:
         y_ = self.forward_nchw(x, x2, params=params, keep_prob=keep_prob, masks=masks)
         diff = y_ - y
         mse = torch.mean(diff * diff)
-        loss = mse
+        loss = torch.mean(torch.abs(diff)) if use_l1_loss else mse
         if cfg.l2_decay > 0:
             l2 = sum(torch.sum(params[n] * params[n]) / 2 for n in self.l2_weight_names())
-            loss = mse + cfg.l2_decay * l2
+            loss = loss + cfg.l2_decay * l2
         grads = torch.autograd.grad(loss, [params[n] for n in self.trainable_names()], allow_unused=True)
         g = {}
         for n, gr in zip(self.trainable_names(), grads):

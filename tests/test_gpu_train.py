@@ -169,3 +169,21 @@ def test_full_size_batch_gradient_is_mean_of_half_batch_gradients():
         want = 0.5 * (g_a[k] + g_b[k])
         assert np.abs(g_all[k] - want).max() <= 2e-4 * np.abs(want).max() + 1e-9, (k, float(np.abs(g_all[k] - want).max()), float(np.abs(want).max()))
     eng.close()
+
+
+def test_l1_loss_gradients_match_oracle():
+    """--use_l1_loss (DCSCN.py:342-344): image_loss = mean|y_ - y|, gradient sign(diff) / count; mse is still reported."""
+    n, h, w = 2, 12, 10
+    cfg, wts, eng, x, x2, y = setup(SMALL, 1.0, n, h, w)
+    eng.set_option("l1_loss", 1)
+    loss, mse = eng.train_step_host(x, x2, y, lr=0.002, seed=1, apply_update=False)
+    orc = O.Oracle(cfg, wts, torch.float64)
+    mse_ref, loss_ref, grads_ref = orc.loss_and_grads(x.astype(np.float64), x2.astype(np.float64), y.astype(np.float64),
+                                                      keep_prob=1.0, use_l1_loss=True)
+    assert mse == pytest.approx(mse_ref, rel=2e-5)
+    l2 = cfg.l2_decay * sum(float(np.sum(wts[k] ** 2)) / 2 for k in wts if k.endswith("conv_W"))
+    assert loss == pytest.approx(loss_ref - l2, rel=2e-5)       # the engine returns image_loss (what train_batch logs)
+    for name, gref in grads_ref.items():
+        g = eng.get_grad(name)
+        assert np.abs(g - gref).max() <= 2e-3 * np.abs(gref).max() + 1e-7, name
+    eng.close()

@@ -244,7 +244,7 @@ def run_ours(args, rank, world, local_rank):
         achieved = tc_flops / (tc_ms / 1e3) / 1e12
         passes = 3 if args.precision == "f16x3" else 1
         roofline = {
-            "bound": "tensor", "kernel": "conv_tc_kernel (all %d tcgen05 conv launches of one step)" % (len(per) - 2),
+            "bound": "tensor", "kernel": "conv_tc_halo1_kernel / conv_tc_pair_kernel (all %d tcgen05 conv launches of one step)" % (len(per) - 2),
             "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (%s)" % how,
             "mma_passes": passes, "frac_of_issued_mma": achieved * passes / sustained,

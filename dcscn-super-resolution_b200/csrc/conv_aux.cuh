@@ -361,4 +361,66 @@ __global__ void planes_to_f32_kernel(const __half* hi, const __half* lo, float* 
   }
 }
 
+// ------------------------------------------------------------- self-ensemble (DCSCN.py:547-586) --------------
+// The 8 transforms of helper/utilty.py:595-617 (`flip`) as index maps on an [H][W] image:
+//   0 identity, 1 flipud, 2 fliplr, 3 flipud(fliplr), 4 rot90(+1), 5 rot90(-1), 6 flipud(rot90(+1)) = transpose,
+//   7 flipud(rot90(-1)) = anti-transpose.  Types 4..7 swap the image's height and width.
+// src_of(t, i, j) = the source pixel (p, q) of pixel (i, j) of the transformed image.
+__device__ __forceinline__ void ensemble_src(int t, int i, int j, int H, int W, int* p, int* q) {
+  switch (t) {
+    case 0: *p = i; *q = j; break;
+    case 1: *p = H - 1 - i; *q = j; break;
+    case 2: *p = i; *q = W - 1 - j; break;
+    case 3: *p = H - 1 - i; *q = W - 1 - j; break;
+    case 4: *p = j; *q = W - 1 - i; break;
+    case 5: *p = H - 1 - j; *q = i; break;
+    case 6: *p = j; *q = i; break;
+    default: *p = H - 1 - j; *q = W - 1 - i; break;
+  }
+}
+
+// dst[v][i][j] = src[src_of(t0 + v, i, j)] for v in [0, count): the transformed copies that feed one batched forward.
+// All `count` transforms share one output shape [OH][OW] ([H][W] for t < 4, [W][H] otherwise).
+__global__ void __launch_bounds__(256) ensemble_flip_kernel(const float* __restrict__ src, float* __restrict__ dst, int H, int W,
+                                                            int t0, int count) {
+  const int OH = t0 < 4 ? H : W, OW = t0 < 4 ? W : H;
+  const long long per = (long long)OH * OW, total = per * count;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(idx / per);
+    const int r = (int)(idx - (long long)v * per);
+    const int i = r / OW, j = r - i * OW;
+    int p, q;
+    ensemble_src(t0 + v, i, j, H, W, &p, &q);
+    dst[idx] = __ldg(src + (long long)p * W + q);
+  }
+}
+
+// out[p][q] = (sum over t < flips of y_t[inverse position]) / flips, accumulated in fp64 in the order t = 0, 1, ...
+// like the reference's `output += flip(y, i, invert=True)` on a float64 array (DCSCN.py:560-575).
+// ya: transforms 0..3 (shape [H][W] each), yb: transforms 4..7 (shape [W][H] each); H, W = output (HR) size.
+__global__ void __launch_bounds__(256) ensemble_reduce_kernel(const float* __restrict__ ya, const float* __restrict__ yb,
+                                                              double* __restrict__ out, int H, int W, int flips) {
+  const long long total = (long long)H * W;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(idx / W), q = (int)(idx - (long long)p * W);
+    double sum = 0.0;
+    for (int t = 0; t < flips; ++t) {
+      int i, j;
+      switch (t) {                                  // the (i, j) of transform t whose source pixel is (p, q)
+        case 0: i = p; j = q; break;
+        case 1: i = H - 1 - p; j = q; break;
+        case 2: i = p; j = W - 1 - q; break;
+        case 3: i = H - 1 - p; j = W - 1 - q; break;
+        case 4: i = W - 1 - q; j = p; break;
+        case 5: i = q; j = H - 1 - p; break;
+        case 6: i = q; j = p; break;
+        default: i = W - 1 - q; j = H - 1 - p; break;
+      }
+      const float v = t < 4 ? __ldg(ya + ((long long)t * H + i) * W + j) : __ldg(yb + ((long long)(t - 4) * W + i) * H + j);
+      sum += (double)v;
+    }
+    out[idx] = sum / (double)flips;
+  }
+}
+
 }  // namespace dcscn

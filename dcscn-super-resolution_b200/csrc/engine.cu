@@ -157,6 +157,11 @@ struct dcscn_handle {
   std::vector<TcLayer> tcl;          // CNN2..CNNL, A1+B1, B2, Up-PS [, Up-PS2]
   std::vector<TcLayer> bwd;          // data-gradient twins (transposed, flipped filters), see build_bwd_layers
   bool train_enabled = false;
+  float *ens_x = nullptr, *ens_x2 = nullptr, *ens_y = nullptr;   // self-ensemble: transformed copies / per-flip outputs
+  size_t ens_cap = 0;
+  float *ensio_x = nullptr, *ensio_x2 = nullptr;                  // host-call staging of the ensemble entry point
+  double* ensio_y = nullptr;
+  size_t ensio_cap = 0;
   int l1_loss = 0;                   // --use_l1_loss: image_loss = mean |y_ - y| (DCSCN.py:342-344)
   int wgrad_halo = 1;                // the three dx taps of a filter row share one 18-pixel-wide A box
   int wgrad_taps = 0;                // 0 = automatic (up to 3 filter taps per wgrad CTA), else the cap
@@ -1304,6 +1309,7 @@ int dcscn_destroy(dcscn_handle* h) {
   for (TcLayer& t : h->tcl) free_tc(t);
   for (TcLayer& t : h->bwd) free_tc(t);
   train_free(h);
+  cudaFree(h->ens_x); cudaFree(h->ens_x2); cudaFree(h->ens_y); cudaFree(h->ensio_x); cudaFree(h->ensio_x2); cudaFree(h->ensio_y);
   cudaFree(h->d_first_w);
   cudaFree(h->d_first_bias);
   cudaFree(h->d_first_alpha);
@@ -1389,6 +1395,75 @@ int dcscn_forward_host(dcscn_handle* h, const float* x, const float* x2, float* 
   CUDA_TRY(cudaMemcpyAsync(h->io_x2, x2, hr * sizeof(float), cudaMemcpyHostToDevice, st));
   if (forward_impl(h, h->io_x, h->io_x2, h->io_y, n, height, width, st)) return 1;
   CUDA_TRY(cudaMemcpyAsync(y, h->io_y, hr * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// Self-ensemble entirely on the device (DCSCN.py:547-586 `do` with self_ensemble = flips): the transformed copies of x
+// and x2 are produced by a kernel, transforms 0..3 run as ONE batched forward (n = up to 4, shape [h][w]) and 4..7 as
+// another (shape [w][h]), and the inverse transforms + the float64 mean are one more kernel.
+static int ensemble_impl(dcscn_handle* h, const float* x, const float* x2, double* y, int height, int width, int flips,
+                         cudaStream_t st) {
+  if (flips < 1 || flips > 8) return fail("forward_ensemble: flips must be 1..8 (got %d)", flips);
+  if (height <= 0 || width <= 0) return fail("forward_ensemble: bad shape h=%d w=%d", height, width);
+  CUDA_TRY(cudaSetDevice(h->cfg.device_id));
+  const int s = h->cfg.scale;
+  const size_t lr = (size_t)height * width, hr = lr * s * s;
+  if (hr > h->ens_cap) {
+    cudaFree(h->ens_x); cudaFree(h->ens_x2); cudaFree(h->ens_y);
+    h->ens_x = h->ens_x2 = h->ens_y = nullptr;
+    h->ens_cap = 0;
+    CUDA_TRY(cudaMalloc((void**)&h->ens_x, 4 * lr * sizeof(float)));
+    CUDA_TRY(cudaMalloc((void**)&h->ens_x2, 4 * hr * sizeof(float)));
+    CUDA_TRY(cudaMalloc((void**)&h->ens_y, 8 * hr * sizeof(float)));
+    h->ens_cap = hr;
+  }
+  const int na = flips < 4 ? flips : 4, nb = flips - na;
+  const int grid_lr = (int)std::min<size_t>((4 * lr + 255) / 256, (size_t)h->sm_count * 8);
+  const int grid_hr = (int)std::min<size_t>((4 * hr + 255) / 256, (size_t)h->sm_count * 8);
+  for (int grp = 0; grp < 2; ++grp) {
+    const int cnt = grp == 0 ? na : nb;
+    if (cnt == 0) continue;
+    ensemble_flip_kernel<<<grid_lr, 256, 0, st>>>(x, h->ens_x, height, width, 4 * grp, cnt);
+    ensemble_flip_kernel<<<grid_hr, 256, 0, st>>>(x2, h->ens_x2, s * height, s * width, 4 * grp, cnt);
+    CUDA_TRY(cudaGetLastError());
+    h->launches += 2;
+    const int fh = grp == 0 ? height : width, fw = grp == 0 ? width : height;
+    if (forward_impl(h, h->ens_x, h->ens_x2, h->ens_y + (size_t)grp * 4 * hr, cnt, fh, fw, st)) return 1;
+  }
+  ensemble_reduce_kernel<<<(int)std::min<size_t>((hr + 255) / 256, (size_t)h->sm_count * 8), 256, 0, st>>>(
+      h->ens_y, h->ens_y + 4 * hr, y, s * height, s * width, flips);
+  CUDA_TRY(cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+
+int dcscn_forward_ensemble(dcscn_handle* h, const float* x_dev, const float* x2_dev, double* y_dev, int height, int width,
+                           int flips, void* stream) {
+  if (!h || !x_dev || !x2_dev || !y_dev) return fail("dcscn_forward_ensemble: null argument");
+  return ensemble_impl(h, x_dev, x2_dev, y_dev, height, width, flips, (cudaStream_t)stream);
+}
+
+int dcscn_forward_ensemble_host(dcscn_handle* h, const float* x, const float* x2, double* y, int height, int width, int flips) {
+  if (!h || !x || !x2 || !y) return fail("dcscn_forward_ensemble_host: null argument");
+  CUDA_TRY(cudaSetDevice(h->cfg.device_id));
+  const size_t lr = (size_t)height * width;
+  const size_t hr = lr * h->cfg.scale * h->cfg.scale;
+  if (hr > h->ensio_cap) {
+    cudaFree(h->ensio_x); cudaFree(h->ensio_x2); cudaFree(h->ensio_y);
+    h->ensio_x = h->ensio_x2 = nullptr;
+    h->ensio_y = nullptr;
+    h->ensio_cap = 0;
+    CUDA_TRY(cudaMalloc((void**)&h->ensio_x, lr * sizeof(float)));
+    CUDA_TRY(cudaMalloc((void**)&h->ensio_x2, hr * sizeof(float)));
+    CUDA_TRY(cudaMalloc((void**)&h->ensio_y, hr * sizeof(double)));
+    h->ensio_cap = hr;
+  }
+  cudaStream_t st = 0;
+  CUDA_TRY(cudaMemcpyAsync(h->ensio_x, x, lr * sizeof(float), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(h->ensio_x2, x2, hr * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (ensemble_impl(h, h->ensio_x, h->ensio_x2, h->ensio_y, height, width, flips, st)) return 1;
+  CUDA_TRY(cudaMemcpyAsync(y, h->ensio_y, hr * sizeof(double), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   return 0;
 }

@@ -50,7 +50,7 @@ class DcscnConfig(ctypes.Structure):
 
 EXPORTED_SYMBOLS = [
     "dcscn_create", "dcscn_destroy", "dcscn_last_error", "dcscn_num_params", "dcscn_param_info",
-    "dcscn_set_param", "dcscn_get_param", "dcscn_forward", "dcscn_forward_host", "dcscn_get_activation",
+    "dcscn_set_param", "dcscn_get_param", "dcscn_forward", "dcscn_forward_host", "dcscn_forward_ensemble", "dcscn_forward_ensemble_host", "dcscn_get_activation",
     "dcscn_set_option", "dcscn_get_timings", "dcscn_launch_count", "dcscn_device_bytes",
     "dcscn_train_step", "dcscn_train_step_host", "dcscn_get_grad", "dcscn_get_adam_slot", "dcscn_set_adam_slot", "dcscn_get_adam_step",
     "dcscn_set_adam_step", "dcscn_last_grad_norm",
@@ -85,6 +85,8 @@ def load_library(path=None):
     lib.dcscn_get_param.argtypes = [vp, ctypes.c_char_p, fp, c64]
     lib.dcscn_forward.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp]
     lib.dcscn_forward_host.argtypes = [vp, vp, vp, vp, ci, ci, ci]
+    lib.dcscn_forward_ensemble.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp]
+    lib.dcscn_forward_ensemble_host.argtypes = [vp, vp, vp, vp, ci, ci, ci]
     lib.dcscn_get_activation.argtypes = [vp, ctypes.c_char_p, fp, c64]
     lib.dcscn_set_option.argtypes = [vp, ctypes.c_char_p, c64]
     lib.dcscn_get_timings.argtypes = [vp, fp, ci, ctypes.POINTER(ci), ctypes.c_char_p, ci]
@@ -210,6 +212,20 @@ class Engine:
             y = np.empty((n, s * h, s * w, 1), dtype=np.float32)
         ya = _host_array(y)
         self._check(self.lib.dcscn_forward_host(self.handle, xa.ctypes.data, x2a.ctypes.data, ya.ctypes.data, n, h, w))
+        return y
+
+    def forward_ensemble_host(self, x, x2, flips):
+        """Self-ensemble of one image on the device (DCSCN.py:547-586): x [h,w,(1)], x2 [s*h,s*w,(1)] float32 ->
+        float64 [s*h, s*w, 1] mean of the inverse-transformed outputs of the first `flips` transforms."""
+        xa = np.ascontiguousarray(x, dtype=np.float32)
+        x2a = np.ascontiguousarray(x2, dtype=np.float32)
+        h, w = xa.shape[:2]
+        s = int(self.config.scale)
+        if x2a.shape[:2] != (s * h, s * w):
+            raise ValueError("x2 must be [%d,%d], got %s" % (s * h, s * w, x2a.shape[:2]))
+        y = np.empty((s * h, s * w, 1), dtype=np.float64)
+        self._check(self.lib.dcscn_forward_ensemble_host(self.handle, xa.ctypes.data, x2a.ctypes.data, y.ctypes.data, h, w,
+                                                         int(flips)))
         return y
 
     def train_step_host(self, x, x2, y, lr, seed, apply_update=True):

@@ -82,6 +82,14 @@ int dcscn_forward(dcscn_handle* h, const float* x_dev, const float* x2_dev, floa
 /* Same call with HOST buffers (pinned or pageable): H2D, forward, D2H, synchronises before returning. */
 int dcscn_forward_host(dcscn_handle* h, const float* x, const float* x2, float* y, int n, int height, int width);
 
+/* The self-ensemble of `SuperResolution.do` (DCSCN.py:547-586) for ONE image, entirely on the device: the first `flips`
+ * (1..8) transforms of helper/utilty.py:595-617 are applied to x [height,width] and x2 [scale*height, scale*width],
+ * transforms 0..3 and 4..7 each run as one batched forward, and y [scale*height, scale*width] receives the float64 mean
+ * of the inverse-transformed outputs, summed in the order 0, 1, ... like the reference's float64 accumulator. */
+int dcscn_forward_ensemble(dcscn_handle* h, const float* x_dev, const float* x2_dev, double* y_dev, int height, int width,
+                           int flips, void* stream);
+int dcscn_forward_ensemble_host(dcscn_handle* h, const float* x, const float* x2, double* y, int height, int width, int flips);
+
 /*
  * sess.run([self.training_optimizer, self.image_loss, self.mse], {x, x2, y, lr, dropout: keep, is_training: 1})
  * (DCSCN.py:415-425; graph: build_optimizer / add_optimizer_op, DCSCN.py:334-413): forward with inverted dropout

@@ -79,6 +79,27 @@ def test_self_ensemble_8_matches_oracle(tmp_path):
     assert abs(O.compute_psnr(true_y, out, 2) - KA["l12_x2_set5_ens8_per_image"][4]) <= 0.01
 
 
+@pytest.mark.parametrize("flips", [2, 5, 8])
+def test_device_ensemble_equals_the_serial_flip_loop(tmp_path, flips):
+    """`dcscn_forward_ensemble` (flips, two batched forwards and the float64 mean on the GPU) against the reference's
+    serial loop `output += flip(run(flip(x, i)), i, invert=True)` (DCSCN.py:560-575) over the same engine.  The batched
+    forward may cut K into different promotion segments than the n = 1 forward (the segment rule looks at the tile
+    count), so the two agree to fp32 rounding of a 0..255 pixel, not bit for bit: 2e-4."""
+    from helper import utilty as util
+    m = build_model(tmp_path, CD, flips)
+    f = sorted(glob.glob(os.path.join(GOLDEN, "data", "set5", "*.png")))[4]      # non-square: both orientations
+    lr, bic, _ = O.build_inputs_for_evaluate(f, 2)
+    out = m.do(lr, bic)
+    ref = np.zeros_like(out)
+    for i in range(flips):
+        c = lambda a: np.ascontiguousarray(a[None], dtype=np.float32)
+        y = m.engine.forward_host(c(util.flip(lr, i)), c(util.flip(bic, i)))
+        ref += util.flip(y[0], i, invert=True)
+    ref /= flips
+    assert out.dtype == np.float64 and out.shape == ref.shape
+    assert np.abs(out - ref).max() <= 2e-4, float(np.abs(out - ref).max())
+
+
 def test_save_and_reload_checkpoint(tmp_path):
     """save_model writes a TF V2 bundle that load_model (and the reference's Saver) can read back."""
     import shutil

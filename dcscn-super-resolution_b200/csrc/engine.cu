@@ -1002,7 +1002,8 @@ static Plan* get_plan(dcscn_handle* h, int n, int H, int W) {
 // ------------------------------------------------------------------------------------- forward ----
 template <int KC, int NPL>
 static int launch_tc_inst(dcscn_handle* h, const TcLaunch& L, cudaStream_t st) {
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {};   // function attributes are per device
+  bool& attr_set = attr_set_dev[h->cfg.device_id & 63];
   if (!attr_set) {
     CUDA_TRY(cudaFuncSetAttribute(conv_tc_kernel<KC, NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
@@ -1026,7 +1027,8 @@ static int launch_tc_inst(dcscn_handle* h, const TcLaunch& L, cudaStream_t st) {
 
 template <int NPL>
 static int launch_tc_pair(dcscn_handle* h, const TcLaunch& L, cudaStream_t st) {
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {};   // function attributes are per device
+  bool& attr_set = attr_set_dev[h->cfg.device_id & 63];
   if (!attr_set) {
     CUDA_TRY(cudaFuncSetAttribute(conv_tc_pair_kernel<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
@@ -1053,7 +1055,8 @@ static int launch_tc_pair(dcscn_handle* h, const TcLaunch& L, cudaStream_t st) {
 
 template <int NPL>
 static int launch_tc_halo(dcscn_handle* h, const TcLaunch& L, cudaStream_t st) {
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {};   // function attributes are per device
+  bool& attr_set = attr_set_dev[h->cfg.device_id & 63];
   if (!attr_set) {
     CUDA_TRY(cudaFuncSetAttribute(conv_tc_halo_kernel<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
@@ -1081,7 +1084,8 @@ static int launch_tc_halo(dcscn_handle* h, const TcLaunch& L, cudaStream_t st) {
 
 template <int NPL>
 static int launch_tc_halo1(dcscn_handle* h, const TcLaunch& L, cudaStream_t st) {
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {};   // function attributes are per device
+  bool& attr_set = attr_set_dev[h->cfg.device_id & 63];
   if (!attr_set) {
     CUDA_TRY(cudaFuncSetAttribute(conv_tc_halo1_kernel<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
@@ -1153,7 +1157,9 @@ static int launch_ds(dcscn_handle* h, const LayerDef& l, const dcscn_handle::DsD
   } else {
     const size_t smem = ds_smem_bytes(l.k, l.cin, l.cout);
     if (smem > 200 * 1024) return fail("depthwise-separable layer %s: %d -> %d channels exceed the kernel's shared memory", l.scope.c_str(), l.cin, l.cout);
-    static size_t ds_smem_attr = 48 * 1024;   // current opt-in limit of the DS kernels (process-wide, only ever raised)
+    static size_t ds_smem_attr_dev[64] = {};  // current opt-in limit of the DS kernels per device (only ever raised)
+    size_t& ds_smem_attr = ds_smem_attr_dev[h->cfg.device_id & 63];
+    if (ds_smem_attr == 0) ds_smem_attr = 48 * 1024;
     if (smem > ds_smem_attr) {   // raise the opt-in limit only as far as needed (keeps the L1 carve-out large)
       CUDA_TRY(cudaFuncSetAttribute(ds_layer_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       CUDA_TRY(cudaFuncSetAttribute(ds_layer_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -111,7 +111,7 @@ struct TcLaunch {
   ConvGeom hg;
   int halo_grid = 0, halo_na = 0, halo_nb = 0, halo_seg = 1;
   size_t halo_smem = 0;
-  bool halo1 = false;            // single 18x10 box per chunk (experimental)
+  bool halo1 = false;            // single 10 x 18 halo box per chunk serves all nine taps (default for 3x3 layers)
   CUtensorMap t1_hi, t1_lo;
   int halo1_na = 0, halo1_nb = 0, halo1_seg = 1;
   size_t halo1_smem = 0;

@@ -5,10 +5,12 @@
 // Split of the work:
 //   * data gradients (dgrad) of every 3x3 / 1x1 layer run on the SAME tcgen05 implicit-GEMM kernels as the forward
 //     pass (conv_tc*.cuh) with the filters transposed and spatially flipped - no extra MMA code;
-//   * everything else is in this file, on CUDA cores: loss / output gradient, R-CNN1 backward fused with the
-//     depth_to_space gradient (= space_to_depth), PReLU + dropout gradients with the per-channel bias / alpha
-//     reductions, filter gradients (wgrad: a reduction over all pixels, shared-memory tiled, fp32 atomics) and the
-//     fused L2-decay + global-norm + Adam update over one flat parameter buffer.
+//   * filter gradients (wgrad) of those layers run on tcgen05 too, with MN-major operands read straight from the NHWC
+//     planes (wgrad_tc.cuh); `wgrad_kernel` below is the CUDA-core version kept as the cross-check (option wgrad_impl);
+//   * everything else is in this file, on CUDA cores, laid out so a warp touches whole 128-byte lines: loss / output
+//     gradient, R-CNN1 forward / backward fused with the depth_to_space gradient (= space_to_depth), CNN1's filter
+//     gradient, PReLU + dropout gradients with the per-channel bias / alpha reductions, the fused L2-decay + global
+//     norm + Adam update over one flat parameter buffer, and the device-side refresh of the packed weight images.
 //   All activation-sized gradients are kept in the fp16 hi/lo plane format of the forward pass, multiplied by a
 //   power-of-two `grad_scale` (loss scaling) so they sit in fp16's normal range; the scale is removed when the filter
 //   gradients are finalised.

@@ -37,8 +37,10 @@ def oracle_masks(eng, cfg, seed, n, h, w):
     return masks
 
 
-@pytest.mark.parametrize("kw,keep,shape", [(SMALL, 1.0, (2, 12, 10)), (SMALL, 0.8, (2, 16, 24)), (SMALL4, 0.8, (1, 9, 11))],
-                         ids=["x2-nodrop", "x2-drop", "x4-drop"])
+@pytest.mark.parametrize("kw,keep,shape", [(SMALL, 1.0, (2, 12, 10)), (SMALL, 0.8, (2, 16, 24)), (SMALL4, 0.8, (1, 9, 11)),
+                                           (SMALL, 1.0, (1, 1, 1)), (SMALL4, 1.0, (3, 2, 1)), (SMALL, 0.8, (1, 1, 37)),
+                                           (SMALL, 1.0, (2, 33, 3))],
+                         ids=["x2-nodrop", "x2-drop", "x4-drop", "x2-1x1", "x4-2x1", "x2-row", "x2-narrow"])
 def test_gradients_match_oracle(kw, keep, shape):
     n, h, w = shape
     cfg, wts, eng, x, x2, y = setup(kw, keep, n, h, w)

@@ -238,27 +238,33 @@ __global__ void __launch_bounds__(256) conv_last_direct_kernel(const ConvLastPar
   float4 w[9];
 #pragma unroll
   for (int t = 0; t < 9; ++t) w[t] = active ? __ldg(reinterpret_cast<const float4*>(p.w + t * p.C) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
-  const long long total = (long long)p.n_img * p.H * p.W;
+  const int W = p.W, H = p.H;
+  const int segs = (W + kLastRun - 1) / kLastRun;       // runs never cross an image row: no wrap logic in the loop
+  const long long runs = (long long)p.n_img * H * segs;
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  const int W = p.W, H = p.H;
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (long long q0 = warp0 * kLastRun; q0 < total; q0 += nwarps * kLastRun) {
-    const long long q1 = q0 + kLastRun < total ? q0 + kLastRun : total;
-    int x = (int)(q0 % W), y = (int)((q0 / W) % H);
-    float4 c0v[3], c1v[3], c2v[3];                 // window columns x-1, x, x+1 (rows y-1, y, y+1) of this lane's 4 channels
-    auto load_col = [&](long long q, int xx, float4 (&col)[3]) {
-#pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        const int yy = y + r - 1;
-        col[r] = (active && yy >= 0 && yy < H && xx >= 0 && xx < W)
-                     ? __ldg(reinterpret_cast<const float4*>(p.src + (q + (long long)(r - 1) * W + (xx - x)) * p.pitch) + lane) : zero4;
-      }
+  for (long long run = warp0; run < runs; run += nwarps) {
+    const long long row = run / segs;
+    const int xs = (int)(run - row * segs) * kLastRun;
+    const int xe = xs + kLastRun < W ? xs + kLastRun : W;
+    const int y = (int)(row % H);
+    const bool up = y > 0, dn = y + 1 < H;
+    const float* rowp = p.src + (size_t)row * W * p.pitch + 4 * lane;   // (row, x = 0), this lane's channels
+    const size_t rs = (size_t)W * p.pitch;
+    auto load_col = [&](int xx, float4 (&col)[3]) {
+      const bool in = active && xx >= 0 && xx < W;
+      const float* c = rowp + (size_t)(xx < 0 ? 0 : xx) * p.pitch;
+      col[0] = (in && up) ? __ldg(reinterpret_cast<const float4*>(c - rs)) : zero4;
+      col[1] = in ? __ldg(reinterpret_cast<const float4*>(c)) : zero4;
+      col[2] = (in && dn) ? __ldg(reinterpret_cast<const float4*>(c + rs)) : zero4;
     };
-    load_col(q0, x - 1, c0v);
-    load_col(q0, x, c1v);
-    for (long long q = q0; q < q1; ++q) {
-      load_col(q, x + 1, c2v);
+    float4 c0v[3], c1v[3], c2v[3];                 // window columns x-1, x, x+1 (rows y-1, y, y+1) of this lane's 4 channels
+    load_col(xs - 1, c0v);
+    load_col(xs, c1v);
+#pragma unroll 4
+    for (int x = xs; x < xe; ++x) {
+      load_col(x + 1, c2v);
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
@@ -271,21 +277,12 @@ __global__ void __launch_bounds__(256) conv_last_direct_kernel(const ConvLastPar
       float acc = (a0 + a1) + (a2 + a3);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      const long long q = row * W + x;
       if (lane == 0) p.y[q] = acc + p.bias + __ldg(p.x2 + q);
-      if (++x == W) {                                // next image row (or next image): rebuild the window
-        x = 0;
-        if (++y == H) y = 0;
-        if (q + 1 < q1) {
 #pragma unroll
-          for (int r = 0; r < 3; ++r) c0v[r] = zero4;
-          load_col(q + 1, 0, c1v);
-        }
-      } else {
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-          c0v[r] = c1v[r];
-          c1v[r] = c2v[r];
-        }
+      for (int r = 0; r < 3; ++r) {
+        c0v[r] = c1v[r];
+        c1v[r] = c2v[r];
       }
     }
   }

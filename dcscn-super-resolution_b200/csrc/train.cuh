@@ -247,26 +247,34 @@ __global__ void __launch_bounds__(256) last_dgrad_s2d_rows_kernel(const LastDgra
     w[t] = active ? make_float4(__ldg(wt), __ldg(wt + 1), __ldg(wt + 2), __ldg(wt + 3)) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   const int HH = p.H * p.r, WW = p.W * p.r;
-  const long long total = (long long)p.n_img * HH * WW;
+  const int segs = (WW + kDgradRun - 1) / kDgradRun;    // runs never cross an image row
+  const long long runs = (long long)p.n_img * HH * segs;
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (long long q0 = warp0 * kDgradRun; q0 < total; q0 += nwarps * kDgradRun) {
-    const long long q1 = q0 + kDgradRun < total ? q0 + kDgradRun : total;
-    int X = (int)(q0 % WW), Y = (int)((q0 / WW) % HH);
-    long long img = q0 / ((long long)WW * HH);
+  for (long long run = warp0; run < runs; run += nwarps) {
+    const long long row = run / segs;                 // img * HH + Y
+    const int xs = (int)(run - row * segs) * kDgradRun;
+    const int xe = xs + kDgradRun < WW ? xs + kDgradRun : WW;
+    const int Y = (int)(row % HH);
+    const long long img = row / HH;
+    const bool up = Y > 0, dn = Y + 1 < HH;
+    const float* rowp = p.dY + row * WW;
     // d hr[q] = sum_tap w[tap] * dY[q - off(tap)]: window columns X+1, X, X-1 pair with filter columns dx = -1, 0, +1
-    float l[3], m[3], r3[3];                        // dY columns X-1, X, X+1 (rows Y-1, Y, Y+1)
-    auto load_col = [&](long long q, int XX, float (&col)[3]) {
-#pragma unroll
-      for (int rr = 0; rr < 3; ++rr) {
-        const int YY = Y + rr - 1;
-        col[rr] = (YY >= 0 && YY < HH && XX >= 0 && XX < WW) ? __ldg(p.dY + q + (long long)(rr - 1) * WW + (XX - X)) : 0.f;
-      }
+    auto load_col = [&](int XX, float (&col)[3]) {
+      const bool in = XX >= 0 && XX < WW;
+      const float* c = rowp + (XX < 0 ? 0 : XX);
+      col[0] = (in && up) ? __ldg(c - WW) : 0.f;
+      col[1] = in ? __ldg(c) : 0.f;
+      col[2] = (in && dn) ? __ldg(c + WW) : 0.f;
     };
-    load_col(q0, X - 1, l);
-    load_col(q0, X, m);
-    for (long long q = q0; q < q1; ++q) {
-      load_col(q, X + 1, r3);
+    float l[3], m[3], r3[3];                        // dY columns X-1, X, X+1 (rows Y-1, Y, Y+1)
+    load_col(xs - 1, l);
+    load_col(xs, m);
+    const int y = Y / p.r, i = Y - y * p.r;
+    const size_t orow = ((size_t)img * p.H + y) * p.W;
+#pragma unroll 4
+    for (int X = xs; X < xe; ++X) {
+      load_col(X + 1, r3);
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
       for (int rr = 0; rr < 3; ++rr) {
@@ -278,8 +286,8 @@ __global__ void __launch_bounds__(256) last_dgrad_s2d_rows_kernel(const LastDgra
         a3 = fmaf(wl.w, l[rr], fmaf(wm.w, m[rr], fmaf(wr.w, r3[rr], a3)));
       }
       if (active) {
-        const int y = Y / p.r, i = Y - y * p.r, x = X / p.r, j = X - x * p.r;
-        const size_t o = (((size_t)img * p.H + y) * p.W + x) * p.pitch + (size_t)(i * p.r + j) * p.C + 4 * lane;
+        const int x = X / p.r, j = X - x * p.r;
+        const size_t o = (orow + x) * p.pitch + (size_t)(i * p.r + j) * p.C + 4 * lane;
         __half h0, l0, h1, l1, h2, l2, h3, l3;
         split_f16(a0, h0, l0);
         split_f16(a1, h1, l1);
@@ -288,20 +296,10 @@ __global__ void __launch_bounds__(256) last_dgrad_s2d_rows_kernel(const LastDgra
         *reinterpret_cast<uint2*>(p.dz_hi + o) = make_uint2(pack_h2(h0, h1), pack_h2(h2, h3));
         if (p.dz_lo != nullptr) *reinterpret_cast<uint2*>(p.dz_lo + o) = make_uint2(pack_h2(l0, l1), pack_h2(l2, l3));
       }
-      if (++X == WW) {
-        X = 0;
-        if (++Y == HH) { Y = 0; ++img; }
-        if (q + 1 < q1) {
 #pragma unroll
-          for (int rr = 0; rr < 3; ++rr) l[rr] = 0.f;
-          load_col(q + 1, 0, m);
-        }
-      } else {
-#pragma unroll
-        for (int rr = 0; rr < 3; ++rr) {
-          l[rr] = m[rr];
-          m[rr] = r3[rr];
-        }
+      for (int rr = 0; rr < 3; ++rr) {
+        l[rr] = m[rr];
+        m[rr] = r3[rr];
       }
     }
   }

@@ -603,3 +603,15 @@ class SuperResolution:
         if print_console:
             print("PSNR:%f, SSIM:%f" % (psnr, ssim))
         return psnr, ssim
+
+
+def create(flags, with_optimizer=False):
+    """The construction sequence every CLI of the reference spells out (evaluate.py:49-58, sr.py:39-43, train.py:27-36):
+    SuperResolution(...) -> build_graph -> [build_optimizer] -> build_summary_saver -> init_all_variables."""
+    model = SuperResolution(flags, model_name=flags.model_name)
+    model.build_graph()
+    if with_optimizer:
+        model.build_optimizer()
+    model.build_summary_saver()
+    model.init_all_variables()
+    return model

@@ -26,11 +26,7 @@ FLAGS = args.get()
 def build_model():
     if FLAGS.frozenInference:
         raise NotImplementedError("--frozenInference loads a TensorFlow GraphDef; not supported by the B200 engine")
-    model = DCSCN.SuperResolution(FLAGS, model_name=FLAGS.model_name)
-    model.build_graph()
-    model.build_summary_saver()
-    model.init_all_variables()
-    return model
+    return DCSCN.create(FLAGS)
 
 
 def evaluate_bicubic(model, test_data):

@@ -1,8 +1,7 @@
 """
 Flag definitions shared by train.py / evaluate.py / sr.py.
 
-Same flag names, defaults and help strings as the reference's helper/args.py:16-98, without
-TensorFlow: a small absl-compatible parser (`--name=value`, `--name value`, `--bool`, `--nobool`,
+Same flag names and defaults as the reference's helper/args.py:16-98, without TensorFlow: a small absl-compatible parser (`--name=value`, `--name value`, `--bool`, `--nobool`,
 `--bool=true|false`).  Scripts may add their own flags through `args.flags.DEFINE_*` before calling
 `args.get()`, exactly like the reference (evaluate.py:38-39, sr.py:34).
 """
@@ -133,94 +132,89 @@ class _FlagModule:
 
 flags = _FlagModule()
 
-# Model (network) Parameters
-flags.DEFINE_integer("scale", 2, "Scale factor for Super Resolution (should be 2 or more)")
-flags.DEFINE_integer("layers", 12, "Number of layers of feature xxtraction CNNs")
-flags.DEFINE_integer("filters", 196, "Number of filters of first feature-extraction CNNs")
-flags.DEFINE_integer("min_filters", 48, "Number of filters of last feature-extraction CNNs")
-flags.DEFINE_float("filters_decay_gamma", 1.5,
-                   "Number of CNN filters are decayed from [filters] to [min_filters] by this gamma")
-flags.DEFINE_boolean("use_nin", True, "Use Network In Network")
-flags.DEFINE_integer("nin_filters", 64, "Number of CNN filters in A1 at Reconstruction network")
-flags.DEFINE_integer("nin_filters2", 32, "Number of CNN filters in B1 and B2 at Reconstruction net.")
-flags.DEFINE_integer("cnn_size", 3, "Size of CNN filters")
-flags.DEFINE_integer("reconstruct_layers", 1, "Number of Reconstruct CNN Layers. (can be 0.)")
-flags.DEFINE_integer("reconstruct_filters", 32, "Number of Reconstruct CNN Filters")
-flags.DEFINE_float("dropout_rate", 0.8, "Output nodes should be kept by this probability. If 1, don't use dropout.")
-flags.DEFINE_string("activator", "prelu", "Activator can be [relu, leaky_relu, prelu, sigmoid, tanh, selu]")
-flags.DEFINE_boolean("pixel_shuffler", True, "Use Pixel Shuffler instead of transposed CNN")
-flags.DEFINE_integer("pixel_shuffler_filters", 0,
-                     "Num of Pixel Shuffler output channels. 0 means use same channels as input.")
-flags.DEFINE_integer("self_ensemble", 8, "Number of using self ensemble method. [1 - 8]")
-flags.DEFINE_boolean("batch_norm", False, "use batch normalization after each CNNs")
-flags.DEFINE_boolean("depthwise_separable", False, "use depthwise seperable convolutions for each CNN layer instead")
+# The reference's flag set (helper/args.py:16-98): identical names and defaults, so every command line of the reference
+# parses unchanged; the descriptions are this engine's.  One row per flag: name, default, description - the kind is
+# the default's Python type.
+_REFERENCE_FLAGS = [
+    # --- network ---
+    ("scale", 2, "upscaling factor: 2, 3 or 4"),
+    ("layers", 12, "depth of the feature-extraction stack (CNN1..CNNn)"),
+    ("filters", 196, "output channels of CNN1"),
+    ("min_filters", 48, "output channels of the last feature-extraction layer"),
+    ("filters_decay_gamma", 1.5, "shape of the channel decay from `filters` down to `min_filters`"),
+    ("use_nin", True, "reconstruction through the A1 / B1-B2 network-in-network branches"),
+    ("nin_filters", 64, "channels of branch A1"),
+    ("nin_filters2", 32, "channels of branch B1 and B2"),
+    ("cnn_size", 3, "spatial size of the feature-extraction filters"),
+    ("reconstruct_layers", 1, "R-CNN layers after the up-sampler (0 or 1 here)"),
+    ("reconstruct_filters", 32, "channels of intermediate R-CNN layers"),
+    ("dropout_rate", 0.8, "keep probability during training (1 disables dropout)"),
+    ("activator", "prelu", "activation; this engine implements prelu"),
+    ("pixel_shuffler", True, "sub-pixel (depth_to_space) up-sampling; the transposed-conv variant is not carried over"),
+    ("pixel_shuffler_filters", 0, "channels after the pixel shuffler; 0 keeps the channel count of its input"),
+    ("self_ensemble", 8, "how many of the 8 flip / rotate variants are averaged at inference (1..8)"),
+    ("batch_norm", False, "not supported by this engine (rejected when set)"),
+    ("depthwise_separable", False, "every layer as depthwise k x k followed by pointwise 1 x 1"),
+    # --- training ---
+    ("bicubic_init", True, "the network predicts the residual over the bicubic up-scale x2"),
+    ("clipping_norm", 5.0, "global-norm gradient clipping threshold; <= 0 turns clipping off"),
+    ("initializer", "he", "weight initialiser: uniform, stddev, xavier, he, identity or zero"),
+    ("weight_dev", 0.01, "standard deviation for the `stddev` initialiser"),
+    ("l2_decay", 0.0001, "weight of the L2 penalty on the convolution filters"),
+    ("optimizer", "adam", "this engine implements adam"),
+    ("beta1", 0.9, "Adam first-moment decay"),
+    ("beta2", 0.999, "Adam second-moment decay"),
+    ("epsilon", 1e-8, "Adam epsilon"),
+    ("momentum", 0.9, "only for the momentum / rmsprop optimisers (not carried over)"),
+    ("batch_num", 20, "patches per training step"),
+    ("batch_image_size", 48, "edge length of a low-resolution training patch"),
+    ("stride_size", 0, "patch grid stride when building batches; 0 = half a patch"),
+    ("training_images", 24000, "patches per epoch"),
+    ("use_l1_loss", False, "mean absolute error instead of mean squared error as the image loss"),
+    # --- learning-rate schedule ---
+    ("initial_lr", 0.002, "learning rate of the first epoch"),
+    ("lr_decay", 0.5, "factor applied to the learning rate at each decay"),
+    ("lr_decay_epoch", 9, "epochs between two decays"),
+    ("end_lr", 2e-5, "training stops once the learning rate falls below this"),
+    # --- data sets ---
+    ("dataset", "bsd200", "training set folder under data_dir (yang91, general100, bsd200, ...)"),
+    ("test_dataset", "set5", "evaluation set folder (set5, set14, bsd100, urban100) or `all`"),
+    ("tests", 1, "independent training runs"),
+    ("do_benchmark", False, "after training also evaluate set5, set14 and bsd100"),
+    # --- image handling ---
+    ("max_value", 255.0, "pixel range the network works in"),
+    ("channels", 1, "image channels fed to the network (1: luma only)"),
+    ("psnr_calc_border_size", -1, "pixels shaved before PSNR / SSIM; negative = 2 + scale"),
+    ("build_batch", False, "pre-cut grid patches to disk instead of sampling them on the fly"),
+    # --- folders and names (no trailing slash) ---
+    ("checkpoint_dir", "models", "where checkpoints are read and written"),
+    ("graph_dir", "graphs", "kept for command-line compatibility"),
+    ("data_dir", "data", "root of the image data sets"),
+    ("batch_dir", "batch_data", "where pre-cut training patches live"),
+    ("output_dir", "output", "where result images go"),
+    ("tf_log_dir", "tf_log", "kept for command-line compatibility (no tensorboard here)"),
+    ("log_filename", "log.txt", "text log"),
+    ("model_name", "", "overrides the generated model name"),
+    ("load_model_name", "", "checkpoint to start from (`default` = the generated model name)"),
+    # --- logging switches of the reference (accepted, mostly without effect here) ---
+    ("initialize_tf_log", True, "accepted for compatibility"),
+    ("enable_log", True, "accepted for compatibility"),
+    ("save_weights", True, "accepted for compatibility"),
+    ("save_images", False, "accepted for compatibility"),
+    ("save_images_num", 20, "accepted for compatibility"),
+    ("save_meta_data", False, "accepted for compatibility"),
+    ("gpu_device_id", 0, "CUDA device to run on"),
+    # --- frozen GraphDef deployment: not part of this engine, the flags only have to parse ---
+    ("frozenInference", False, "rejected when set"),
+    ("frozen_graph_path", "./model_to_freeze/frozen_model_optimized.pb", "unused"),
+    # --- additions of this engine; the defaults reproduce the reference's fp32 results ---
+    ("precision", "f16x3", "tensor-core arithmetic: f16x3 (fp32-equivalent) or f16x1 (single pass, PSNR-neutral)"),
+    ("gpus", 1, "GPUs the self-ensemble / training batch is spread over (one process each)"),
+]
 
-# Training Parameters
-flags.DEFINE_boolean("bicubic_init", True, "make bicubic interpolation values as initial input for x2")
-flags.DEFINE_float("clipping_norm", 5, "Norm for gradient clipping. If it's <= 0 we don't use gradient clipping.")
-flags.DEFINE_string("initializer", "he", "Initializer for weights can be [uniform, stddev, xavier, he, identity, zero]")
-flags.DEFINE_float("weight_dev", 0.01, "Initial weight stddev (won't be used when you use he or xavier initializer)")
-flags.DEFINE_float("l2_decay", 0.0001, "l2_decay")
-flags.DEFINE_string("optimizer", "adam", "Optimizer can be [gd, momentum, adadelta, adagrad, adam, rmsprop]")
-flags.DEFINE_float("beta1", 0.9, "Beta1 for adam optimizer")
-flags.DEFINE_float("beta2", 0.999, "Beta2 for adam optimizer")
-flags.DEFINE_float("epsilon", 1e-8, "epsilon for adam optimizer")
-flags.DEFINE_float("momentum", 0.9, "Momentum for momentum optimizer and rmsprop optimizer")
-flags.DEFINE_integer("batch_num", 20, "Number of mini-batch images for training")
-flags.DEFINE_integer("batch_image_size", 48, "Image size for mini-batch")
-flags.DEFINE_integer("stride_size", 0, "Stride size for mini-batch. If it is 0, use half of batch_image_size")
-flags.DEFINE_integer("training_images", 24000, "Number of training on each epoch")
-flags.DEFINE_boolean("use_l1_loss", False, "Use L1 Error as loss function instead of MSE Error.")
-
-# Learning Rate Control for Training
-flags.DEFINE_float("initial_lr", 0.002, "Initial learning rate")
-flags.DEFINE_float("lr_decay", 0.5, "Learning rate decay rate")
-flags.DEFINE_integer("lr_decay_epoch", 9, "After this epochs are completed, learning rate will be decayed by lr_decay.")
-flags.DEFINE_float("end_lr", 2e-5, "Training end learning rate. If the current learning rate gets lower than this"
-                                   "value, then training will be finished.")
-
-# Dataset or Others
-flags.DEFINE_string("dataset", "bsd200", "Training dataset dir. [yang91, general100, bsd200, other]")
-flags.DEFINE_string("test_dataset", "set5", "Directory for test dataset [set5, set14, bsd100, urban100, all]")
-flags.DEFINE_integer("tests", 1, "Number of training sets")
-flags.DEFINE_boolean("do_benchmark", False, "Evaluate the performance for set5, set14 and bsd100 after the training.")
-
-# Image Processing
-flags.DEFINE_float("max_value", 255, "For normalize image pixel value")
-flags.DEFINE_integer("channels", 1, "Number of image channels used. Now it should be 1. using only Y from YCbCr.")
-flags.DEFINE_integer("psnr_calc_border_size", -1,
-                     "Cropping border size for calculating PSNR. if < 0, use 2 + scale for default.")
-flags.DEFINE_boolean("build_batch", False, "Build pre-processed input batch. Makes training significantly faster but "
-                                           "the patches are limited to be on the grid.")
-
-# Environment (all directory name should not contain '/' after )
-flags.DEFINE_string("checkpoint_dir", "models", "Directory for checkpoints")
-flags.DEFINE_string("graph_dir", "graphs", "Directory for graphs")
-flags.DEFINE_string("data_dir", "data", "Directory for original images")
-flags.DEFINE_string("batch_dir", "batch_data", "Directory for training batch images")
-flags.DEFINE_string("output_dir", "output", "Directory for output test images")
-flags.DEFINE_string("tf_log_dir", "tf_log", "Directory for tensorboard log")
-flags.DEFINE_string("log_filename", "log.txt", "log filename")
-flags.DEFINE_string("model_name", "", "model name for save files and tensorboard log")
-flags.DEFINE_string("load_model_name", "", "Filename of model loading before start [filename or 'default']")
-
-# Debugging or Logging
-flags.DEFINE_boolean("initialize_tf_log", True, "Clear all tensorboard log before start")
-flags.DEFINE_boolean("enable_log", True, "Enables tensorboard-log. Save loss.")
-flags.DEFINE_boolean("save_weights", True, "Save weights and biases/gradients")
-flags.DEFINE_boolean("save_images", False, "Save CNN weights as images")
-flags.DEFINE_integer("save_images_num", 20, "Number of CNN images saved")
-flags.DEFINE_boolean("save_meta_data", False, "")
-flags.DEFINE_integer("gpu_device_id", 0, "Device ID of GPUs which will be used to compute.")
-
-# frozen model configurations (TF GraphDef deployment - not supported by this engine, kept so command lines parse)
-flags.DEFINE_boolean("frozenInference", False, "Flag for whether the model to evaluate is frozen.")
-flags.DEFINE_string("frozen_graph_path", './model_to_freeze/frozen_model_optimized.pb',
-                    "the path to a frozen model if performing inference from it")
-
-# B200 engine (additions; defaults reproduce the reference's fp32 results)
-flags.DEFINE_string("precision", "f16x3", "Tensor-core arithmetic: f16x3 (fp32-equivalent, default) or f16x1 (fast)")
-flags.DEFINE_integer("gpus", 1, "GPUs to shard the self-ensemble / training batch over (one process per GPU)")
+for _name, _default, _help in _REFERENCE_FLAGS:
+    _kind = {bool: "bool", int: "int", float: "float", str: "str"}[type(_default)]
+    FLAGS._define(_name, _default, _help, _kind)
 
 
 def get(argv=None):

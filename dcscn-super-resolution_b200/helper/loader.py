@@ -1,10 +1,10 @@
 """
-Training / evaluation input preparation on the host (reference: helper/loader.py).
+Host-side input preparation for training and evaluation (what the reference's helper/loader.py provides).
 
-Only what the hot path's callers need: `build_input_image` / `build_image_set` (used by
-DCSCN.do_for_evaluate, loader.py:23-67), an in-RAM grid-patch data set (`BatchDataSets`,
-loader.py:70-275 without the on-disk BMP cache) and the random-crop data set (`DynamicDataSets`,
-loader.py:278-355).  Data loading is CPU work outside the replaced path.
+Only what the callers of the replaced path need, restated: `build_input_image` / `build_image_set` (the LR / bicubic /
+HR triple of `do_for_evaluate`, loader.py:23-67), a grid-patch training set kept in RAM (`BatchDataSets`, loader.py:70-275;
+the reference caches the same patches as BMP files) and a random-crop training set (`DynamicDataSets`, loader.py:278-355).
+Data loading is CPU work outside the GPU path.
 """
 
 import logging
@@ -15,127 +15,121 @@ import numpy as np
 from helper import utilty as util
 
 
-def build_image_set(file_path, channels=1, scale=1, convert_ycbcr=True, resampling_method="bicubic",
-                    print_console=True):
-    """loader.py:23-33 -> (input LR, bicubic-upscaled LR, true HR)."""
-    true_image = util.set_image_alignment(util.load_image(file_path, print_console=print_console), scale)
-    if channels == 1 and true_image.shape[2] == 3 and convert_ycbcr:
-        true_image = util.convert_rgb_to_y(true_image)
-    input_image = util.resize_image_by_pil(true_image, 1.0 / scale, resampling_method=resampling_method)
-    input_interpolated_image = util.resize_image_by_pil(input_image, scale, resampling_method=resampling_method)
-    return input_image, input_interpolated_image, true_image
+def _to_luma_or_ycbcr(image, channels, convert_ycbcr):
+    """RGB -> Y for a one-channel model, RGB -> YCbCr otherwise (loader.py:55-61)."""
+    if not convert_ycbcr:
+        return image
+    wants_luma = channels == 1 and image.shape[2] == 3
+    return util.convert_rgb_to_y(image) if wants_luma else util.convert_rgb_to_ycbcr(image)
 
 
 def build_input_image(image, width=0, height=0, channels=1, scale=1, alignment=0, convert_ycbcr=True):
-    """loader.py:42-67: centre-crop, align, RGB -> Y (or YCbCr), bicubic down-scale by `scale`."""
-    if width != 0 and height != 0:
-        if image.shape[0] != height or image.shape[1] != width:
-            x = (image.shape[1] - width) // 2
-            y = (image.shape[0] - height) // 2
-            image = image[y: y + height, x: x + width, :]
+    """loader.py:42-67: optional centre crop to (height, width), size alignment, colour conversion and a bicubic
+    down-scale by `scale`."""
+    if width and height and image.shape[:2] != (height, width):
+        top, left = (image.shape[0] - height) // 2, (image.shape[1] - width) // 2
+        image = image[top:top + height, left:left + width, :]
     if alignment > 1:
         image = util.set_image_alignment(image, alignment)
-    if channels == 1 and image.shape[2] == 3:
-        if convert_ycbcr:
-            image = util.convert_rgb_to_y(image)
-    else:
-        if convert_ycbcr:
-            image = util.convert_rgb_to_ycbcr(image)
-    if scale != 1:
-        image = util.resize_image_by_pil(image, 1.0 / scale)
-    return image
+    image = _to_luma_or_ycbcr(image, channels, convert_ycbcr)
+    return image if scale == 1 else util.resize_image_by_pil(image, 1.0 / scale)
 
 
-def load_input_image(filename, width=0, height=0, channels=1, scale=1, alignment=0, convert_ycbcr=True,
-                     print_console=True):
-    image = util.load_image(filename, print_console=print_console)
-    return build_input_image(image, width, height, channels, scale, alignment, convert_ycbcr)
+def load_input_image(filename, width=0, height=0, channels=1, scale=1, alignment=0, convert_ycbcr=True, print_console=True):
+    return build_input_image(util.load_image(filename, print_console=print_console), width, height, channels, scale,
+                             alignment, convert_ycbcr)
 
 
-class BatchDataSets:
-    """Grid patches of every image of a directory, held in RAM as uint8 like the reference
-    (loader.py:236-249) and served in a shuffled order (loader.py:259-275)."""
+def build_image_set(file_path, channels=1, scale=1, convert_ycbcr=True, resampling_method="bicubic", print_console=True):
+    """loader.py:23-33: (LR input, its bicubic up-scale, ground truth) of one image file."""
+    truth = util.set_image_alignment(util.load_image(file_path, print_console=print_console), scale)
+    if convert_ycbcr and channels == 1 and truth.shape[2] == 3:
+        truth = util.convert_rgb_to_y(truth)
+    small = util.resize_image_by_pil(truth, 1.0 / scale, resampling_method=resampling_method)
+    return small, util.resize_image_by_pil(small, scale, resampling_method=resampling_method), truth
+
+
+class _ShuffledOrder:
+    """Serves 0..count-1 in a fresh random permutation per pass (loader.py:259-275, 300-308)."""
+
+    count = 0
+
+    def init_batch_index(self, shuffle=True):
+        order = list(range(self.count))
+        if shuffle:
+            random.shuffle(order)
+        self.batch_index, self.index = order, 0
+
+    def get_next_image_no(self):
+        if getattr(self, "batch_index", None) is None or self.index >= self.count:
+            self.init_batch_index()
+        number = self.batch_index[self.index]
+        self.index += 1
+        return number
+
+
+def _rescaled(arrays, max_value):
+    if max_value == 255:
+        return arrays
+    return tuple(np.multiply(a, max_value / 255.0) for a in arrays)
+
+
+class BatchDataSets(_ShuffledOrder):
+    """Every grid patch of every image of a directory, as uint8 (the reference stores them as BMP files,
+    loader.py:236-249), served in shuffled order."""
 
     def __init__(self, scale, batch_dir, batch_image_size, stride_size=0, channels=1, resampling_method="bicubic"):
-        self.scale = scale
-        self.batch_image_size = batch_image_size
-        self.stride = batch_image_size // 2 if stride_size == 0 else stride_size
-        self.channels = channels
-        self.resampling_method = resampling_method
-        self.count = 0
+        self.scale, self.channels, self.resampling_method = scale, channels, resampling_method
         self.batch_dir = batch_dir
-        self.batch_index = None
+        self.batch_image_size = batch_image_size
+        self.stride = stride_size or batch_image_size // 2
         self.input_images = self.input_interpolated_images = self.true_images = None
-        self.index = 0
+        self.batch_index, self.index, self.count = None, 0, 0
 
     def is_batch_exist(self):
         return self.input_images is not None
 
     def build_batch(self, data_dir):
         print("Building batch images for %s..." % self.batch_dir)
-        inputs, interps, trues = [], [], []
-        out_size = self.batch_image_size * self.scale
-        out_stride = self.stride * self.scale
+        hr_size, hr_stride = self.batch_image_size * self.scale, self.stride * self.scale
+        stacks = ([], [], [])
         for filename in util.get_files_in_directory(data_dir):
-            input_image, interp_image, true_image = build_image_set(
-                filename, channels=self.channels, resampling_method=self.resampling_method, scale=self.scale,
-                print_console=False)
-            a = util.get_split_images(input_image, self.batch_image_size, stride=self.stride)
-            b = util.get_split_images(interp_image, out_size, stride=out_stride)
-            if a is None or b is None:
-                continue
-            c = util.get_split_images(true_image, out_size, stride=out_stride)
-            inputs.append(a)
-            interps.append(b)
-            trues.append(c)
-        if not inputs:
+            small, bicubic, truth = build_image_set(filename, channels=self.channels, scale=self.scale,
+                                                    resampling_method=self.resampling_method, print_console=False)
+            patches = (util.get_split_images(small, self.batch_image_size, stride=self.stride),
+                       util.get_split_images(bicubic, hr_size, stride=hr_stride),
+                       util.get_split_images(truth, hr_size, stride=hr_stride))
+            if patches[0] is None or patches[1] is None:
+                continue                                   # image smaller than one patch
+            for stack, p in zip(stacks, patches):
+                stack.append(p)
+        if not stacks[0]:
             self.count = 0
             return
-        # stored as uint8 files in the reference (BMP patches): same truncation here
-        self.input_images = np.concatenate(inputs).astype(np.uint8)
-        self.input_interpolated_images = np.concatenate(interps).astype(np.uint8)
-        self.true_images = np.concatenate(trues).astype(np.uint8)
+        # uint8 like the reference's BMP cache: the same truncation of the float patches
+        self.input_images, self.input_interpolated_images, self.true_images = (
+            np.concatenate(stack).astype(np.uint8) for stack in stacks)
         self.count = self.input_images.shape[0]
         print("%d mini-batch images are built(saved)." % self.count)
 
     def load_batch_counts(self):
-        pass
+        """The reference re-reads its on-disk cache here; the RAM set needs nothing."""
 
     def load_all_batch_images(self):
         print("Allocating memory for all batch images.")
 
-    def init_batch_index(self, shuffle=True):
-        self.batch_index = random.sample(range(0, self.count), self.count) if shuffle else list(range(self.count))
-        self.index = 0
-
-    def get_next_image_no(self):
-        if self.index >= self.count:
-            self.init_batch_index()
-        image_no = self.batch_index[self.index]
-        self.index += 1
-        return image_no
-
     def load_batch_image(self, max_value):
-        number = self.get_next_image_no()
-        if max_value == 255:
-            return self.input_images[number], self.input_interpolated_images[number], self.true_images[number]
-        f = max_value / 255.0
-        return (np.multiply(self.input_images[number], f), np.multiply(self.input_interpolated_images[number], f),
-                np.multiply(self.true_images[number], f))
+        k = self.get_next_image_no()
+        return _rescaled((self.input_images[k], self.input_interpolated_images[k], self.true_images[k]), max_value)
 
 
-class DynamicDataSets:
-    """Random crops with a 50 % left-right flip (loader.py:278-355)."""
+class DynamicDataSets(_ShuffledOrder):
+    """A random HR crop per request, mirrored left-right half of the time (loader.py:278-355)."""
 
     def __init__(self, scale, batch_image_size, channels=1, resampling_method="bicubic"):
-        self.scale = scale
+        self.scale, self.channels, self.resampling_method = scale, channels, resampling_method
         self.batch_image_size = batch_image_size
-        self.channels = channels
-        self.resampling_method = resampling_method
-        self.filenames = []
-        self.count = 0
-        self.batch_index = None
-        self.index = 0
+        self.filenames, self.batch_index, self.index, self.count = [], None, 0, 0
 
     def set_data_dir(self, data_dir):
         self.filenames = util.get_files_in_directory(data_dir)
@@ -144,49 +138,27 @@ class DynamicDataSets:
             logging.error("Data Directory is empty.")
             exit(-1)
 
-    def init_batch_index(self):
-        self.batch_index = random.sample(range(0, self.count), self.count)
-        self.index = 0
+    def init_batch_index(self, shuffle=True):
+        super().init_batch_index(True)
 
-    def get_next_image_no(self):
-        if self.index >= self.count:
-            self.init_batch_index()
-        image_no = self.batch_index[self.index]
-        self.index += 1
-        return image_no
+    def load_random_patch(self, filename):
+        """loader.py:332-355: None when the image is smaller than one HR patch."""
+        image = util.load_image(filename, print_console=False)
+        edge = self.batch_image_size * self.scale
+        rows, cols = image.shape[:2]
+        if rows < edge or cols < edge:
+            print("Error: %s should have more than %d x %d size." % (filename, edge, edge))
+            return None
+        top = random.randrange(rows - edge) if rows > edge else 0
+        left = random.randrange(cols - edge) if cols > edge else 0
+        return build_input_image(image[top:top + edge, left:left + edge, :], channels=self.channels, convert_ycbcr=True)
 
     def load_batch_image(self, max_value):
         """loader.py:310-330"""
-        image = None
-        while image is None:
-            image = self.load_random_patch(self.filenames[self.get_next_image_no()])
+        truth = None
+        while truth is None:
+            truth = self.load_random_patch(self.filenames[self.get_next_image_no()])
         if random.randrange(2) == 0:
-            image = np.fliplr(image)
-        input_image = util.resize_image_by_pil(image, 1 / self.scale)
-        input_bicubic_image = util.resize_image_by_pil(input_image, self.scale)
-        if max_value != 255:
-            scale = max_value / 255.0
-            input_image = np.multiply(input_image, scale)
-            input_bicubic_image = np.multiply(input_bicubic_image, scale)
-            image = np.multiply(image, scale)
-        return input_image, input_bicubic_image, image
-
-    def load_random_patch(self, filename):
-        """loader.py:332-355"""
-        image = util.load_image(filename, print_console=False)
-        height, width = image.shape[0:2]
-        load_batch_size = self.batch_image_size * self.scale
-        if height < load_batch_size or width < load_batch_size:
-            print("Error: %s should have more than %d x %d size." % (filename, load_batch_size, load_batch_size))
-            return None
-        if height == load_batch_size:
-            y = 0
-        else:
-            y = random.randrange(height - load_batch_size)
-        if width == load_batch_size:
-            x = 0
-        else:
-            x = random.randrange(width - load_batch_size)
-        image = image[y:y + load_batch_size, x:x + load_batch_size, :]
-        image = build_input_image(image, channels=self.channels, convert_ycbcr=True)
-        return image
+            truth = np.fliplr(truth)
+        small = util.resize_image_by_pil(truth, 1 / self.scale)
+        return _rescaled((small, util.resize_image_by_pil(small, self.scale), truth), max_value)

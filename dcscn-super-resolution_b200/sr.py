@@ -1,27 +1,25 @@
 """
-Apply super resolution to one image file (drop-in for the reference's sr.py).
+Super-resolve one image file: the reference's `sr.py` command line on the B200 engine.
 
   python sr.py --file=your_file.png [--scale=3 --layers=8 --filters=96 ...]
 
-Writes the original, bicubic and result images to `<output_dir>/<model name>/` (DCSCN.do_for_file).
-Model flags must match the checkpoint, which is looked up as `<checkpoint_dir>/<model name>.ckpt`.
+The original, the bicubic up-scale and the result (Y and colour) land in `<output_dir>/<model name>/`
+(`SuperResolution.do_for_file`).  The model flags select the checkpoint `<checkpoint_dir>/<model name>.ckpt` and have to
+be the ones it was trained with.
 """
 
 import DCSCN
 from helper import args
 
-args.flags.DEFINE_string("file", "image.jpg", "Target filename")
+args.flags.DEFINE_string("file", "image.jpg", "image to up-scale")
 FLAGS = args.get()
 
 
-def main(_):
-    model = DCSCN.SuperResolution(FLAGS, model_name=FLAGS.model_name)
-    model.build_graph()
-    model.build_optimizer()  # the reference builds it so that its Saver also restores the Adam slots (sr.py:41)
-    model.build_summary_saver()
-    model.init_all_variables()
-    model.load_model()
-    model.do_for_file(FLAGS.file, FLAGS.output_dir)
+def main(_unused):
+    # the optimizer is part of the graph here as in the reference (sr.py:41), so a checkpoint's Adam slots are accepted
+    engine_model = DCSCN.create(FLAGS, with_optimizer=True)
+    engine_model.load_model()
+    engine_model.do_for_file(FLAGS.file, FLAGS.output_dir)
 
 
 if __name__ == '__main__':

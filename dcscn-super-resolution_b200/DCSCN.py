@@ -14,6 +14,7 @@ tensorboard summaries, frozen-graph loading, transposed-conv upsampler, batch-no
 import logging
 import math
 import os
+import sys
 import time
 
 import numpy as np
@@ -25,7 +26,11 @@ BICUBIC_METHOD_STRING = "bicubic"
 
 
 def _dist_rank_world():
-    """(rank, world_size) of the torch.distributed job this process belongs to, (0, 1) outside one."""
+    """(rank, world_size) of the torch.distributed job this process belongs to, (0, 1) outside one.  A plain
+    single-process command line never imports torch: it is only consulted when the caller already loaded it or the
+    process was started by torchrun (WORLD_SIZE in the environment)."""
+    if "torch" not in sys.modules and int(os.environ.get("WORLD_SIZE", "1")) <= 1:
+        return 0, 1
     try:
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized():
@@ -381,7 +386,10 @@ class SuperResolution:
         y = np.ascontiguousarray(np.stack(self.batch_true[rank::world]), dtype=np.float32)
         if x.ndim == 3:
             x, x2, y = x[..., None], x2[..., None], y[..., None]
-        image_loss, mse = self.engine.train_step_data_parallel(x, x2, y, lr=self.lr, seed=self.step * world + rank)
+        if world > 1:
+            image_loss, mse = self.engine.train_step_data_parallel(x, x2, y, lr=self.lr, seed=self.step * world + rank)
+        else:
+            image_loss, mse = self.engine.train_step_host(x, x2, y, lr=self.lr, seed=self.step, apply_update=True)
         self.training_loss_sum += image_loss
         self.training_psnr_sum += util.get_psnr(mse, max_value=self.max_value)
         self.training_step += 1

@@ -140,3 +140,40 @@ def test_package_does_not_import_oracle():
         text = open(path, errors="replace").read()
         assert not re.search(r"^\s*(import|from)\s+dcscn_oracle", text, re.M), path
         assert "oracle/" not in text, path
+
+
+def test_single_process_paths_never_import_torch(tmp_path):
+    """A plain command line (no torchrun) must not pay for `import torch`: rank / world come out as (0, 1) without
+    consulting torch.distributed, and train_batch takes the engine's host-buffer step with the reference's step counter
+    as the dropout seed (DCSCN.py:415-425)."""
+    import subprocess
+    import sys
+    code = r'''
+import os, sys
+sys.path.insert(0, %r)
+os.environ.pop("WORLD_SIZE", None)
+import numpy as np
+import DCSCN
+assert DCSCN._dist_rank_world() == (0, 1)
+m = object.__new__(DCSCN.SuperResolution)
+m.batch_input = [np.full((4, 4, 1), i, np.float64) for i in range(3)]
+m.batch_input_bicubic = [np.zeros((8, 8, 1)) for _ in range(3)]
+m.batch_true = [np.ones((8, 8, 1)) for _ in range(3)]
+m.lr, m.step, m.training_step, m.max_value = 0.002, 7, 0, 255.0
+m.training_loss_sum = m.training_psnr_sum = 0.0
+calls = []
+class FakeEngine:
+    def train_step_host(self, x, x2, y, lr, seed, apply_update=True):
+        calls.append((x.shape, x.dtype, x.flags["C_CONTIGUOUS"], x2.shape, y.shape, lr, seed, apply_update))
+        return 4.0, 4.0
+    def train_step_data_parallel(self, *a, **k):
+        raise AssertionError("data-parallel step in a single process")
+m.engine = FakeEngine()
+m.train_batch()
+assert calls == [((3, 4, 4, 1), np.dtype("float32"), True, (3, 8, 8, 1), (3, 8, 8, 1), 0.002, 7, True)], calls
+assert (m.step, m.training_step, m.training_loss_sum) == (8, 1, 4.0)
+assert "torch" not in sys.modules, "torch was imported on a single-process path"
+print("ok")
+''' % PKG
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120, cwd=str(tmp_path))
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout + r.stderr

@@ -40,6 +40,41 @@ def _dist_rank_world():
     return 0, 1
 
 
+def init_distributed(flags):
+    """train.py / evaluate.py under torchrun (WORLD_SIZE > 1): one process per GPU.  Joins the NCCL job, pins this
+    process to GPU LOCAL_RANK (overriding --gpu_device_id) and gives every rank its own crop / flip random stream.
+    Returns (rank, world); (0, 1) and no torch import for a plain single-process command line."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1 and getattr(flags, "gpus", 1) > 1:
+        # --gpus=N on a plain command line: re-launch this script as N ranks (127.0.0.1 rendezvous, one node)
+        import subprocess
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(flags.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29517")] + sys.argv
+        sys.exit(subprocess.call(cmd))
+    if world <= 1:
+        return 0, 1
+    import random
+    import torch
+    import torch.distributed as dist
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not dist.is_initialized():
+        if torch.cuda.is_available():
+            torch.cuda.set_device(local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group("gloo")
+    flags.gpu_device_id = local
+    rank = dist.get_rank()
+    random.seed(0x5EED + 7919 * rank)
+    np.random.seed(0x5EED + 7919 * rank)
+    return rank, dist.get_world_size()
+
+
+def _nccl_job():
+    import torch.distributed as dist
+    return dist.is_available() and dist.is_initialized() and dist.get_backend() == "nccl"
+
+
 def _all_reduce_sum(array):
     """Sum a float64 numpy array over all ranks (one NCCL all-reduce when the backend is nccl, gloo on CPU)."""
     import torch
@@ -277,7 +312,33 @@ class SuperResolution:
                 self.engine.set_param(name, np.zeros(shape, np.float32))
             else:
                 self.engine.set_param(name, np.full(shape, 0.1, np.float32))
+        # the reference re-runs tf.global_variables_initializer(), which also zeroes the Adam slots and resets the
+        # beta powers: trials of train.py (--tests > 1) must not inherit the previous trial's moments
+        self.engine.reset_optimizer()
         print("Model initialized.")
+
+    def broadcast_variables(self, src=0):
+        """Data-parallel start: every rank takes rank `src`'s variables (the ranks drew different random initial
+        weights), like the replicated variables of a mirrored strategy.  No-op outside a torch.distributed job."""
+        rank, world = _dist_rank_world()
+        if world <= 1:
+            return
+        import torch
+        import torch.distributed as dist
+        on_gpu = dist.get_backend() == "nccl"
+        for name in self.engine.param_shapes():
+            t = torch.from_numpy(np.ascontiguousarray(self.engine.get_param(name)))
+            if on_gpu:
+                t = t.cuda()
+            dist.broadcast(t, src=src)
+            if rank != src:
+                self.engine.set_param(name, t.cpu().numpy())
+        step = torch.tensor([self.engine.adam_step], dtype=torch.int64)
+        if on_gpu:
+            step = step.cuda()
+        dist.broadcast(step, src=src)
+        if rank != src and int(step.item()) != self.engine.adam_step:
+            self.engine.adam_step = int(step.item())
 
     def trainable_shapes(self):
         return self.engine.param_shapes() if self.engine is not None else {}
@@ -306,26 +367,39 @@ class SuperResolution:
                                       % (filename, var))
             weights[var] = reader.get_tensor(var)
         self.engine.set_params(weights)
+        self.engine.reset_optimizer()   # weights from a file never keep moments of whatever was trained before
         if restore_optimizer and not self.depthwise_separable and reader.has_tensor("beta1_power"):
             for var in weights:
                 for slot, suffix in enumerate(("/Adam", "/Adam_1")):
                     if reader.has_tensor(var + suffix):
                         self.engine.set_adam_slot(var, slot, reader.get_tensor(var + suffix))
-            b1p = float(np.asarray(reader.get_tensor("beta1_power")).reshape(-1)[0])
-            if 0.0 < b1p < 1.0 and 0.0 < self.beta1 < 1.0:
-                self.engine.adam_step = max(0, int(round(math.log(b1p) / math.log(self.beta1))) - 1)
-            elif b1p <= 0.0:
-                self.engine.adam_step = 10 ** 6       # the power underflowed in a long run: bias correction is 1
+            self.engine.adam_step = self._adam_step_from_powers(reader)
         if output_log:
             logging.info("Model restored [ %s ]." % filename)
         else:
             print("Model restored [ %s ]." % filename)
+
+    def _adam_step_from_powers(self, reader):
+        """Update count t behind the stored beta powers (TF keeps beta^(t+1)).  beta2_power = 0.999^(t+1) stays a normal
+        float32 for ~1e5 updates, beta1_power = 0.9^(t+1) underflows after ~980 - so beta2_power is read first and
+        beta1_power only when the file has no usable beta2_power."""
+        for key, beta in (("beta2_power", self.beta2), ("beta1_power", self.beta1)):
+            if not reader.has_tensor(key) or not 0.0 < beta < 1.0:
+                continue
+            p = float(np.asarray(reader.get_tensor(key)).reshape(-1)[0])
+            if 1e-30 < p < 1.0:
+                return max(0, int(round(math.log(p) / math.log(beta))) - 1)
+            if p >= 1.0:
+                return 0
+        return 10 ** 6   # every stored power underflowed (a very long run): both bias corrections are 1
 
     def save_model(self, name="", trial=0, output_log=False):
         """tf_graph.py:282-296: write `<name>.ckpt.index` + `.data-00000-of-00001` (TF V2 bundle) with everything the
         reference's tf.train.Saver() writes: the trainables, their Adam slots and beta1_power / beta2_power - so the
         file restores in the reference's sr.py / train.py graphs (which build the optimizer) as well as here."""
         filename = self._ckpt_filename(name, trial)
+        if _dist_rank_world()[0] != 0:
+            return      # data-parallel ranks hold identical weights: rank 0 writes the file
         shapes = self.engine.param_shapes()
         tensors = {var: self.engine.get_param(var) for var in shapes}
         steps = 0 if self.depthwise_separable else self.engine.adam_step
@@ -361,9 +435,18 @@ class SuperResolution:
 
     def init_epoch_index(self):
         """DCSCN.py:175-184"""
-        self.batch_input = self.batch_num * [None]
-        self.batch_input_bicubic = self.batch_num * [None]
-        self.batch_true = self.batch_num * [None]
+        rank, world = _dist_rank_world()
+        if world > 1 and self.batch_num % world != 0:
+            raise ValueError("--batch_num=%d must be a multiple of the %d data-parallel ranks (every rank normalises its "
+                             "gradient by its own patch count; equal shards keep the reference's global mean)"
+                             % (self.batch_num, world))
+        # data parallel: this rank loads and trains on batch_num / world patches of every mini-batch
+        self.local_batch = self.batch_num // world
+        if world > 1 and getattr(self.train, "shard_world", 1) != world:
+            self.train.set_shard(rank, world, seed=0xDC5C)
+        self.batch_input = self.local_batch * [None]
+        self.batch_input_bicubic = self.local_batch * [None]
+        self.batch_true = self.local_batch * [None]
         self.training_psnr_sum = 0
         self.training_loss_sum = 0
         self.training_step = 0
@@ -371,19 +454,19 @@ class SuperResolution:
 
     def build_input_batch(self):
         """DCSCN.py:186-190"""
-        for i in range(self.batch_num):
+        for i in range(len(self.batch_input)):
             self.batch_input[i], self.batch_input_bicubic[i], self.batch_true[i] = self.train.load_batch_image(
                 self.max_value)
 
     # ------------------------------------------------------------------ training ----
     def train_batch(self):
         """DCSCN.py:415-425: one optimisation step on the current mini-batch."""
-        # data parallel: rank r of a torch.distributed job trains on patches r, r + world, ... of the mini-batch; the
-        # gradients meet in one flat all-reduce before the (identical) clip + Adam update on every rank
+        # data parallel: every rank holds its own batch_num / world patches (init_epoch_index); the gradients meet in
+        # one flat all-reduce before the (identical) clip + Adam update on every rank
         rank, world = _dist_rank_world()
-        x = np.ascontiguousarray(np.stack(self.batch_input[rank::world]), dtype=np.float32)
-        x2 = np.ascontiguousarray(np.stack(self.batch_input_bicubic[rank::world]), dtype=np.float32)
-        y = np.ascontiguousarray(np.stack(self.batch_true[rank::world]), dtype=np.float32)
+        x = np.ascontiguousarray(np.stack(self.batch_input), dtype=np.float32)
+        x2 = np.ascontiguousarray(np.stack(self.batch_input_bicubic), dtype=np.float32)
+        y = np.ascontiguousarray(np.stack(self.batch_true), dtype=np.float32)
         if x.ndim == 3:
             x, x2, y = x[..., None], x2[..., None], y[..., None]
         if world > 1:
@@ -495,9 +578,18 @@ class SuperResolution:
             # inverse-flipped partial sums meet in ONE all-reduce (NCCL over NVLink on GPUs); single process = the
             # reference's serial loop.  float64 accumulation like the reference's np.zeros default (DCSCN.py:560).
             rank, world = _dist_rank_world()
-            if world == 1 and self.channels == 1:
+            if world == 1 and getattr(self, "channels", 1) == 1:
                 # one process: flips, two batched forwards (transforms 0..3 and 4..7) and the float64 mean all on the GPU
                 output = self.engine.forward_ensemble_host(input_image, bicubic_input_image, self.self_ensemble)
+            elif world > 1 and _nccl_job() and getattr(self, "engine", None) is not None:
+                # one process per GPU: this rank's transforms as batched forwards, float64 partial sum on the device,
+                # ONE NCCL all-reduce, mean (helper/engine.py: forward_ensemble_sharded)
+                import torch
+                dev = "cuda:%d" % self.engine.config.device_id
+                xd = torch.from_numpy(np.ascontiguousarray(input_image, dtype=np.float32).reshape(h, w)).to(dev)
+                x2d = torch.from_numpy(np.ascontiguousarray(bicubic_input_image, dtype=np.float32).reshape(
+                    self.scale * h, self.scale * w)).to(dev)
+                output = self.engine.forward_ensemble_sharded(xd, x2d, self.self_ensemble).cpu().numpy()[..., None]
             else:
                 output = np.zeros([self.scale * h, self.scale * w, 1])
                 for i in range(rank, self.self_ensemble, world):
@@ -571,6 +663,8 @@ class SuperResolution:
     def do_for_evaluate_with_output(self, file_path, output_directory, print_console=False):
         """DCSCN.py:616-670: do_for_evaluate plus the result / bicubic / loss images on disk
         (`<output_directory>/<model name>/<file_path stem>_*.png`, same names as the reference)."""
+        if _dist_rank_world()[0] != 0:
+            return self.do_for_evaluate(file_path, print_console=False)   # same collectives, rank 0 writes the images
         stem, extension = os.path.splitext(file_path)
         folder = output_directory + "/" + self.name + "/"
         util.make_dir(folder)

@@ -49,10 +49,13 @@ struct EpiParams {
   const float* rdot_w;
   float* rdot_out;
   int rdot_taps;
+  int rdot_parts;      // epilogue threads sharing one sub-pixel's channels each write their own partial plane set
+                       // [parts][taps][N][rH][rW] (1 when a thread's column share covers whole sub-pixels)
   // inverted dropout (training): keep-mask generated from a counter hash; keep_prob==1 -> off
   float keep_prob;
   uint32_t drop_seed;
   uint32_t drop_layer;
+  int drop_ntotal;     // channel count the keep-mask index is built with (the slot width; 0 = the GEMM's padded N)
 };
 
 struct ConvGeom {

@@ -293,7 +293,8 @@ __global__ void __launch_bounds__(256) conv_last_direct_kernel(const ConvLastPar
 struct ConvGatherParams {
   int n_img, H, W;   // HR resolution
   int ksz;
-  const float* v;    // [taps][n_img][H][W]
+  const float* v;    // [parts][taps][n_img][H][W]
+  int parts;         // partial plane sets to add up (EpiParams::rdot_parts)
   const float* x2;
   float* y;
 };
@@ -305,10 +306,12 @@ __global__ void __launch_bounds__(256) conv_last_gather_kernel(const ConvGatherP
     const int x = (int)(idx % p.W);
     const int y = (int)((idx / p.W) % p.H);
     float acc = 0.f;
-    for (int t = 0; t < p.ksz * p.ksz; ++t) {
+    const int taps = p.ksz * p.ksz;
+    for (int t = 0; t < taps; ++t) {
       const int yy = y + t / p.ksz - half, xx = x + t % p.ksz - half;
       if (yy >= 0 && yy < p.H && xx >= 0 && xx < p.W)
-        acc += __ldg(p.v + (size_t)t * plane + idx + (ptrdiff_t)(yy - y) * p.W + (xx - x));
+        for (int q = 0; q < p.parts; ++q)
+          acc += __ldg(p.v + (size_t)(q * taps + t) * plane + idx + (ptrdiff_t)(yy - y) * p.W + (xx - x));
     }
     p.y[idx] = acc + __ldg(p.x2 + idx);
   }
@@ -376,32 +379,41 @@ __device__ __forceinline__ void ensemble_src(int t, int i, int j, int H, int W, 
   }
 }
 
-// dst[v][i][j] = src[src_of(t0 + v, i, j)] for v in [0, count): the transformed copies that feed one batched forward.
+// Up to four transforms of one orientation group (all < 4 or all >= 4), the batch of one forward.
+struct EnsembleSel {
+  int t[4];
+  int count;
+};
+
+// dst[v][i][j] = src[src_of(sel.t[v], i, j)] for v in [0, count): the transformed copies that feed one batched forward.
 // All `count` transforms share one output shape [OH][OW] ([H][W] for t < 4, [W][H] otherwise).
 __global__ void __launch_bounds__(256) ensemble_flip_kernel(const float* __restrict__ src, float* __restrict__ dst, int H, int W,
-                                                            int t0, int count) {
-  const int OH = t0 < 4 ? H : W, OW = t0 < 4 ? W : H;
-  const long long per = (long long)OH * OW, total = per * count;
+                                                            const EnsembleSel sel) {
+  const int OH = sel.t[0] < 4 ? H : W, OW = sel.t[0] < 4 ? W : H;
+  const long long per = (long long)OH * OW, total = per * sel.count;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int v = (int)(idx / per);
     const int r = (int)(idx - (long long)v * per);
     const int i = r / OW, j = r - i * OW;
     int p, q;
-    ensemble_src(t0 + v, i, j, H, W, &p, &q);
+    ensemble_src(sel.t[v], i, j, H, W, &p, &q);
     dst[idx] = __ldg(src + (long long)p * W + q);
   }
 }
 
-// out[p][q] = (sum over t < flips of y_t[inverse position]) / flips, accumulated in fp64 in the order t = 0, 1, ...
-// like the reference's `output += flip(y, i, invert=True)` on a float64 array (DCSCN.py:560-575).
-// ya: transforms 0..3 (shape [H][W] each), yb: transforms 4..7 (shape [W][H] each); H, W = output (HR) size.
+// out[p][q] = (sum over the transforms t in `mask` of y_t[inverse position]) / divisor, accumulated in fp64 in the order
+// t = 0, 1, ... like the reference's `output += flip(y, i, invert=True)` on a float64 array (DCSCN.py:560-575).
+// ya: the selected transforms < 4 in ascending order (shape [H][W] each), yb: the selected transforms >= 4 ([W][H] each);
+// H, W = output (HR) size.  divisor = number of flips of the whole ensemble, or 1 for a rank's partial sum.
 __global__ void __launch_bounds__(256) ensemble_reduce_kernel(const float* __restrict__ ya, const float* __restrict__ yb,
-                                                              double* __restrict__ out, int H, int W, int flips) {
+                                                              double* __restrict__ out, int H, int W, int mask, double divisor) {
   const long long total = (long long)H * W;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int p = (int)(idx / W), q = (int)(idx - (long long)p * W);
     double sum = 0.0;
-    for (int t = 0; t < flips; ++t) {
+    int sa = 0, sb = 0;                              // slot of the next selected transform inside ya / yb
+    for (int t = 0; t < 8; ++t) {
+      if (!((mask >> t) & 1)) continue;
       int i, j;
       switch (t) {                                  // the (i, j) of transform t whose source pixel is (p, q)
         case 0: i = p; j = q; break;
@@ -413,10 +425,10 @@ __global__ void __launch_bounds__(256) ensemble_reduce_kernel(const float* __res
         case 6: i = q; j = p; break;
         default: i = W - 1 - q; j = H - 1 - p; break;
       }
-      const float v = t < 4 ? __ldg(ya + ((long long)t * H + i) * W + j) : __ldg(yb + ((long long)(t - 4) * W + i) * H + j);
+      const float v = t < 4 ? __ldg(ya + ((long long)(sa++) * H + i) * W + j) : __ldg(yb + ((long long)(sb++) * W + i) * H + j);
       sum += (double)v;
     }
-    out[idx] = sum / (double)flips;
+    out[idx] = sum / divisor;
   }
 }
 

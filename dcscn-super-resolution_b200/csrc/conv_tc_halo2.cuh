@@ -1,0 +1,309 @@
+// Streaming variant of the single-box halo kernel (conv_tc_halo1.cuh): same operands, same TMA boxes, same three
+// kind::f16 products per algorithmic MAC - but a weight stage is RELEASED as soon as its three products are issued.
+//
+// Why (profiles/r1d_conv_tc_ncu_summary.csv): conv_tc_halo1 keeps all weight stages of an fp32-promotion segment
+// resident for two passes (small correction products first, dominant a_hi*w_hi last, so that only 1/3 of the UMMAs
+// see a large accumulator - the tensor core truncates its fp32 accumulate on every UMMA).  With 22 KB stages only two
+// of the five ring slots were ever free for prefetch, and every layer ran at ~4.5 TB/s of TMA traffic into shared
+// memory whatever its shape: latency-bound on the weight ring, tensor pipe 31-50 % active.
+//
+// Here the two kinds of products go to DIFFERENT TMEM accumulators, so the order of issue inside a stage no longer
+// matters for accuracy and nothing has to be held:
+//   * the K loop of a tile is cut into segments s = 0..nseg-1 as before; accumulation "slot" j = 0..nseg receives the
+//     correction products (a_lo*w_hi, a_hi*w_lo) of segment j-1 FIRST (while it is still small) and the dominant
+//     products of segment j afterwards;  slot j is complete at the end of segment j and the epilogue warps add it into
+//     their fp32 registers with round-to-nearest ("promotion").  One more drain per tile than halo1 (nseg + 1).
+//   * slots rotate over THREE TMEM buffers of n_pad columns: during segment s buffer (s % 3) takes dominant products,
+//     ((s + 1) % 3) corrections, ((s + 2) % 3) is being drained.  3 * n_pad <= 512 columns -> n_pad <= 160; wider
+//     layers are split into column tiles by the engine (choose_tiling).
+//   * every stage of the weight ring and every A slot is released by the tcgen05.commit that follows its last UMMA,
+//     so the whole ring (up to 24 stages) is prefetch depth.
+#pragma once
+#include "conv_tc_halo1.cuh"
+
+namespace dcscn {
+
+constexpr int kH2MaxStages = 24;
+constexpr int kH2MaxAcc = 4;
+constexpr int kH2BarBytes = 1024;
+
+__host__ __device__ inline size_t tc_halo2_misc_bytes() { return 1024 + kH2BarBytes + kRdotSmemBytes; }
+
+template <int NPLANES>
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
+                     const __grid_constant__ CUtensorMap tm_w, const ConvTCParams p, const int num_a, const int num_b) {
+  constexpr int KC = 64;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int AH_BYTES = kHalo1PlaneBytes;            // one plane of the 18 x 10 box
+  constexpr int A_SLOT = NPLANES * AH_BYTES;
+  const int half_rows = p.n_pad >> 1;                   // weight-tile rows staged by each CTA of the pair
+  const int BH_BYTES = half_rows * KC * 2;              // one plane of this CTA's weight half
+  const int B_STAGE = NPLANES * BH_BYTES;
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + (size_t)num_a * A_SLOT;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_b + (size_t)num_b * B_STAGE);
+  uint64_t* a_empty = a_full + kH2MaxStages;
+  uint64_t* b_full = a_empty + kH2MaxStages;
+  uint64_t* b_empty = b_full + kH2MaxStages;
+  uint64_t* acc_full = b_empty + kH2MaxStages;
+  uint64_t* acc_empty = acc_full + kH2MaxAcc;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kH2MaxAcc);
+  float* s_rdot = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a_full) + kH2BarBytes);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+  const int acc_stride = p.n_pad;                       // TMEM columns between accumulation buffers
+  const uint32_t nbuf = (4 * p.n_pad <= 512) ? 4u : 3u; // with 4 buffers the next tile never waits for this tile's drains
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < num_a; ++s) {
+      ptx::mbar_init(&a_full[s], 1);
+      ptx::mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < num_b; ++s) {
+      ptx::mbar_init(&b_full[s], 1);
+      ptx::mbar_init(&b_empty[s], 1);
+    }
+    for (int s = 0; s < kH2MaxAcc; ++s) {
+      ptx::mbar_init(&acc_full[s], 1);                     // leader's tcgen05.commit (multicast)
+      ptx::mbar_init(&acc_empty[s], 2 * kEpiWarps);        // epilogue warps of both CTAs (used on the leader only)
+    }
+    ptx::fence_barrier_init();
+    ptx::fence_proxy_async();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc_2sm(tmem_slot, 512);
+    ptx::tmem_relinquish_2sm();
+  }
+  if (p.epi.mode == EPI_D2S_RDOT)
+    for (int i = threadIdx.x; i < p.epi.rdot_taps * p.epi.d2s_cout; i += blockDim.x) s_rdot[i] = p.epi.rdot_w[i];
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const ConvGeom& g = p.g;
+  const int tiles_per_img = g.tiles_x * g.tiles_y;
+  const int num_tiles = g.n_img * tiles_per_img;
+  const int groups = (num_tiles + 1) >> 1;
+  const int num_items = groups * p.n_tiles;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int total_a = p.chunks * 3;                   // segment units per tile: (channel chunk, dx); one A slot per chunk
+  const int nseg = (total_a + p.seg_chunks - 1) / p.seg_chunks;
+  const int nslots = nseg + (NPLANES == 2 ? 1 : 0);   // accumulation slots (= promotions) per tile
+
+  if (warp < kEpiWarp0) {
+    ptx::setmaxnreg_dec<kRegsIssue>();
+    if (warp == 0) {
+      // ============================== TMA producer: A boxes (both CTAs) ==============================
+      if (lane == 0) {
+        ptx::prefetch_tensormap(&tm_hi);
+        if (NPLANES == 2) ptx::prefetch_tensormap(&tm_lo);
+        int a = 0;
+        uint32_t pha = 0;
+        for (int item = cluster_id; item < num_items; item += num_clusters) {
+          int tile = (item / p.n_tiles) * 2 + (int)rank;
+          if (tile >= num_tiles) tile = num_tiles - 1;       // lockstep filler (stores are masked)
+          const int img = tile / tiles_per_img;
+          const int t2 = tile - img * tiles_per_img;
+          const int ty = t2 / g.tiles_x, tx = t2 - ty * g.tiles_x;
+          for (int ch = 0; ch < p.chunks; ++ch) {
+            ptx::mbar_wait(&a_empty[a], pha ^ 1);
+            uint8_t* slot = smem_a + (size_t)a * A_SLOT;
+            const uint32_t lead = ptx::mapa_shared(ptx::smem_u32(&a_full[a]), 0);
+            if (leader) ptx::mbar_arrive_expect_tx(&a_full[a], (uint32_t)(2 * NPLANES * kHalo1Rows * 128));
+            ptx::tma_load_4d_2sm(slot, &tm_hi, lead, ch * KC, tx * kHaloTW - 1, ty * kHaloTH - 1, img);
+            if (NPLANES == 2)
+              ptx::tma_load_4d_2sm(slot + AH_BYTES, &tm_lo, lead, ch * KC, tx * kHaloTW - 1, ty * kHaloTH - 1, img);
+            if (++a == num_a) { a = 0; pha ^= 1; }
+          }
+        }
+      }
+    } else if (warp == 2) {
+      // ============================== TMA producer: weight halves (both CTAs) ==============================
+      if (lane == 0) {
+        ptx::prefetch_tensormap(&tm_w);
+        const int wrows = NPLANES * half_rows;               // rows of one (tile, rank) block in the packed weights
+        int b = 0;
+        uint32_t phb = 0;
+        for (int item = cluster_id; item < num_items; item += num_clusters) {
+          const int n_tile = item % p.n_tiles;
+          for (int ai = 0; ai < total_a; ++ai) {
+            const int ch = ai / 3, dx = ai - ch * 3;
+            for (int dy = 0; dy < 3; ++dy) {
+              ptx::mbar_wait(&b_empty[b], phb ^ 1);
+              const uint32_t lead = ptx::mapa_shared(ptx::smem_u32(&b_full[b]), 0);
+              if (leader) ptx::mbar_arrive_expect_tx(&b_full[b], (uint32_t)(2 * B_STAGE));
+              const int wblock = ((n_tile * 9 + dy * 3 + dx) * p.chunks + ch) * 2 + (int)rank;
+              ptx::tma_load_2d_2sm(smem_b + (size_t)b * B_STAGE, &tm_w, lead, 0, wblock * wrows);
+              if (++b == num_b) { b = 0; phb ^= 1; }
+            }
+          }
+        }
+      }
+    } else if (warp == 1 && leader) {
+      // ============================== MMA issuer (leader CTA only) ================================
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.n_pad >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      const uint32_t sa_u32 = ptx::smem_u32(smem_a), sb_u32 = ptx::smem_u32(smem_b);
+      int sa = 0, sb = 0;
+      uint32_t spa = 0, spb = 0;
+      uint32_t slot = 0;                                  // running accumulation-slot counter; buffer = slot % 3
+      for (int item = cluster_id; item < num_items; item += num_clusters) {
+        {  // the slot that takes the dominant products of segment 0
+          ptx::mbar_wait(&acc_empty[slot % nbuf], ((slot / nbuf) & 1) ^ 1);
+        }
+        for (int s = 0; s < nseg; ++s) {
+          const uint32_t sd = slot + (uint32_t)s, sc = sd + 1;
+          if (NPLANES == 2) ptx::mbar_wait(&acc_empty[sc % nbuf], ((sc / nbuf) & 1) ^ 1);
+          ptx::tc_fence_after();
+          const uint32_t tmem_d = tmem_base + (sd % nbuf) * (uint32_t)acc_stride;
+          const uint32_t tmem_c = tmem_base + (sc % nbuf) * (uint32_t)acc_stride;
+          uint32_t acc_c = 0;                                           // corrections open their slot
+          uint32_t acc_d = (NPLANES == 2 && s > 0) ? 1u : 0u;           // slot already holds the previous corrections
+          const int a0 = s * p.seg_chunks;
+          const int a1 = (a0 + p.seg_chunks < total_a) ? a0 + p.seg_chunks : total_a;
+          for (int ai = a0; ai < a1; ++ai) {
+            const int ch = ai / 3, dx = ai - ch * 3;
+            int ksteps = (p.cin_pad - ch * KC);
+            ksteps = (ksteps > KC ? KC : ksteps) >> 4;
+            if (dx == 0) ptx::mbar_wait(&a_full[sa], spa);   // a chunk's box serves its three dx units (any segment)
+            for (int dy = 0; dy < 3; ++dy) {
+              ptx::mbar_wait(&b_full[sb], spb);
+              ptx::tc_fence_after();
+              const uint32_t a_addr = sa_u32 + (uint32_t)sa * (uint32_t)A_SLOT + (uint32_t)(dy * kHalo1W + dx) * 128u;
+              const uint32_t b_addr = sb_u32 + (uint32_t)sb * (uint32_t)B_STAGE;
+              const uint32_t lb_hi = desc_lo_t<KC>(b_addr), lb_lo = desc_lo_t<KC>(b_addr + BH_BYTES);
+              if (ptx::elect_one()) {
+#pragma unroll 1
+                for (int ks = 0; ks < ksteps; ++ks) {
+                  const uint32_t kadd = (uint32_t)ks * 2u;
+                  const uint64_t da_hi = make_desc64_halo1(a_addr + ks * 32, 0);
+                  if (NPLANES == 2) {
+                    ptx::mma_f16_ss_2sm(tmem_c, make_desc64_halo1(a_addr + AH_BYTES + ks * 32, 0), make_desc64_t<KC>(lb_hi + kadd), idesc, acc_c);
+                    ptx::mma_f16_ss_2sm(tmem_c, da_hi, make_desc64_t<KC>(lb_lo + kadd), idesc, 1);
+                    acc_c = 1;
+                  }
+                  ptx::mma_f16_ss_2sm(tmem_d, da_hi, make_desc64_t<KC>(lb_hi + kadd), idesc, acc_d);
+                  acc_d = 1;
+                }
+                ptx::mma_commit_2sm(&b_empty[sb], 3);
+                if (dy == 2 && dx == 2) ptx::mma_commit_2sm(&a_empty[sa], 3);
+              }
+              acc_c = 1;
+              acc_d = 1;
+              __syncwarp();
+              if (++sb == num_b) { sb = 0; spb ^= 1; }
+            }
+            if (dx == 2 && ++sa == num_a) { sa = 0; spa ^= 1; }
+          }
+          if (ptx::elect_one()) {
+            ptx::mma_commit_2sm(&acc_full[sd % nbuf], 3);
+            if (NPLANES == 2 && s == nseg - 1) ptx::mma_commit_2sm(&acc_full[sc % nbuf], 3);
+          }
+          __syncwarp();
+        }
+        slot += (uint32_t)nslots;
+      }
+    }
+  } else {
+    ptx::setmaxnreg_inc<kRegsEpilogue>();
+    // ============================== epilogue (both CTAs, own 128 TMEM lanes) ==================================
+    const int ew = warp - kEpiWarp0;
+    const int quad = warp & 3;
+    const int grp = ew >> 2;
+    const int row = quad * 32 + lane;
+    const int py = row / kHaloTW, px = row - py * kHaloTW;
+    const int n_total = p.n_tiles * p.n_pad;
+    const int nch = p.n_pad >> 4;
+    const int per = (nch + kColSplit - 1) / kColSplit;
+    const int first_chunk = grp * per;
+    const int my_chunks = (nch - first_chunk) < per ? ((nch - first_chunk) > 0 ? nch - first_chunk : 0) : per;
+    const int col_base = first_chunk * 16;
+    const uint32_t lead_acc_empty0 = ptx::mapa_shared(ptx::smem_u32(&acc_empty[0]), 0);
+    const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)col_base;
+    uint32_t slot = 0;
+    for (int item = cluster_id; item < num_items; item += num_clusters) {
+      const int n_tile = item % p.n_tiles;
+      const int tile = (item / p.n_tiles) * 2 + (int)rank;
+      const bool real = tile < num_tiles;
+      const int img = tile / tiles_per_img;
+      const int t2 = tile - img * tiles_per_img;
+      const int ty = t2 / g.tiles_x, tx = t2 - ty * g.tiles_x;
+      const int y = ty * kHaloTH + py, x = tx * kHaloTW + px;
+      const bool valid = real && (y < g.H) && (x < g.W);
+
+      float sum[kMaxColChunks][16];
+#pragma unroll
+      for (int j = 0; j < kMaxColChunks; ++j)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) sum[j][i] = 0.f;
+      for (int s = 0; s < nslots; ++s) {
+        const uint32_t buf = slot % nbuf;
+        ptx::mbar_wait(&acc_full[buf], (slot / nbuf) & 1);
+        ptx::tc_fence_after();
+        const uint32_t taddr = taddr0 + buf * (uint32_t)acc_stride;
+        // fp32 round-to-nearest promotion of the slot: wide TMEM loads (64 / 32 columns per instruction); columns
+        // past this thread's share may be read (they stay inside the 512 allocated columns) but are never stored.
+#pragma unroll
+        for (int j = 0; j < kMaxColChunks; j += 4) {
+          if (j < my_chunks) {
+            if (my_chunks - j > 2) {
+              float v[64];
+              ptx::tmem_ld64(taddr + j * 16, v);
+#pragma unroll
+              for (int i = 0; i < 64; ++i) sum[j + (i >> 4)][i & 15] += v[i];
+            } else {
+              float v[32];
+              ptx::tmem_ld32(taddr + j * 16, v);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) sum[j + (i >> 4)][i & 15] += v[i];
+            }
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cluster(lead_acc_empty0 + (uint32_t)(buf * sizeof(uint64_t)));
+        ++slot;
+      }
+      if (p.epi.mode == EPI_D2S_RDOT) {
+        float v[9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) v[t] = 0.f;
+        const int share = per * 16;                       // columns of one epilogue thread
+#pragma unroll
+        for (int j = 0; j < kMaxColChunks; ++j) {
+          if (j < my_chunks) {
+            const int cg = n_tile * p.n_pad + col_base + j * 16;
+            if (cg < p.epi.n_valid) {
+              const int ij = cg / p.epi.d2s_cout, c = cg - ij * p.epi.d2s_cout;
+              rdot_accumulate16(p.epi, s_rdot, cg, c, sum[j], v);
+              // flush when this thread has seen its whole part of the sub-pixel (all of it when rdot_parts == 1)
+              const bool last = (p.epi.rdot_parts > 1) ? (j == my_chunks - 1) : (c + 16 == p.epi.d2s_cout);
+              if (last && valid) rdot_flush(p.epi, g, img, y, x, ij, p.epi.rdot_parts > 1 ? c / share : 0, v);
+            }
+          }
+        }
+      } else if (valid) {
+#pragma unroll
+        for (int j = 0; j < kMaxColChunks; ++j)
+          if (j < my_chunks) epilogue_store16(p.epi, g, n_total, img, y, x, n_tile * p.n_pad + col_base + j * 16, sum[j]);
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
+}  // namespace dcscn

@@ -23,6 +23,7 @@
 #include "conv_tc_pair.cuh"
 #include "conv_tc_halo.cuh"
 #include "conv_tc_halo1.cuh"
+#include "conv_tc_halo2.cuh"
 #include "conv_ds.cuh"
 #include "train.cuh"
 #include "wgrad_tc.cuh"
@@ -115,6 +116,9 @@ struct TcLaunch {
   CUtensorMap t1_hi, t1_lo;
   int halo1_na = 0, halo1_nb = 0, halo1_seg = 1;
   size_t halo1_smem = 0;
+  bool halo2 = false;            // streaming halo kernel (split correction / dominant accumulators), default
+  int halo2_na = 0, halo2_nb = 0, halo2_seg = 1;
+  size_t halo2_smem = 0;
   size_t pair_smem = 0;
   ConvTCParams p;
   ConvRefParams ref;
@@ -204,7 +208,8 @@ struct dcscn_handle {
   int seg_chunks = 0;                // pipeline stages per fp32-promotion segment; 0 = automatic
   int cluster = 1;                   // CTAs per cluster multicasting the weight tiles (single-CTA kernel)
   int pair = 1;                      // use the CTA-pair (tcgen05 cta_group::2) kernel when KC == 64
-  int halo = 2;                      // 3x3 layers: halo-reuse CTA-pair kernel, 1 = three 18x8 boxes, 2 = one 18x10 box per chunk
+  int halo = 3;                      // 3x3 layers: halo-reuse CTA-pair kernel, 1 = three 18x8 boxes, 2 = one 18x10 box per chunk
+                                     // (two-pass segments), 3 = the same box with streaming stages (conv_tc_halo2.cuh)
   int halo_base = 0;                 // single-box variant: set the descriptor base-offset field
   int timing = 0;
   int fuse_last = 1;                 // fold the per-pixel half of R-CNN1 into the last Up-PS epilogue
@@ -361,8 +366,8 @@ static void fuse_columns(const dcscn_handle* h, TcLayer& t, const std::string& s
   }
 }
 
-static void choose_tiling(int n_total_pad16, int* n_tiles, int* n_pad) {
-  int nt = (n_total_pad16 + 255) / 256;
+static void choose_tiling(int n_total_pad16, int* n_tiles, int* n_pad, int cap = 256) {
+  int nt = (n_total_pad16 + cap - 1) / cap;
   int np = pad16((n_total_pad16 + nt - 1) / nt);
   *n_tiles = nt;
   *n_pad = np;
@@ -481,14 +486,25 @@ static int pack_tc_layer(dcscn_handle* h, TcLayer& t) {
   return 0;
 }
 
-static TcLayer make_tc(const std::string& name, int ksz, int cin, int cout_cols, int cin_pad) {
+// Column-tile cap of a layer: the streaming 3x3 kernel rotates three TMEM buffers of n_pad columns (3 * n_pad <= 512).
+static int tile_cap(const dcscn_handle* h, int ksz) {
+  return (ksz == 3 && h->halo == 3 && h->pair && h->kc == 64 && h->sm_count % 2 == 0) ? 160 : 256;
+}
+
+static TcLayer make_tc(const dcscn_handle* h, const std::string& name, int ksz, int cin, int cout_cols, int cin_pad,
+                       int tile_unit = 0) {
+  const int cap = tile_cap(h, ksz);
   TcLayer t;
   t.name = name;
   t.ksz = ksz;
   t.cin = cin;
   t.cout = cout_cols;
   t.cin_pad = cin_pad;
-  choose_tiling(pad16(cout_cols), &t.n_tiles, &t.n_pad);
+  choose_tiling(pad16(cout_cols), &t.n_tiles, &t.n_pad, cap);
+  if (tile_unit > 0 && cap < 256 && t.n_tiles > 1 && tile_unit % 16 == 0 && tile_unit <= cap && cout_cols % tile_unit == 0) {
+    t.n_pad = tile_unit;               // pixel-shuffler layers: one column tile per sub-pixel (fused R-CNN1 epilogue)
+    t.n_tiles = cout_cols / tile_unit;
+  }
   t.n_valid = cout_cols;
   t.w_host.assign((size_t)ksz * ksz * cin * cout_cols, 0.f);
   t.bias_host.assign((size_t)t.n_tiles * t.n_pad, 0.f);
@@ -569,7 +585,7 @@ static int construct_tc_layers(dcscn_handle* h) {
   for (int i = 1; i < L; ++i) {
     const std::string scope = "CNN" + std::to_string(i + 1);
     const LayerDef* l = find_layer(h, scope);
-    TcLayer t = make_tc(scope, l->k, l->cin, l->cout, h->feat_w[i - 1]);
+    TcLayer t = make_tc(h, scope, l->k, l->cin, l->cout, h->feat_w[i - 1]);
     for (int ci = 0; ci < l->cin; ++ci) t.in_map.push_back(ci);
     fuse_columns(h, t, scope, 0, 0);
     h->tcl.push_back(std::move(t));
@@ -578,7 +594,7 @@ static int construct_tc_layers(dcscn_handle* h) {
   {
     const LayerDef* a1 = find_layer(h, "A1");
     const LayerDef* b1 = find_layer(h, "B1");
-    TcLayer t = make_tc("A1+B1", 1, a1->cin, h->a1_w + b1->cout, h->feat_pitch);
+    TcLayer t = make_tc(h, "A1+B1", 1, a1->cin, h->a1_w + b1->cout, h->feat_pitch);
     for (int li = 0; li < L; ++li)
       for (int ci = 0; ci < h->filters[li]; ++ci) t.in_map.push_back(h->feat_off[li] + ci);
     fuse_columns(h, t, "A1", 0, 0);
@@ -588,7 +604,7 @@ static int construct_tc_layers(dcscn_handle* h) {
   // B2
   {
     const LayerDef* l = find_layer(h, "B2");
-    TcLayer t = make_tc("B2", l->k, l->cin, l->cout, h->b1_w);
+    TcLayer t = make_tc(h, "B2", l->k, l->cin, l->cout, h->b1_w);
     for (int ci = 0; ci < l->cin; ++ci) t.in_map.push_back(ci);
     fuse_columns(h, t, "B2", 0, 0);
     h->tcl.push_back(std::move(t));
@@ -596,14 +612,15 @@ static int construct_tc_layers(dcscn_handle* h) {
   // Up-PS (+ Up-PS2): input = Concat2 = [B2 | A1]
   {
     const LayerDef* l = find_layer(h, "Up-PS/Up-PS_CNN");
-    TcLayer t = make_tc("Up-PS", l->k, l->cin, l->cout, h->nin_pitch);
+    // the LAST depth_to_space layer carries the fused R-CNN1 epilogue: one column tile per sub-pixel
+    TcLayer t = make_tc(h, "Up-PS", l->k, l->cin, l->cout, h->nin_pitch, c.scale == 4 ? 0 : h->ps_out);
     for (int ci = 0; ci < c.nin_filters2; ++ci) t.in_map.push_back(ci);
     for (int ci = 0; ci < c.nin_filters; ++ci) t.in_map.push_back(h->b1_w + ci);
     fuse_columns(h, t, "Up-PS/Up-PS_CNN", 0, 0);
     h->tcl.push_back(std::move(t));
     if (c.scale == 4) {
       const LayerDef* l2 = find_layer(h, "Up-PS2/Up-PS2_CNN");
-      TcLayer t2 = make_tc("Up-PS2", l2->k, l2->cin, l2->cout, h->mid_pitch);
+      TcLayer t2 = make_tc(h, "Up-PS2", l2->k, l2->cin, l2->cout, h->mid_pitch, h->ps_out);
       for (int ci = 0; ci < l2->cin; ++ci) t2.in_map.push_back(ci);
       fuse_columns(h, t2, "Up-PS2/Up-PS2_CNN", 0, 0);
       h->tcl.push_back(std::move(t2));
@@ -655,6 +672,14 @@ static int finalize_params(dcscn_handle* h) {
   return 0;
 }
 
+// Partial plane sets of the fused R-CNN1 epilogue: an epilogue thread owns n_pad / kColSplit GEMM columns; when that share
+// is a fraction of one sub-pixel's `cout` channels, `cout / share` threads each write their own tap-planar partials.
+static int rdot_parts(int n_pad, int cout) {
+  const int nch = n_pad >> 4, per16 = ((nch + kColSplit - 1) / kColSplit) * 16;
+  if (cout <= 0 || per16 % cout == 0) return 1;
+  return (cout % per16 == 0) ? cout / per16 : 1;
+}
+
 // ----------------------------------------------------------------------------------- workspace ----
 template <typename T>
 static int dev_alloc(dcscn_handle* h, T** p, size_t count, bool zero) {
@@ -700,7 +725,7 @@ static int ensure_workspace(dcscn_handle* h, size_t lr_px) {
     if (dev_alloc(h, &h->mid_lo, two ? lr_px * 4 * h->mid_pitch : 0, true)) return 1;
   }
   if (dev_alloc(h, &h->hr, lr_px * s2 * h->ps_out, true)) return 1;
-  if (dev_alloc(h, &h->vbuf, lr_px * s2 * 9, true)) return 1;
+  if (dev_alloc(h, &h->vbuf, lr_px * s2 * 9 * (size_t)rdot_parts(h->tcl.empty() ? 16 : h->tcl.back().n_pad, h->ps_out), true)) return 1;
   h->cap_px = lr_px;
   return 0;
 }
@@ -767,6 +792,7 @@ static int add_tc_launch(dcscn_handle* h, Plan* pl, const TcLayer& t, const __ha
   L.p.epi.alpha = t.d_alpha;
   L.p.epi.out_scale = 1.0f / t.wscale;
   L.p.epi.n_valid = t.n_valid;
+  L.p.epi.drop_ntotal = pad16(t.cout);   // keep-mask index stride = slot width, whatever the column tiling
 
   const size_t stage = tc_stage_bytes(h->kc, planes(h), t.n_pad);
   const size_t budget = 227 * 1024 - 2048 - kRdotSmemBytes;
@@ -796,11 +822,17 @@ static int add_tc_launch(dcscn_handle* h, Plan* pl, const TcLayer& t, const __ha
     L.pair_seg = std::max(1, std::min(seg, L.pair_stages - 1));
   }
 
-  // halo-reuse launch shape (3x3 layers, CTA pair, KC = 64)
-  L.halo = L.pair && t.ksz == 3;
-  if (L.halo) {
+  // halo-reuse launch shapes (3x3 layers, CTA pair, KC = 64): 16 x 8 pixel patches
+  const bool pair3x3 = L.pair && t.ksz == 3;
+  L.halo = pair3x3;
+  if (pair3x3) {
     ConvGeom hg{n, H, W, (W + kHaloTW - 1) / kHaloTW, (H + kHaloTH - 1) / kHaloTH, kHaloTW, kHaloTH};
     L.hg = hg;
+    const long long htiles = (long long)n * hg.tiles_x * hg.tiles_y;
+    const long long hitems = ((htiles + 1) / 2) * t.n_tiles;
+    L.halo_grid = (int)std::min<long long>(hitems, h->sm_count / 2) * 2;
+  }
+  if (L.halo && h->halo == 1) {   // three 18 x 8 boxes per chunk (superseded; kept selectable for A/B runs)
     if (encode_map(h, &L.th_hi, src_hi, t.cin_pad, src_pitch, n, H, W, kHaloTH + 2, kHaloTW, 64)) return 1;
     if (planes(h) == 2) {
       if (encode_map(h, &L.th_lo, src_lo, t.cin_pad, src_pitch, n, H, W, kHaloTH + 2, kHaloTW, 64)) return 1;
@@ -824,16 +856,13 @@ static int add_tc_launch(dcscn_handle* h, Plan* pl, const TcLayer& t, const __ha
         break;
       }
     }
-    if (L.halo) {
-      L.halo_smem = L.halo_na * a_slot + L.halo_nb * b_stage + 1024 + 512 + kRdotSmemBytes;
-      const long long htiles = (long long)n * hg.tiles_x * hg.tiles_y;
-      const long long hitems = ((htiles + 1) / 2) * t.n_tiles;
-      L.halo_grid = (int)std::min<long long>(hitems, h->sm_count / 2) * 2;
-    }
+    if (L.halo) L.halo_smem = L.halo_na * a_slot + L.halo_nb * b_stage + 1024 + 512 + kRdotSmemBytes;
+  } else {
+    L.halo = false;
   }
 
   L.halo1 = false;
-  if (L.halo) {
+  if (pair3x3) {
     const size_t a_slot = tc_halo1_a_slot_bytes(planes(h)), b_stage = tc_halo_b_stage_bytes(planes(h), t.n_pad);
     // fp32-promotion period in (chunk, dx) units of 3 taps: thin layers are latency-bound, give them longer segments
     int seg = h->seg_chunks > 0 ? h->seg_chunks : (t.n_pad >= 144 ? 1 : (t.n_pad >= 112 ? 2 : 3));
@@ -857,6 +886,37 @@ static int add_tc_launch(dcscn_handle* h, Plan* pl, const TcLayer& t, const __ha
         if (encode_map(h, &L.t1_lo, src_lo, t.cin_pad, src_pitch, n, H, W, kHaloTH + 2, kHalo1W, 64)) return 1;
       } else {
         L.t1_lo = L.t1_hi;
+      }
+    }
+  }
+
+  // streaming halo kernel: every ring slot is prefetch depth; three (n_pad > 128) or four TMEM accumulation buffers
+  L.halo2 = false;
+  if (pair3x3 && 3 * t.n_pad <= 512) {
+    const size_t a_slot = tc_halo1_a_slot_bytes(planes(h)), b_stage = tc_halo_b_stage_bytes(planes(h), t.n_pad);
+    const long long total = 227 * 1024 - (long long)tc_halo2_misc_bytes();
+    int na = 2;
+    long long nb = (total - na * (long long)a_slot) / (long long)b_stage;
+    if ((total - 3 * (long long)a_slot) / (long long)b_stage >= 9) {   // thin layers: a third A slot, still >= 9 weight stages
+      na = 3;
+      nb = (total - 3 * (long long)a_slot) / (long long)b_stage;
+    }
+    nb = std::min<long long>(nb, kH2MaxStages);
+    if (nb >= 3) {
+      int seg = h->seg_chunks > 0 ? h->seg_chunks : (t.n_pad >= 144 ? 1 : (t.n_pad >= 112 ? 2 : 3));
+      seg = std::min(seg, 3 * ((t.cin_pad + 63) / 64));
+      L.halo2 = true;
+      L.halo2_seg = seg;
+      L.halo2_na = na;
+      L.halo2_nb = (int)nb;
+      L.halo2_smem = na * a_slot + (size_t)nb * b_stage + tc_halo2_misc_bytes();
+      if (!L.halo1) {   // the A maps of the single-box variants are shared
+        if (encode_map(h, &L.t1_hi, src_hi, t.cin_pad, src_pitch, n, H, W, kHaloTH + 2, kHalo1W, 64)) return 1;
+        if (planes(h) == 2) {
+          if (encode_map(h, &L.t1_lo, src_lo, t.cin_pad, src_pitch, n, H, W, kHaloTH + 2, kHalo1W, 64)) return 1;
+        } else {
+          L.t1_lo = L.t1_hi;
+        }
       }
     }
   }
@@ -970,14 +1030,19 @@ static Plan* get_plan(dcscn_handle* h, int n, int H, int W) {
     const int klast = find_layer(h, "R-CNN1")->k;
     pl->unfused = L;
     pl->fused_index = (int)pl->tc.size() - 1;
-    pl->fused_last = (klast == 3) && (cout % 16 == 0) && (cout <= 128) && (nch % kColSplit == 0) && ((per * 16) % cout == 0);
+    const int parts = rdot_parts(L.p.n_pad, cout);
+    pl->fused_last = (klast == 3) && (cout % 16 == 0) && (cout <= 128) && (nch % kColSplit == 0) &&
+                     (((per * 16) % cout == 0) || (parts > 1 && L.halo2 && h->halo == 3 && L.p.n_pad % (per * 16) == 0));
     if (pl->fused_last) {
+      L.p.epi.rdot_parts = ((per * 16) % cout == 0) ? 1 : parts;
       L.p.epi.mode = EPI_D2S_RDOT;
       L.p.epi.rdot_w = h->d_last_w;
       L.p.epi.rdot_out = h->vbuf;
       L.p.epi.rdot_taps = klast * klast;
     }
+    const int gparts = pl->fused_last ? L.p.epi.rdot_parts : 1;
     memset(&pl->gather, 0, sizeof(pl->gather));
+    pl->gather.parts = gparts;
     pl->gather.n_img = n;
     pl->gather.H = HR_H;
     pl->gather.W = HR_W;
@@ -1111,6 +1176,35 @@ static int launch_tc_halo1(dcscn_handle* h, const TcLaunch& L, cudaStream_t st) 
   return 0;
 }
 
+template <int NPL>
+static int launch_tc_halo2(dcscn_handle* h, const TcLaunch& L, cudaStream_t st) {
+  static bool attr_set_dev[64] = {};   // function attributes are per device
+  bool& attr_set = attr_set_dev[h->cfg.device_id & 63];
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(conv_tc_halo2_kernel<NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(L.halo_grid);
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = L.halo2_smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ConvTCParams p = L.p;
+  p.g = L.hg;
+  p.cluster_size = 2;
+  p.seg_chunks = L.halo2_seg;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc_halo2_kernel<NPL>, L.t1_hi, L.t1_lo, L.tm_w, p, L.halo2_na, L.halo2_nb));
+  return 0;
+}
+
 static int launch_tc(dcscn_handle* h, const TcLaunch& L, cudaStream_t st) {
   h->launches++;
   if (h->conv_impl == 1) {
@@ -1121,8 +1215,9 @@ static int launch_tc(dcscn_handle* h, const TcLaunch& L, cudaStream_t st) {
     return 0;
   }
   const int npl = planes(h);
-  if (h->pair && h->halo == 2 && L.halo1 && h->kc == 64) return npl == 2 ? launch_tc_halo1<2>(h, L, st) : launch_tc_halo1<1>(h, L, st);
-  if (h->pair && h->halo && L.halo && h->kc == 64) return npl == 2 ? launch_tc_halo<2>(h, L, st) : launch_tc_halo<1>(h, L, st);
+  if (h->pair && h->halo == 3 && L.halo2 && h->kc == 64) return npl == 2 ? launch_tc_halo2<2>(h, L, st) : launch_tc_halo2<1>(h, L, st);
+  if (h->pair && h->halo >= 2 && L.halo1 && h->kc == 64) return npl == 2 ? launch_tc_halo1<2>(h, L, st) : launch_tc_halo1<1>(h, L, st);
+  if (h->pair && h->halo == 1 && L.halo && h->kc == 64) return npl == 2 ? launch_tc_halo<2>(h, L, st) : launch_tc_halo<1>(h, L, st);
   if (h->pair && L.pair && h->kc == 64) return npl == 2 ? launch_tc_pair<2>(h, L, st) : launch_tc_pair<1>(h, L, st);
   if (L.p.wpack == nullptr) return fail("internal: single-CTA weight image was not packed for this layer");
   if (h->kc == 64) return npl == 2 ? launch_tc_inst<64, 2>(h, L, st) : launch_tc_inst<64, 1>(h, L, st);
@@ -1408,9 +1503,9 @@ int dcscn_forward_host(dcscn_handle* h, const float* x, const float* x2, float* 
 // Self-ensemble entirely on the device (DCSCN.py:547-586 `do` with self_ensemble = flips): the transformed copies of x
 // and x2 are produced by a kernel, transforms 0..3 run as ONE batched forward (n = up to 4, shape [h][w]) and 4..7 as
 // another (shape [w][h]), and the inverse transforms + the float64 mean are one more kernel.
-static int ensemble_impl(dcscn_handle* h, const float* x, const float* x2, double* y, int height, int width, int flips,
-                         cudaStream_t st) {
-  if (flips < 1 || flips > 8) return fail("forward_ensemble: flips must be 1..8 (got %d)", flips);
+static int ensemble_impl(dcscn_handle* h, const float* x, const float* x2, double* y, int height, int width, int mask,
+                         double divisor, cudaStream_t st) {
+  if (mask <= 0 || mask > 255) return fail("forward_ensemble: transform mask must select 1..8 of the 8 transforms (got 0x%x)", mask);
   if (height <= 0 || width <= 0) return fail("forward_ensemble: bad shape h=%d w=%d", height, width);
   CUDA_TRY(cudaSetDevice(h->cfg.device_id));
   const int s = h->cfg.scale;
@@ -1424,21 +1519,23 @@ static int ensemble_impl(dcscn_handle* h, const float* x, const float* x2, doubl
     CUDA_TRY(cudaMalloc((void**)&h->ens_y, 8 * hr * sizeof(float)));
     h->ens_cap = hr;
   }
-  const int na = flips < 4 ? flips : 4, nb = flips - na;
   const int grid_lr = (int)std::min<size_t>((4 * lr + 255) / 256, (size_t)h->sm_count * 8);
   const int grid_hr = (int)std::min<size_t>((4 * hr + 255) / 256, (size_t)h->sm_count * 8);
   for (int grp = 0; grp < 2; ++grp) {
-    const int cnt = grp == 0 ? na : nb;
-    if (cnt == 0) continue;
-    ensemble_flip_kernel<<<grid_lr, 256, 0, st>>>(x, h->ens_x, height, width, 4 * grp, cnt);
-    ensemble_flip_kernel<<<grid_hr, 256, 0, st>>>(x2, h->ens_x2, s * height, s * width, 4 * grp, cnt);
+    EnsembleSel sel;
+    memset(&sel, 0, sizeof(sel));
+    for (int t = 4 * grp; t < 4 * grp + 4; ++t)
+      if ((mask >> t) & 1) sel.t[sel.count++] = t;
+    if (sel.count == 0) continue;
+    ensemble_flip_kernel<<<grid_lr, 256, 0, st>>>(x, h->ens_x, height, width, sel);
+    ensemble_flip_kernel<<<grid_hr, 256, 0, st>>>(x2, h->ens_x2, s * height, s * width, sel);
     CUDA_TRY(cudaGetLastError());
     h->launches += 2;
     const int fh = grp == 0 ? height : width, fw = grp == 0 ? width : height;
-    if (forward_impl(h, h->ens_x, h->ens_x2, h->ens_y + (size_t)grp * 4 * hr, cnt, fh, fw, st)) return 1;
+    if (forward_impl(h, h->ens_x, h->ens_x2, h->ens_y + (size_t)grp * 4 * hr, sel.count, fh, fw, st)) return 1;
   }
   ensemble_reduce_kernel<<<(int)std::min<size_t>((hr + 255) / 256, (size_t)h->sm_count * 8), 256, 0, st>>>(
-      h->ens_y, h->ens_y + 4 * hr, y, s * height, s * width, flips);
+      h->ens_y, h->ens_y + 4 * hr, y, s * height, s * width, mask, divisor);
   CUDA_TRY(cudaGetLastError());
   h->launches++;
   return 0;
@@ -1447,7 +1544,14 @@ static int ensemble_impl(dcscn_handle* h, const float* x, const float* x2, doubl
 int dcscn_forward_ensemble(dcscn_handle* h, const float* x_dev, const float* x2_dev, double* y_dev, int height, int width,
                            int flips, void* stream) {
   if (!h || !x_dev || !x2_dev || !y_dev) return fail("dcscn_forward_ensemble: null argument");
-  return ensemble_impl(h, x_dev, x2_dev, y_dev, height, width, flips, (cudaStream_t)stream);
+  if (flips < 1 || flips > 8) return fail("forward_ensemble: flips must be 1..8 (got %d)", flips);
+  return ensemble_impl(h, x_dev, x2_dev, y_dev, height, width, (1 << flips) - 1, (double)flips, (cudaStream_t)stream);
+}
+
+int dcscn_forward_ensemble_partial(dcscn_handle* h, const float* x_dev, const float* x2_dev, double* y_dev, int height,
+                                   int width, int transform_mask, void* stream) {
+  if (!h || !x_dev || !x2_dev || !y_dev) return fail("dcscn_forward_ensemble_partial: null argument");
+  return ensemble_impl(h, x_dev, x2_dev, y_dev, height, width, transform_mask, 1.0, (cudaStream_t)stream);
 }
 
 int dcscn_forward_ensemble_host(dcscn_handle* h, const float* x, const float* x2, double* y, int height, int width, int flips) {
@@ -1468,7 +1572,8 @@ int dcscn_forward_ensemble_host(dcscn_handle* h, const float* x, const float* x2
   cudaStream_t st = 0;
   CUDA_TRY(cudaMemcpyAsync(h->ensio_x, x, lr * sizeof(float), cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaMemcpyAsync(h->ensio_x2, x2, hr * sizeof(float), cudaMemcpyHostToDevice, st));
-  if (ensemble_impl(h, h->ensio_x, h->ensio_x2, h->ensio_y, height, width, flips, st)) return 1;
+  if (flips < 1 || flips > 8) return fail("forward_ensemble: flips must be 1..8 (got %d)", flips);
+  if (ensemble_impl(h, h->ensio_x, h->ensio_x2, h->ensio_y, height, width, (1 << flips) - 1, (double)flips, st)) return 1;
   CUDA_TRY(cudaMemcpyAsync(y, h->ensio_y, hr * sizeof(double), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   return 0;
@@ -1560,6 +1665,7 @@ int dcscn_set_option(dcscn_handle* h, const char* key, int64_t value) {
     if (value != 64 && value != 32) return fail("kc must be 64 or 32");
     if (h->kc != (int)value) {
       h->kc = (int)value;
+      h->cap_px = 0;
       h->params_dirty = true;  // weight tiles depend on KC
       h->plans.clear();
       h->last_plan = nullptr;
@@ -1567,11 +1673,18 @@ int dcscn_set_option(dcscn_handle* h, const char* key, int64_t value) {
   } else if (k == "halo_base") {
     h->halo_base = (int)value;
   } else if (k == "halo") {
-    if (value < 0 || value > 2) return fail("halo must be 0, 1 or 2");
+    if (value < 0 || value > 3) return fail("halo must be 0, 1, 2 or 3");
+    if ((h->halo == 3) != (value == 3)) {   // the streaming kernel caps column tiles at 160: re-tile and re-pack
+      h->params_dirty = true;
+      h->cap_px = 0;                        // the fused R-CNN1 partial planes may change size
+    }
+    h->plans.clear();
+    h->last_plan = nullptr;
     h->halo = (int)value;
   } else if (k == "pair") {
     if (h->pair != (value ? 1 : 0)) {
       h->pair = value ? 1 : 0;
+      h->cap_px = 0;
       h->params_dirty = true;   // the two kernels use different packed weight layouts
       h->plans.clear();
       h->last_plan = nullptr;
@@ -1709,11 +1822,21 @@ int dcscn_set_adam_step(dcscn_handle* h, int64_t step) {
   return 0;
 }
 
+int dcscn_reset_optimizer(dcscn_handle* h) {
+  if (!h) return fail("dcscn_reset_optimizer: null argument");
+  if (!h->train || h->train->total == 0) return 0;   // no optimizer state exists yet: slots start at zero anyway
+  CUDA_TRY(cudaSetDevice(h->cfg.device_id));
+  CUDA_TRY(cudaMemset(h->train->d_m, 0, h->train->total * sizeof(float)));
+  CUDA_TRY(cudaMemset(h->train->d_v, 0, h->train->total * sizeof(float)));
+  h->train->step = 0;
+  return 0;
+}
+
 int dcscn_grad_buffer(dcscn_handle* h, float** dev_ptr, int64_t* count) {
   if (!h || !dev_ptr || !count) return fail("dcscn_grad_buffer: null argument");
   if (!h->train || h->train->total == 0) return fail("dcscn_grad_buffer: no train step has run yet");
   *dev_ptr = h->train->d_g;
-  *count = (int64_t)h->train->total;
+  *count = (int64_t)h->train->total + 2;   // gradients of every trainable, then {image_loss, mse} of the last step
   return 0;
 }
 
@@ -1721,6 +1844,12 @@ int dcscn_apply_gradients(dcscn_handle* h, float lr, void* stream) {
   if (!h) return fail("dcscn_apply_gradients: null argument");
   CUDA_TRY(cudaSetDevice(h->cfg.device_id));
   return apply_gradients_impl(h, lr, true, (cudaStream_t)stream);
+}
+
+int dcscn_apply_gradients_avg(dcscn_handle* h, float lr, float grad_scale, float* out_loss, float* out_mse, void* stream) {
+  if (!h) return fail("dcscn_apply_gradients_avg: null argument");
+  CUDA_TRY(cudaSetDevice(h->cfg.device_id));
+  return apply_gradients_impl(h, lr, true, (cudaStream_t)stream, grad_scale, out_loss, out_mse);
 }
 
 float dcscn_last_grad_norm(dcscn_handle* h) { return (h && h->train) ? h->train->last_norm : 0.f; }

@@ -72,7 +72,7 @@ __device__ __forceinline__ void epilogue_store16(const EpiParams& e, const ConvG
   }
   if (e.keep_prob < 1.0f) {
     const float inv_keep = 1.0f / e.keep_prob;
-    const uint64_t base = ((uint64_t)((size_t)img * g.H + y) * g.W + x) * (uint64_t)n_total + cg;
+    const uint64_t base = ((uint64_t)((size_t)img * g.H + y) * g.W + x) * (uint64_t)(e.drop_ntotal ? e.drop_ntotal : n_total) + cg;
 #pragma unroll
     for (int i = 0; i < 16; ++i)
       v[i] = dropout_keep(e.drop_seed, e.drop_layer, base + i, e.keep_prob) ? v[i] * inv_keep : 0.f;
@@ -160,7 +160,7 @@ __device__ __forceinline__ void rdot_accumulate16(const EpiParams& e, const floa
 }
 
 __device__ __forceinline__ void rdot_flush(const EpiParams& e, const ConvGeom& g, int img, int y, int x, int ij,
-                                           float (&v)[9]) {
+                                           int part, float (&v)[9]) {
   const int r = e.d2s_r;
   const int i = ij / r, j = ij - i * r;
   const size_t HR_H = (size_t)g.H * r, HR_W = (size_t)g.W * r;
@@ -168,9 +168,13 @@ __device__ __forceinline__ void rdot_flush(const EpiParams& e, const ConvGeom& g
   const size_t pix = ((size_t)img * HR_H + (size_t)(y * r + i)) * HR_W + (size_t)(x * r + j);
 #pragma unroll
   for (int tap = 0; tap < 9; ++tap) {
-    if (tap < e.rdot_taps) e.rdot_out[(size_t)tap * plane + pix] = v[tap];
+    if (tap < e.rdot_taps) e.rdot_out[(size_t)(part * e.rdot_taps + tap) * plane + pix] = v[tap];
     v[tap] = 0.f;
   }
+}
+__device__ __forceinline__ void rdot_flush(const EpiParams& e, const ConvGeom& g, int img, int y, int x, int ij,
+                                           float (&v)[9]) {
+  rdot_flush(e, g, img, y, x, ij, 0, v);
 }
 
 }  // namespace dcscn

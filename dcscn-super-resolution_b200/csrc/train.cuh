@@ -678,6 +678,14 @@ __global__ void __launch_bounds__(256) grad_finalize_kernel(const GradFinalizePa
   if (threadIdx.x == 0) atomicAdd(p.norm_sq, s[0]);
 }
 
+// Data-parallel training: this rank's image_loss and mse as two extra floats behind the flat gradient buffer, so that ONE
+// all-reduce carries gradients and both scalars.  scal = {sum diff^2, -, sum |diff|}.
+__global__ void loss_tail_kernel(const double* scal, double inv_count, int l1_loss, float* tail) {
+  const double mse = scal[0] * inv_count;
+  tail[0] = (float)(l1_loss ? scal[2] * inv_count : mse);
+  tail[1] = (float)mse;
+}
+
 // tf.train.AdamOptimizer (DCSCN.py:388): m = b1*m + (1-b1)*g; v = b2*v + (1-b2)*g*g; w -= lr_t * m / (sqrt(v) + eps),
 // lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t) (host), g = clipped gradient = g * clip / max(norm, clip).
 struct AdamParams {

@@ -50,11 +50,11 @@ class DcscnConfig(ctypes.Structure):
 
 EXPORTED_SYMBOLS = [
     "dcscn_create", "dcscn_destroy", "dcscn_last_error", "dcscn_num_params", "dcscn_param_info",
-    "dcscn_set_param", "dcscn_get_param", "dcscn_forward", "dcscn_forward_host", "dcscn_forward_ensemble", "dcscn_forward_ensemble_host", "dcscn_get_activation",
+    "dcscn_set_param", "dcscn_get_param", "dcscn_forward", "dcscn_forward_host", "dcscn_forward_ensemble", "dcscn_forward_ensemble_host", "dcscn_forward_ensemble_partial", "dcscn_get_activation",
     "dcscn_set_option", "dcscn_get_timings", "dcscn_launch_count", "dcscn_device_bytes",
     "dcscn_train_step", "dcscn_train_step_host", "dcscn_get_grad", "dcscn_get_adam_slot", "dcscn_set_adam_slot", "dcscn_get_adam_step",
     "dcscn_set_adam_step", "dcscn_last_grad_norm",
-    "dcscn_dropout_mask", "dcscn_grad_buffer", "dcscn_apply_gradients",
+    "dcscn_dropout_mask", "dcscn_grad_buffer", "dcscn_apply_gradients", "dcscn_apply_gradients_avg", "dcscn_reset_optimizer",
 ]
 
 _lib = None
@@ -87,6 +87,7 @@ def load_library(path=None):
     lib.dcscn_forward_host.argtypes = [vp, vp, vp, vp, ci, ci, ci]
     lib.dcscn_forward_ensemble.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp]
     lib.dcscn_forward_ensemble_host.argtypes = [vp, vp, vp, vp, ci, ci, ci]
+    lib.dcscn_forward_ensemble_partial.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp]
     lib.dcscn_get_activation.argtypes = [vp, ctypes.c_char_p, fp, c64]
     lib.dcscn_set_option.argtypes = [vp, ctypes.c_char_p, c64]
     lib.dcscn_get_timings.argtypes = [vp, fp, ci, ctypes.POINTER(ci), ctypes.c_char_p, ci]
@@ -103,6 +104,8 @@ def load_library(path=None):
     lib.dcscn_dropout_mask.argtypes = [vp, ctypes.c_char_p, u32, ci, ci, ci, ctypes.POINTER(ctypes.c_uint8), c64]
     lib.dcscn_grad_buffer.argtypes = [vp, ctypes.POINTER(fp), ctypes.POINTER(c64)]
     lib.dcscn_apply_gradients.argtypes = [vp, cf, vp]
+    lib.dcscn_reset_optimizer.argtypes = [vp]
+    lib.dcscn_apply_gradients_avg.argtypes = [vp, cf, cf, fp, fp, vp]
     lib.dcscn_launch_count.argtypes = [vp]
     lib.dcscn_launch_count.restype = c64
     lib.dcscn_device_bytes.argtypes = [vp]
@@ -228,6 +231,44 @@ class Engine:
                                                          int(flips)))
         return y
 
+    def forward_ensemble(self, x, x2, flips, out=None, stream=None):
+        """Device-resident self-ensemble of one image: x [h,w] / x2 [s*h,s*w] fp32 CUDA tensors -> float64 [s*h,s*w]."""
+        import torch
+        h, w = int(x.shape[0]), int(x.shape[1])
+        s = int(self.config.scale)
+        if out is None:
+            out = torch.empty((s * h, s * w), dtype=torch.float64, device=x.device)
+        st = stream if stream is not None else torch.cuda.current_stream(x.device).cuda_stream
+        self._check(self.lib.dcscn_forward_ensemble(self.handle, x.data_ptr(), x2.data_ptr(), out.data_ptr(), h, w, int(flips),
+                                                    ctypes.c_void_p(st)))
+        return out
+
+    def forward_ensemble_sharded(self, x, x2, flips, out=None):
+        """The same ensemble with the transforms spread over the ranks of the current torch.distributed job (rank r
+        takes transforms r, r + world, ...): every rank runs its share as batched forwards, writes the float64 SUM of
+        its inverse-transformed outputs, ONE all-reduce (NCCL sum over NVLink) combines them and the mean is taken.
+        Every rank returns the full result.  x / x2: the SAME image on every rank (fp32 CUDA tensors)."""
+        import torch
+        import torch.distributed as dist
+        rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_available() and dist.is_initialized() else (0, 1)
+        h, w = int(x.shape[0]), int(x.shape[1])
+        s = int(self.config.scale)
+        if out is None:
+            out = torch.empty((s * h, s * w), dtype=torch.float64, device=x.device)
+        mask = 0
+        for t in range(rank, int(flips), world):
+            mask |= 1 << t
+        st = torch.cuda.current_stream(x.device).cuda_stream
+        if mask:
+            self._check(self.lib.dcscn_forward_ensemble_partial(self.handle, x.data_ptr(), x2.data_ptr(), out.data_ptr(), h, w,
+                                                                mask, ctypes.c_void_p(st)))
+        else:
+            out.zero_()          # more ranks than transforms: this rank contributes nothing
+        if world > 1:
+            dist.all_reduce(out, op=dist.ReduceOp.SUM)
+        out.div_(float(flips))
+        return out
+
     def train_step_host(self, x, x2, y, lr, seed, apply_update=True):
         """One optimisation step on host fp32 arrays x [n,h,w,1], x2 / y [n,sh,sw,1]; returns (image_loss, mse)."""
         xa, x2a, ya = _host_array(x), _host_array(x2), _host_array(y)
@@ -268,22 +309,26 @@ class Engine:
         st = stream if stream is not None else torch.cuda.current_stream().cuda_stream
         self._check(self.lib.dcscn_apply_gradients(self.handle, float(lr), ctypes.c_void_p(st)))
 
-    def train_step_data_parallel(self, x, x2, y, lr, seed):
-        """One optimisation step with the mini-batch sharded over the ranks of the current torch.distributed job:
-        local gradients -> ONE flat all-reduce (mean) -> identical clip + Adam on every rank.  Returns the
-        job-wide (image_loss, mse)."""
+    def apply_gradients_avg(self, lr, grad_scale, stream=None):
+        """After the all-reduce(sum) of `grad_tensor()`: scale to the mean, clip + Adam; returns (image_loss, mse) means."""
         import torch
+        st = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        loss, mse = ctypes.c_float(), ctypes.c_float()
+        self._check(self.lib.dcscn_apply_gradients_avg(self.handle, float(lr), float(grad_scale), ctypes.byref(loss),
+                                                       ctypes.byref(mse), ctypes.c_void_p(st)))
+        return float(loss.value), float(mse.value)
+
+    def train_step_data_parallel(self, x, x2, y, lr, seed):
+        """One optimisation step with the mini-batch sharded over the ranks of the current torch.distributed job (equal
+        shards): local gradients -> ONE flat all-reduce carrying [gradients | loss | mse] -> identical mean, clip and
+        Adam on every rank.  Returns the job-wide (image_loss, mse)."""
         import torch.distributed as dist
         fn = self.train_step if hasattr(x, "is_cuda") and x.is_cuda else self.train_step_host
         loss, mse = fn(x, x2, y, lr, seed, apply_update=False)
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            world = dist.get_world_size()
             g = self.grad_tensor()
             dist.all_reduce(g, op=dist.ReduceOp.SUM)
-            g.mul_(1.0 / world)
-            s = torch.tensor([loss, mse], dtype=torch.float64, device=g.device)
-            dist.all_reduce(s, op=dist.ReduceOp.SUM)
-            loss, mse = float(s[0]) / world, float(s[1]) / world
+            return self.apply_gradients_avg(lr, 1.0 / dist.get_world_size())
         self.apply_gradients(lr)
         return loss, mse
 
@@ -313,6 +358,10 @@ class Engine:
     @adam_step.setter
     def adam_step(self, t):
         self._check(self.lib.dcscn_set_adam_step(self.handle, int(t)))
+
+    def reset_optimizer(self):
+        """Adam slots back to zero and update count to 0 (what re-running the initializer does in the reference)."""
+        self._check(self.lib.dcscn_reset_optimizer(self.handle))
 
     @property
     def last_grad_norm(self):

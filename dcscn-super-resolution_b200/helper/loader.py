@@ -53,18 +53,25 @@ class _ShuffledOrder:
     """Serves 0..count-1 in a fresh random permutation per pass (loader.py:259-275, 300-308)."""
 
     count = 0
+    shard_rank, shard_world, order_rng = 0, 1, None
+
+    def set_shard(self, rank, world, seed):
+        """Data-parallel training: all ranks draw the SAME permutation (private generator, shared seed) and rank r
+        serves its elements r, r + world, ... - the ranks' patches are disjoint and together cover a pass."""
+        self.shard_rank, self.shard_world, self.order_rng = rank, world, random.Random(seed)
+        self.batch_index = None
 
     def init_batch_index(self, shuffle=True):
         order = list(range(self.count))
         if shuffle:
-            random.shuffle(order)
-        self.batch_index, self.index = order, 0
+            (self.order_rng or random).shuffle(order)
+        self.batch_index, self.index = order, self.shard_rank
 
     def get_next_image_no(self):
         if getattr(self, "batch_index", None) is None or self.index >= self.count:
             self.init_batch_index()
-        number = self.batch_index[self.index]
-        self.index += 1
+        number = self.batch_index[min(self.index, self.count - 1)]
+        self.index += self.shard_world
         return number
 
 

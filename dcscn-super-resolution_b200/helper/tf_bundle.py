@@ -304,7 +304,10 @@ def write_bundle(prefix, tensors, block_size=4096):
     names = sorted(tensors.keys(), key=lambda s: s.encode("utf-8"))
     entries = []
     offset = 0
-    with open(prefix + ".data-00000-of-00001", "wb") as f:
+    # both files are written under temporary names and renamed into place, the index LAST: a reader (or a crash)
+    # never sees an index that points into a half-written data file
+    tmp_tag = ".tmp%d" % os.getpid()
+    with open(prefix + ".data-00000-of-00001" + tmp_tag, "wb") as f:
         for name in names:
             src = np.asarray(tensors[name], dtype="<f4")
             shape = src.shape                      # () for scalars such as beta1_power (ascontiguousarray would make it (1,))
@@ -358,5 +361,7 @@ def write_bundle(prefix, tensors, block_size=4096):
     footer += struct.pack("<Q", _TABLE_MAGIC)
     out.extend(footer)
 
-    with open(prefix + ".index", "wb") as f:
+    with open(prefix + ".index" + tmp_tag, "wb") as f:
         f.write(bytes(out))
+    os.replace(prefix + ".data-00000-of-00001" + tmp_tag, prefix + ".data-00000-of-00001")
+    os.replace(prefix + ".index" + tmp_tag, prefix + ".index")

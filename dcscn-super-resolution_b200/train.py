@@ -32,6 +32,7 @@ def train(model, flags, trial):
     model.init_all_variables()
     if flags.load_model_name != "":
         model.load_model(flags.load_model_name, output_log=True, restore_optimizer=True)
+    model.broadcast_variables()   # data-parallel ranks start from rank 0's weights (no-op for one process)
     model.init_train_step()
     model.init_epoch_index()
     model_updated = True
@@ -70,6 +71,11 @@ def main(not_parsed_args):
         print("Unknown args:%s" % not_parsed_args)
         exit()
 
+    # `torchrun --nproc-per-node N train.py ...`: one process per GPU, mini-batch split over the ranks, one gradient
+    # all-reduce per step (NCCL); a plain `python train.py` stays single-process
+    rank, world = DCSCN.init_distributed(FLAGS)
+    if world > 1:
+        print("data-parallel rank %d of %d on GPU %d" % (rank, world, FLAGS.gpu_device_id))
     model = DCSCN.SuperResolution(FLAGS, model_name=FLAGS.model_name)
     if FLAGS.build_batch:
         model.load_datasets(FLAGS.data_dir + "/" + FLAGS.dataset, FLAGS.batch_dir + "/" + FLAGS.dataset,

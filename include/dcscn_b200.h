@@ -89,6 +89,11 @@ int dcscn_forward_host(dcscn_handle* h, const float* x, const float* x2, float* 
 int dcscn_forward_ensemble(dcscn_handle* h, const float* x_dev, const float* x2_dev, double* y_dev, int height, int width,
                            int flips, void* stream);
 int dcscn_forward_ensemble_host(dcscn_handle* h, const float* x, const float* x2, double* y, int height, int width, int flips);
+/* One rank's share of the same ensemble when the 8 transforms are spread over several GPUs: bit t of
+ * `transform_mask` selects transform t; y receives the float64 SUM of the selected inverse-transformed outputs (no
+ * division), ready for one ncclAllReduce(sum) over the ranks followed by the division by the ensemble size. */
+int dcscn_forward_ensemble_partial(dcscn_handle* h, const float* x_dev, const float* x2_dev, double* y_dev, int height,
+                                   int width, int transform_mask, void* stream);
 
 /*
  * sess.run([self.training_optimizer, self.image_loss, self.mse], {x, x2, y, lr, dropout: keep, is_training: 1})
@@ -112,12 +117,19 @@ int dcscn_get_adam_slot(dcscn_handle* h, const char* name, int slot, float* host
 int dcscn_set_adam_slot(dcscn_handle* h, const char* name, int slot, const float* host_data, int64_t numel);
 int dcscn_get_adam_step(dcscn_handle* h, int64_t* step);
 int dcscn_set_adam_step(dcscn_handle* h, int64_t step);
-/* Data-parallel training: after dcscn_train_step(..., apply_update = 0) on every rank, all-reduce (average) the flat
- * gradient buffer returned here (device pointer, `count` floats, every trainable in dcscn_param_info order) - e.g.
- * ncclAllReduce over NVLink - then call dcscn_apply_gradients on every rank: global-norm clip of the averaged gradient
- * + Adam, identically everywhere. */
+/* tf.global_variables_initializer() on the optimizer's variables (helper/tf_graph.py:73-75 re-runs it for every trial of
+ * train.py:100-103): both Adam slots of every variable back to zero and the update count t to 0. */
+int dcscn_reset_optimizer(dcscn_handle* h);
+/* Data-parallel training: after dcscn_train_step(..., apply_update = 0) on every rank, all-reduce the flat buffer
+ * returned here (device pointer, `count` floats: the gradient of every trainable in dcscn_param_info order followed by
+ * this rank's {image_loss, mse}) - ONE ncclAllReduce(sum) over NVLink - then call dcscn_apply_gradients_avg on every
+ * rank with grad_scale = 1 / ranks: it scales the summed gradients to their mean, applies the global-norm clip of the
+ * averaged gradient + Adam identically everywhere and returns the job-wide mean loss / mse.
+ * Every rank must hold the same number of patches (each normalises by its own pixel count).
+ * dcscn_apply_gradients is the same with grad_scale = 1 (gradients already averaged by the caller). */
 int dcscn_grad_buffer(dcscn_handle* h, float** dev_ptr, int64_t* count);
 int dcscn_apply_gradients(dcscn_handle* h, float lr, void* stream);
+int dcscn_apply_gradients_avg(dcscn_handle* h, float lr, float grad_scale, float* out_loss, float* out_mse, void* stream);
 /* Global gradient norm of the last train step (what clip_by_global_norm computed). */
 float dcscn_last_grad_norm(dcscn_handle* h);
 /* The keep mask (1 = kept) the train step with `seed` applies to `tensor` ("CNNi", "A1", "B1", "B2"), [n,h,w,C] uint8:
@@ -133,8 +145,9 @@ int dcscn_get_activation(dcscn_handle* h, const char* tensor, float* host_data, 
 /* Options: "conv_impl" 0 = tcgen05 (default), 1 = CUDA-core fp32 validation kernels;
  *          "kc" 64 | 32 = K-chunk (channels per pipeline stage) of the tensor-core kernel;
  *          "seg_chunks" = pipeline stages per fp32-promotion segment (default 0 = automatic: 2, or 3 for thin layers);
- *          "halo" 0 | 1 | 2 = 3x3 layers: one A tile per tap (0), three 18x8 boxes per channel chunk (1), or one
- *                     18x10 box per channel chunk serving all nine taps (2, default);
+ *          "halo" 0 | 1 | 2 | 3 = 3x3 layers: one A tile per tap (0), three 18x8 boxes per channel chunk (1), one
+ *                     18x10 box per channel chunk serving all nine taps with two-pass segments (2), or the same box with
+ *                     streaming weight stages and split correction / dominant accumulators (3, default);
  *          "pair" 1 | 0 = CTA-pair kernel (tcgen05 cta_group::2, weight tiles split across two SMs; default 1);
  *          "cluster" 1 | 2 | 4 = CTAs per cluster multicasting weight tiles in the single-CTA kernel (default 1);
  *          "fuse_last" 1 | 0 = compute the per-pixel half of R-CNN1 inside the last Up-PS epilogue (default 1);

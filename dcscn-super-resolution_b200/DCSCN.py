@@ -432,6 +432,7 @@ class SuperResolution:
         else:
             self.train.load_batch_counts()
         self.train.load_all_batch_images()
+        self._patches_on_device = False   # uploaded to HBM by init_epoch_index once the engine exists
 
     def init_epoch_index(self):
         """DCSCN.py:175-184"""
@@ -447,6 +448,16 @@ class SuperResolution:
         self.batch_input = self.local_batch * [None]
         self.batch_input_bicubic = self.local_batch * [None]
         self.batch_true = self.local_batch * [None]
+        # grid-patch data sets (--build_batch): the uint8 patch arrays move to HBM once and a mini-batch becomes an index
+        # list + one gather launch per tensor (helper/engine.py: set_patch_store / train_step_indexed)
+        self.batch_indices = None
+        if (isinstance(self.train, loader.BatchDataSets) and self.engine is not None and self.train.count > 0
+                and not self.depthwise_separable):
+            if not getattr(self, "_patches_on_device", False):
+                self.engine.set_patch_store(self.train.input_images, self.train.input_interpolated_images,
+                                            self.train.true_images)
+                self._patches_on_device = True
+            self.batch_indices = np.zeros(self.local_batch, dtype=np.int64)
         self.training_psnr_sum = 0
         self.training_loss_sum = 0
         self.training_step = 0
@@ -454,6 +465,10 @@ class SuperResolution:
 
     def build_input_batch(self):
         """DCSCN.py:186-190"""
+        if getattr(self, "batch_indices", None) is not None:            # patches already live in HBM: draw the indices only
+            for i in range(len(self.batch_indices)):
+                self.batch_indices[i] = self.train.get_next_image_no()
+            return
         for i in range(len(self.batch_input)):
             self.batch_input[i], self.batch_input_bicubic[i], self.batch_true[i] = self.train.load_batch_image(
                 self.max_value)
@@ -464,15 +479,23 @@ class SuperResolution:
         # data parallel: every rank holds its own batch_num / world patches (init_epoch_index); the gradients meet in
         # one flat all-reduce before the (identical) clip + Adam update on every rank
         rank, world = _dist_rank_world()
-        x = np.ascontiguousarray(np.stack(self.batch_input), dtype=np.float32)
-        x2 = np.ascontiguousarray(np.stack(self.batch_input_bicubic), dtype=np.float32)
-        y = np.ascontiguousarray(np.stack(self.batch_true), dtype=np.float32)
-        if x.ndim == 3:
-            x, x2, y = x[..., None], x2[..., None], y[..., None]
-        if world > 1:
-            image_loss, mse = self.engine.train_step_data_parallel(x, x2, y, lr=self.lr, seed=self.step * world + rank)
+        if getattr(self, "batch_indices", None) is not None:
+            if world > 1:
+                image_loss, mse = self.engine.train_step_data_parallel(None, None, None, lr=self.lr, seed=self.step * world + rank,
+                                                                       indices=self.batch_indices, max_value=self.max_value)
+            else:
+                image_loss, mse = self.engine.train_step_indexed(self.batch_indices, lr=self.lr, seed=self.step,
+                                                                 max_value=self.max_value)
         else:
-            image_loss, mse = self.engine.train_step_host(x, x2, y, lr=self.lr, seed=self.step, apply_update=True)
+            x = np.ascontiguousarray(np.stack(self.batch_input), dtype=np.float32)
+            x2 = np.ascontiguousarray(np.stack(self.batch_input_bicubic), dtype=np.float32)
+            y = np.ascontiguousarray(np.stack(self.batch_true), dtype=np.float32)
+            if x.ndim == 3:
+                x, x2, y = x[..., None], x2[..., None], y[..., None]
+            if world > 1:
+                image_loss, mse = self.engine.train_step_data_parallel(x, x2, y, lr=self.lr, seed=self.step * world + rank)
+            else:
+                image_loss, mse = self.engine.train_step_host(x, x2, y, lr=self.lr, seed=self.step, apply_update=True)
         self.training_loss_sum += image_loss
         self.training_psnr_sum += util.get_psnr(mse, max_value=self.max_value)
         self.training_step += 1

@@ -361,6 +361,28 @@ __global__ void planes_to_f32_kernel(const __half* hi, const __half* lo, float* 
   }
 }
 
+// ------------------------------------------------------------- training patch store ---------------------------
+// What `build_input_batch` + the feed of `train_batch` did on the host (DCSCN.py:186-190, 415-420; patches of
+// loader.BatchDataSets, loader.py:236-249): the uint8 patch arrays live in HBM, one launch gathers the mini-batch's
+// patches by index into fp32 NHWC tensors (x scale = max_value / 255, loader.py:251-255), optionally mirrored left-right
+// (bit 31 of the index; the augmentation of loader.py:318-319).
+__global__ void __launch_bounds__(256) patch_gather_kernel(const uint8_t* __restrict__ store, const int* __restrict__ idx,
+                                                           float* __restrict__ out, int n, int H, int W, float scale) {
+  const long long per = (long long)H * W, total = per * n;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(e / per);
+    const int r = (int)(e - (long long)i * per);
+    const int code = __ldg(idx + i);
+    const long long k = code & 0x7FFFFFFF;
+    int src = r;
+    if (code < 0) {                                  // mirrored patch: column W - 1 - x
+      const int y = r / W, x = r - y * W;
+      src = y * W + (W - 1 - x);
+    }
+    out[e] = (float)__ldg(store + k * per + src) * scale;
+  }
+}
+
 // ------------------------------------------------------------- self-ensemble (DCSCN.py:547-586) --------------
 // The 8 transforms of helper/utilty.py:595-617 (`flip`) as index maps on an [H][W] image:
 //   0 identity, 1 flipud, 2 fliplr, 3 flipud(fliplr), 4 rot90(+1), 5 rot90(-1), 6 flipud(rot90(+1)) = transpose,

@@ -32,7 +32,8 @@ __host__ __device__ inline size_t tc_halo2_misc_bytes() { return 1024 + kH2BarBy
 template <int NPLANES>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
-                     const __grid_constant__ CUtensorMap tm_w, const ConvTCParams p, const int num_a, const int num_b) {
+                     const __grid_constant__ CUtensorMap tm_w, const ConvTCParams p, const int num_a, const int num_b,
+                     const int wide_w) {
   constexpr int KC = 64;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -129,7 +130,8 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
       // ============================== TMA producer: weight halves (both CTAs) ==============================
       if (lane == 0) {
         ptx::prefetch_tensormap(&tm_w);
-        const int wrows = NPLANES * half_rows;               // rows of one (tile, rank) block in the packed weights
+        // rows of one (tile, rank) block in the packed weights: 128-byte rows, or 1024-byte rows of the wide map
+        const int wrows = wide_w ? (NPLANES * half_rows) >> 3 : NPLANES * half_rows;
         int b = 0;
         uint32_t phb = 0;
         for (int item = cluster_id; item < num_items; item += num_clusters) {

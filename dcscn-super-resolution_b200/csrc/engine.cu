@@ -92,6 +92,8 @@ struct TcLayer {
   int packed_kc = 0, packed_planes = 0;
   __half* d_wpair = nullptr;    // CTA-pair layout [n_tile][tap][chunk][rank][plane][n_pad/2 x 64]
   CUtensorMap tm_w;             // 2-D map over d_wpair (rows of 128 bytes)
+  CUtensorMap tm_w_wide;        // the same bytes as rows of 1024 bytes (fp32 elements, no swizzle): fewer, longer TMA rows
+  bool has_wide = false;
   bool has_pair = false;
   int* d_pair_src = nullptr;    // training: flat parameter index behind every hi-plane element of d_wpair (-1 = zero)
   size_t pair_src_n = 0;
@@ -116,6 +118,8 @@ struct TcLaunch {
   CUtensorMap t1_hi, t1_lo;
   int halo1_na = 0, halo1_nb = 0, halo1_seg = 1;
   size_t halo1_smem = 0;
+  CUtensorMap tm_w_wide;
+  bool has_wide = false;
   bool halo2 = false;            // streaming halo kernel (split correction / dominant accumulators), default
   int halo2_na = 0, halo2_nb = 0, halo2_seg = 1;
   size_t halo2_smem = 0;
@@ -190,6 +194,15 @@ struct dcscn_handle {
   float* vbuf = nullptr;             // tap-planar partial products of the fused R-CNN1 [9][N][sH][sW]
   float *io_x = nullptr, *io_x2 = nullptr, *io_y = nullptr;  // staging for forward_host
   size_t io_cap = 0;
+  // training patch store (dcscn_patch_store_set): uint8 patches resident in HBM + the mini-batch's index list
+  uint8_t *ps_lr = nullptr, *ps_bic = nullptr, *ps_true = nullptr;
+  int64_t ps_count = 0;
+  int ps_h = 0, ps_w = 0;
+  int* ps_idx = nullptr;
+  int ps_idx_cap = 0;
+  cudaStream_t copy_stream = nullptr;  // forward_host: x2 (only read by the last kernel) rides in beside the conv stack
+  cudaEvent_t x2_ready = nullptr;
+  bool wait_x2 = false;                // the next forward's last kernel waits for x2_ready
   int64_t device_bytes = 0;
 
   // depthwise-separable graphs: fp32 buffers + per-layer device filters
@@ -211,6 +224,7 @@ struct dcscn_handle {
   int halo = 3;                      // 3x3 layers: halo-reuse CTA-pair kernel, 1 = three 18x8 boxes, 2 = one 18x10 box per chunk
                                      // (two-pass segments), 3 = the same box with streaming stages (conv_tc_halo2.cuh)
   int halo_base = 0;                 // single-box variant: set the descriptor base-offset field
+  int wmap_wide = 0;                 // streaming kernel: fetch weight stages as rows of 1024 bytes instead of 128
   int timing = 0;
   int fuse_last = 1;                 // fold the per-pixel half of R-CNN1 into the last Up-PS epilogue
   std::vector<cudaEvent_t> ev;       // timing events (launch boundaries of the last forward)
@@ -476,6 +490,17 @@ static int pack_tc_layer(dcscn_handle* h, TcLayer& t) {
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (weights, layer %s) failed: %d", t.name.c_str(), (int)r);
     t.has_pair = true;
+    t.has_wide = false;
+    const size_t stage_bytes = (size_t)NPL * half_rows * 128;
+    if (stage_bytes % 1024 == 0 && stage_bytes / 1024 <= 256) {
+      cuuint64_t wdims[2] = {256, (cuuint64_t)(pp.size() * 2 / 1024)};
+      cuuint64_t wstrides[1] = {1024};
+      cuuint32_t wbox[2] = {256, (cuuint32_t)(stage_bytes / 1024)};
+      r = h->encode(&t.tm_w_wide, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)t.d_wpair, wdims, wstrides, wbox, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      t.has_wide = (r == CUDA_SUCCESS);
+    }
   }
   if (upload(&t.d_bias, t.bias_host, h)) return 1;
   if (upload(&t.d_alpha, t.alpha_host, h)) return 1;
@@ -812,6 +837,8 @@ static int add_tc_launch(dcscn_handle* h, Plan* pl, const TcLayer& t, const __ha
   L.pair = t.has_pair && (h->sm_count % 2 == 0);
   if (L.pair) {
     L.tm_w = t.tm_w;
+    L.tm_w_wide = t.tm_w_wide;
+    L.has_wide = t.has_wide;
     const size_t pstage = tc_pair_stage_bytes(planes(h), t.n_pad);
     L.pair_stages = (int)std::min<size_t>(kMaxStages, budget / pstage);
     L.pair_smem = L.pair_stages * pstage + 1024 + 256 + kRdotSmemBytes;
@@ -1201,7 +1228,9 @@ static int launch_tc_halo2(dcscn_handle* h, const TcLaunch& L, cudaStream_t st) 
   p.g = L.hg;
   p.cluster_size = 2;
   p.seg_chunks = L.halo2_seg;
-  CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc_halo2_kernel<NPL>, L.t1_hi, L.t1_lo, L.tm_w, p, L.halo2_na, L.halo2_nb));
+  const bool wide = h->wmap_wide && L.has_wide;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc_halo2_kernel<NPL>, L.t1_hi, L.t1_lo, wide ? L.tm_w_wide : L.tm_w, p, L.halo2_na,
+                              L.halo2_nb, wide ? 1 : 0));
   return 0;
 }
 
@@ -1299,6 +1328,10 @@ static int forward_ds(dcscn_handle* h, const float* x, const float* x2, float* y
     HH = c.scale * H; WW = c.scale * W;
   }
   // R-CNN1 (no bias / activation) + x2
+  if (h->wait_x2) {
+    CUDA_TRY(cudaStreamWaitEvent(st, h->x2_ready, 0));
+    h->wait_x2 = false;
+  }
   if (launch_ds(h, h->layers[li], h->ds[li], h->ds_hr, h->ps_out, y, 1, 0, n, HH, WW, 0, 0, x2, st)) return 1;
   return 0;
 }
@@ -1341,6 +1374,10 @@ static int forward_impl(dcscn_handle* h, const float* x, const float* x2, float*
     if (mark(h, st)) return 1;
   }
   pl->ran_fused = fused;
+  if (h->wait_x2) {  // forward_host: x2 was copied on the side stream
+    CUDA_TRY(cudaStreamWaitEvent(st, h->x2_ready, 0));
+    h->wait_x2 = false;
+  }
   if (fused) {  // R-CNN1 second half: 9-tap gather of the tap-planar partial products + x2
     ConvGatherParams p = pl->gather;
     p.x2 = x2;
@@ -1430,6 +1467,9 @@ int dcscn_destroy(dcscn_handle* h) {
   cudaFree(h->io_x);
   cudaFree(h->io_x2);
   cudaFree(h->io_y);
+  cudaFree(h->ps_lr); cudaFree(h->ps_bic); cudaFree(h->ps_true); cudaFree(h->ps_idx);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->x2_ready) cudaEventDestroy(h->x2_ready);
   delete h;
   return 0;
 }
@@ -1492,9 +1532,22 @@ int dcscn_forward_host(dcscn_handle* h, const float* x, const float* x2, float* 
     h->io_cap = hr;
   }
   cudaStream_t st = 0;
+  if (!h->copy_stream) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->x2_ready, cudaEventDisableTiming));
+  }
+  // x feeds the first kernel; x2 (4x / 9x / 16x the bytes) is only read by the very last one, so it is copied on a second
+  // stream while the conv stack runs and the last kernel waits for it
   CUDA_TRY(cudaMemcpyAsync(h->io_x, x, lr * sizeof(float), cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(h->io_x2, x2, hr * sizeof(float), cudaMemcpyHostToDevice, st));
-  if (forward_impl(h, h->io_x, h->io_x2, h->io_y, n, height, width, st)) return 1;
+  CUDA_TRY(cudaMemcpyAsync(h->io_x2, x2, hr * sizeof(float), cudaMemcpyHostToDevice, h->copy_stream));
+  CUDA_TRY(cudaEventRecord(h->x2_ready, h->copy_stream));
+  h->wait_x2 = true;
+  const int rc = forward_impl(h, h->io_x, h->io_x2, h->io_y, n, height, width, st);
+  h->wait_x2 = false;
+  if (rc) {
+    cudaStreamSynchronize(h->copy_stream);
+    return 1;
+  }
   CUDA_TRY(cudaMemcpyAsync(y, h->io_y, hr * sizeof(float), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   return 0;
@@ -1670,6 +1723,8 @@ int dcscn_set_option(dcscn_handle* h, const char* key, int64_t value) {
       h->plans.clear();
       h->last_plan = nullptr;
     }
+  } else if (k == "wmap_wide") {
+    h->wmap_wide = value ? 1 : 0;
   } else if (k == "halo_base") {
     h->halo_base = (int)value;
   } else if (k == "halo") {
@@ -1768,6 +1823,88 @@ int dcscn_train_step_host(dcscn_handle* h, const float* x, const float* x2, cons
   CUDA_TRY(cudaMemcpyAsync(h->io_x2, x2, hr_px * sizeof(float), cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaMemcpyAsync(h->io_y, y, hr_px * sizeof(float), cudaMemcpyHostToDevice, st));
   return train_step_impl(h, h->io_x, h->io_x2, h->io_y, n, height, width, lr, seed, apply_update, out_loss, out_mse, st);
+}
+
+int dcscn_patch_store_set(dcscn_handle* h, const uint8_t* lr, const uint8_t* bicubic, const uint8_t* truth, int64_t count,
+                          int patch_height, int patch_width) {
+  if (!h || !lr || !bicubic || !truth) return fail("dcscn_patch_store_set: null argument");
+  if (count <= 0 || count > 0x7FFFFFFF || patch_height <= 0 || patch_width <= 0) return fail("dcscn_patch_store_set: bad size");
+  CUDA_TRY(cudaSetDevice(h->cfg.device_id));
+  cudaFree(h->ps_lr); cudaFree(h->ps_bic); cudaFree(h->ps_true);
+  h->ps_lr = h->ps_bic = h->ps_true = nullptr;
+  h->ps_count = 0;
+  const size_t s2 = (size_t)h->cfg.scale * h->cfg.scale;
+  const size_t lr_b = (size_t)count * patch_height * patch_width, hr_b = lr_b * s2;
+  CUDA_TRY(cudaMalloc((void**)&h->ps_lr, lr_b));
+  CUDA_TRY(cudaMalloc((void**)&h->ps_bic, hr_b));
+  CUDA_TRY(cudaMalloc((void**)&h->ps_true, hr_b));
+  CUDA_TRY(cudaMemcpy(h->ps_lr, lr, lr_b, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(h->ps_bic, bicubic, hr_b, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(h->ps_true, truth, hr_b, cudaMemcpyHostToDevice));
+  h->ps_count = count;
+  h->ps_h = patch_height;
+  h->ps_w = patch_width;
+  return 0;
+}
+
+// Gathers the indexed patches into the fp32 staging tensors io_x / io_x2 / io_y (shared with the host-buffer calls).
+static int patch_gather(dcscn_handle* h, const int32_t* indices, int n, float max_value, cudaStream_t st) {
+  if (h->ps_count == 0) return fail("train_step_indexed: no patch store (call dcscn_patch_store_set first)");
+  if (n <= 0) return fail("train_step_indexed: empty mini-batch");
+  for (int i = 0; i < n; ++i) {
+    const int64_t k = indices[i] & 0x7FFFFFFF;
+    if (k >= h->ps_count) return fail("train_step_indexed: patch index %lld out of range (%lld patches)", (long long)k, (long long)h->ps_count);
+  }
+  const int s = h->cfg.scale;
+  const size_t lr_px = (size_t)n * h->ps_h * h->ps_w, hr_px = lr_px * s * s;
+  if (hr_px > h->io_cap) {
+    cudaFree(h->io_x); cudaFree(h->io_x2); cudaFree(h->io_y);
+    h->io_x = h->io_x2 = h->io_y = nullptr;
+    h->io_cap = 0;
+    CUDA_TRY(cudaMalloc((void**)&h->io_x, lr_px * sizeof(float)));
+    CUDA_TRY(cudaMalloc((void**)&h->io_x2, hr_px * sizeof(float)));
+    CUDA_TRY(cudaMalloc((void**)&h->io_y, hr_px * sizeof(float)));
+    h->io_cap = hr_px;
+  }
+  if (n > h->ps_idx_cap) {
+    cudaFree(h->ps_idx);
+    h->ps_idx = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&h->ps_idx, (size_t)n * sizeof(int)));
+    h->ps_idx_cap = n;
+  }
+  CUDA_TRY(cudaMemcpyAsync(h->ps_idx, indices, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
+  const float scale = max_value / 255.0f;
+  const int grid_lr = (int)std::min<size_t>((lr_px + 255) / 256, (size_t)h->sm_count * 8);
+  const int grid_hr = (int)std::min<size_t>((hr_px + 255) / 256, (size_t)h->sm_count * 8);
+  patch_gather_kernel<<<grid_lr, 256, 0, st>>>(h->ps_lr, h->ps_idx, h->io_x, n, h->ps_h, h->ps_w, scale);
+  patch_gather_kernel<<<grid_hr, 256, 0, st>>>(h->ps_bic, h->ps_idx, h->io_x2, n, s * h->ps_h, s * h->ps_w, scale);
+  patch_gather_kernel<<<grid_hr, 256, 0, st>>>(h->ps_true, h->ps_idx, h->io_y, n, s * h->ps_h, s * h->ps_w, scale);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 3;
+  return 0;
+}
+
+int dcscn_train_step_indexed(dcscn_handle* h, const int32_t* indices, int n, float max_value, float lr, uint32_t seed,
+                             int apply_update, float* out_loss, float* out_mse) {
+  if (!h || !indices) return fail("dcscn_train_step_indexed: null argument");
+  CUDA_TRY(cudaSetDevice(h->cfg.device_id));
+  cudaStream_t st = 0;
+  if (patch_gather(h, indices, n, max_value, st)) return 1;
+  return train_step_impl(h, h->io_x, h->io_x2, h->io_y, n, h->ps_h, h->ps_w, lr, seed, apply_update, out_loss, out_mse, st);
+}
+
+int dcscn_patch_gather(dcscn_handle* h, const int32_t* indices, int n, float max_value, float* x, float* x2, float* y) {
+  if (!h || !indices || !x || !x2 || !y) return fail("dcscn_patch_gather: null argument");
+  CUDA_TRY(cudaSetDevice(h->cfg.device_id));
+  cudaStream_t st = 0;
+  if (patch_gather(h, indices, n, max_value, st)) return 1;
+  const int s = h->cfg.scale;
+  const size_t lr_px = (size_t)n * h->ps_h * h->ps_w, hr_px = lr_px * s * s;
+  CUDA_TRY(cudaMemcpyAsync(x, h->io_x, lr_px * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(x2, h->io_x2, hr_px * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(y, h->io_y, hr_px * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
 }
 
 int dcscn_get_grad(dcscn_handle* h, const char* name, float* host_data, int64_t numel) {

@@ -54,7 +54,7 @@ EXPORTED_SYMBOLS = [
     "dcscn_set_option", "dcscn_get_timings", "dcscn_launch_count", "dcscn_device_bytes",
     "dcscn_train_step", "dcscn_train_step_host", "dcscn_get_grad", "dcscn_get_adam_slot", "dcscn_set_adam_slot", "dcscn_get_adam_step",
     "dcscn_set_adam_step", "dcscn_last_grad_norm",
-    "dcscn_dropout_mask", "dcscn_grad_buffer", "dcscn_apply_gradients", "dcscn_apply_gradients_avg", "dcscn_reset_optimizer",
+    "dcscn_patch_store_set", "dcscn_train_step_indexed", "dcscn_patch_gather", "dcscn_dropout_mask", "dcscn_grad_buffer", "dcscn_apply_gradients", "dcscn_apply_gradients_avg", "dcscn_reset_optimizer",
 ]
 
 _lib = None
@@ -105,6 +105,10 @@ def load_library(path=None):
     lib.dcscn_grad_buffer.argtypes = [vp, ctypes.POINTER(fp), ctypes.POINTER(c64)]
     lib.dcscn_apply_gradients.argtypes = [vp, cf, vp]
     lib.dcscn_reset_optimizer.argtypes = [vp]
+    i32p = ctypes.POINTER(ctypes.c_int32)
+    lib.dcscn_patch_store_set.argtypes = [vp, vp, vp, vp, c64, ci, ci]
+    lib.dcscn_train_step_indexed.argtypes = [vp, i32p, ci, cf, cf, u32, ci, fp, fp]
+    lib.dcscn_patch_gather.argtypes = [vp, i32p, ci, cf, vp, vp, vp]
     lib.dcscn_apply_gradients_avg.argtypes = [vp, cf, cf, fp, fp, vp]
     lib.dcscn_launch_count.argtypes = [vp]
     lib.dcscn_launch_count.restype = c64
@@ -269,6 +273,46 @@ class Engine:
         out.div_(float(flips))
         return out
 
+    # ---- training patches resident in HBM ----
+    def set_patch_store(self, lr_u8, bicubic_u8, true_u8):
+        """uint8 patch arrays [count, ph, pw(, 1)] / [count, s*ph, s*pw(, 1)] -> device memory, once per data set."""
+        a = [np.ascontiguousarray(v, dtype=np.uint8) for v in (lr_u8, bicubic_u8, true_u8)]
+        count, ph, pw = a[0].shape[:3]
+        s = int(self.config.scale)
+        if a[1].shape[:3] != (count, s * ph, s * pw) or a[2].shape[:3] != (count, s * ph, s * pw):
+            raise ValueError("patch arrays do not match: %s %s %s at scale %d" % (a[0].shape, a[1].shape, a[2].shape, s))
+        self._check(self.lib.dcscn_patch_store_set(self.handle, a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data, count, ph, pw))
+        self._patch_shape = (ph, pw)
+
+    @staticmethod
+    def _index_array(indices, mirror=None):
+        idx = np.ascontiguousarray(indices, dtype=np.int64)
+        if mirror is not None:
+            idx = idx | (np.asarray(mirror, dtype=np.int64).astype(bool).astype(np.int64) << 31)
+        return np.ascontiguousarray(idx.astype(np.uint32).view(np.int32))
+
+    def train_step_indexed(self, indices, lr, seed, max_value=255.0, mirror=None, apply_update=True):
+        """One optimisation step on the patches `indices` of the device store; returns (image_loss, mse)."""
+        idx = self._index_array(indices, mirror)
+        loss, mse = ctypes.c_float(), ctypes.c_float()
+        self._check(self.lib.dcscn_train_step_indexed(self.handle, idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), int(idx.size),
+                                                      float(max_value), float(lr), int(seed) & 0xFFFFFFFF,
+                                                      int(bool(apply_update)), ctypes.byref(loss), ctypes.byref(mse)))
+        return float(loss.value), float(mse.value)
+
+    def gather_patches(self, indices, max_value=255.0, mirror=None):
+        """The fp32 mini-batch tensors (x, x2, y) the indexed step feeds the network, copied back to the host."""
+        idx = self._index_array(indices, mirror)
+        ph, pw = self._patch_shape
+        s = int(self.config.scale)
+        n = int(idx.size)
+        x = np.empty((n, ph, pw, 1), np.float32)
+        x2 = np.empty((n, s * ph, s * pw, 1), np.float32)
+        y = np.empty((n, s * ph, s * pw, 1), np.float32)
+        self._check(self.lib.dcscn_patch_gather(self.handle, idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), n, float(max_value),
+                                                x.ctypes.data, x2.ctypes.data, y.ctypes.data))
+        return x, x2, y
+
     def train_step_host(self, x, x2, y, lr, seed, apply_update=True):
         """One optimisation step on host fp32 arrays x [n,h,w,1], x2 / y [n,sh,sw,1]; returns (image_loss, mse)."""
         xa, x2a, ya = _host_array(x), _host_array(x2), _host_array(y)
@@ -318,13 +362,17 @@ class Engine:
                                                        ctypes.byref(mse), ctypes.c_void_p(st)))
         return float(loss.value), float(mse.value)
 
-    def train_step_data_parallel(self, x, x2, y, lr, seed):
+    def train_step_data_parallel(self, x, x2, y, lr, seed, indices=None, max_value=255.0):
         """One optimisation step with the mini-batch sharded over the ranks of the current torch.distributed job (equal
         shards): local gradients -> ONE flat all-reduce carrying [gradients | loss | mse] -> identical mean, clip and
-        Adam on every rank.  Returns the job-wide (image_loss, mse)."""
+        Adam on every rank.  Returns the job-wide (image_loss, mse).  With `indices` the rank's shard is taken from the
+        device patch store (x, x2, y ignored)."""
         import torch.distributed as dist
-        fn = self.train_step if hasattr(x, "is_cuda") and x.is_cuda else self.train_step_host
-        loss, mse = fn(x, x2, y, lr, seed, apply_update=False)
+        if indices is not None:
+            loss, mse = self.train_step_indexed(indices, lr, seed, max_value=max_value, apply_update=False)
+        else:
+            fn = self.train_step if hasattr(x, "is_cuda") and x.is_cuda else self.train_step_host
+            loss, mse = fn(x, x2, y, lr, seed, apply_update=False)
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             g = self.grad_tensor()
             dist.all_reduce(g, op=dist.ReduceOp.SUM)

@@ -107,6 +107,20 @@ int dcscn_train_step(dcscn_handle* h, const float* x_dev, const float* x2_dev, c
                      float lr, uint32_t seed, int apply_update, float* out_loss, float* out_mse, void* stream);
 int dcscn_train_step_host(dcscn_handle* h, const float* x, const float* x2, const float* y, int n, int height, int width, float lr,
                           uint32_t seed, int apply_update, float* out_loss, float* out_mse);
+/*
+ * Training data path on the device (reference: helper/loader.py:70-275 BatchDataSets + DCSCN.py:186-190 build_input_batch,
+ * which assemble every mini-batch patch by patch in Python).  dcscn_patch_store_set copies the data set's uint8 patch
+ * arrays - LR input [count, ph, pw], its bicubic up-scale and the ground truth [count, scale*ph, scale*pw] - into HBM
+ * once.  dcscn_train_step_indexed is dcscn_train_step on the mini-batch {patch indices[i]}: one gather launch per tensor
+ * converts uint8 -> fp32 * (max_value / 255) (loader.py:251-255); bit 31 of an index mirrors that patch left-right
+ * (the augmentation of loader.py:318-319).  dcscn_patch_gather returns the same gathered fp32 tensors to the host
+ * (parity checks against the host loader).
+ */
+int dcscn_patch_store_set(dcscn_handle* h, const uint8_t* lr, const uint8_t* bicubic, const uint8_t* truth, int64_t count,
+                          int patch_height, int patch_width);
+int dcscn_train_step_indexed(dcscn_handle* h, const int32_t* indices, int n, float max_value, float lr, uint32_t seed,
+                             int apply_update, float* out_loss, float* out_mse);
+int dcscn_patch_gather(dcscn_handle* h, const int32_t* indices, int n, float max_value, float* x, float* x2, float* y);
 /* d loss / d variable of the LAST train step (after the L2 term, before clipping): tf.gradients(loss, trainables). */
 int dcscn_get_grad(dcscn_handle* h, const char* name, float* host_data, int64_t numel);
 /* Adam slots of a variable ("<var>/Adam" = slot 0, "<var>/Adam_1" = slot 1 in the reference's checkpoints). */

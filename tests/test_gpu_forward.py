@@ -167,7 +167,11 @@ def test_l12_stress_noise_tiles():
     eng = make_engine({}, w)
     y = gpu_forward(eng, x, x2)
     eng.close()
-    assert np.abs(y - y64).max() <= stress_bound(y32, y64)
+    err = float(np.abs(y - y64).max())
+    assert err <= stress_bound(y32, y64)
+    # north_star's bar stated absolutely at BASELINE configs[1]'s own input distribution: 1e-3 against the exact (fp64)
+    # forward.  (The fp32 CPU forward is at ~2.4e-3 on these tiles; the split-accumulator tcgen05 path is inside 1e-3.)
+    assert err <= TOL, err
 
 
 def test_full_batch_properties():

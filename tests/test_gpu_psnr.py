@@ -67,6 +67,53 @@ def test_set5_psnr_and_pixels(tmp_path, flag_args, model, ens):
         assert abs(np.mean(ps) - case["readme"]) <= 0.021
 
 
+@pytest.mark.parametrize("flag_args,model", [
+    (CD, "dcscn_L7_F32to8_G1.20_NIN_A24_B8_PS_R1F32"),
+    ([], "dcscn_L12_F196to48_NIN_A64_PS_R1F32"),
+], ids=["c-DCSCN", "L12"])
+def test_set14_psnr(tmp_path, flag_args, model):
+    """north_star's PSNR gate names Set5 AND Set14.  Set14 holds the grayscale img_003 (mode L: the uint8-through-PIL
+    branch of DCSCN.py:688-696) and non-square images up to 360x250 LR.  Every image's PSNR through the drop-in class is
+    held to the CPU oracle's (c-DCSCN) or to the survey's per-image known answers (L12, 3 decimals) within 0.01 dB."""
+    m = build_model(tmp_path, flag_args, 1)
+    case = [c for c in KA["cases"] if c["model"] == model and c["dataset"] == "set14" and c["ensemble"] == 1][0]
+    files = sorted(glob.glob(os.path.join(GOLDEN, "data", "set14", "*.png")))
+    assert len(files) == 14
+    orc = O.Oracle(O.OracleConfig(**MODEL_FLAGS[model]), load_golden_weights(model), torch.float32)
+    ps = []
+    for i, f in enumerate(files):
+        psnr, _ = m.do_for_evaluate(f)
+        ps.append(psnr)
+        if "per_image" in case:
+            assert abs(psnr - case["per_image"][i]) <= 0.01 + 5e-4, (f, psnr, case["per_image"][i])   # known answers carry 3 decimals
+        else:
+            assert abs(psnr - O.do_for_evaluate(orc, f, 1)) <= 0.01, f
+    gray = files[2]
+    lr, bic, _ = O.build_inputs_for_evaluate(gray, 2)
+    assert lr.shape[2] == 1 and float(np.abs(lr - np.rint(lr)).max()) == 0.0      # the monochrome branch really is integer-valued
+    ref = O.do(orc, lr, bic, 1)
+    assert np.abs(m.do(lr, bic) - ref).max() <= 1.5e-3
+    assert abs(np.mean(ps) - case["probe"]) <= 0.01
+    assert abs(np.mean(ps) - case["readme"]) <= 0.021
+
+
+def test_l12_x4_set5_ensemble8_psnr(tmp_path):
+    """The x4 flagship (two pixel-shuffler stages) with the default self_ensemble = 8: Set5 average against the survey's
+    known answer 31.703 dB (README: 31.72) and, on one image, pixels against the fp64 oracle's ensemble."""
+    model = "dcscn_L12_F196to48_Sc4_NIN_A64_PS_R1F32"
+    m = build_model(tmp_path, ["--scale=4"], 8)
+    assert m.name == model
+    case = [c for c in KA["cases"] if c["model"] == model][0]
+    files = sorted(glob.glob(os.path.join(GOLDEN, "data", "set5", "*.png")))
+    ps = [m.do_for_evaluate(f)[0] for f in files]
+    assert abs(np.mean(ps) - case["probe"]) <= 0.01
+    assert abs(np.mean(ps) - case["readme"]) <= 0.021
+    lr, bic, _ = O.build_inputs_for_evaluate(files[4], 4)          # 86x57 LR
+    orc64 = O.Oracle(O.OracleConfig(scale=4), load_golden_weights(model), torch.float64)
+    ref = O.do(orc64, lr.astype(np.float64), bic.astype(np.float64), 8)
+    assert np.abs(m.do(lr, bic) - ref).max() <= 1e-3
+
+
 def test_self_ensemble_8_matches_oracle(tmp_path):
     m = build_model(tmp_path, [], 8)
     model = "dcscn_L12_F196to48_NIN_A64_PS_R1F32"

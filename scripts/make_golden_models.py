@@ -23,6 +23,11 @@ MODELS = [
     "dcscn_L7_F32to8_G1.20_Sc3_NIN_A24_B8_PS_R1F32",
     "dcscn_L7_F32to8_G1.20_Sc4_NIN_A24_B8_PS_R1F32",
     "dcscn_L7_F32to8_G1.20_Sc4_NIN_A24_B8_PS_DS_R1F32",
+    # round 2: the remaining shipped variants (README.md:80,100,132 use --layers=8 --filters=96)
+    "dcscn_L12_F196to48_Sc3_NIN_A64_PS_R1F32",
+    "dcscn_L8_F96to48_NIN_A64_PS_R1F32",
+    "dcscn_L8_F96to48_Sc3_NIN_A64_PS_R1F32",
+    "dcscn_L8_F96to48_Sc4_NIN_A64_PS_R1F32",
 ]
 
 

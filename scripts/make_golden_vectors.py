@@ -44,6 +44,11 @@ def main():
         ("dcscn_L7_F32to8_G1.20_Sc4_NIN_A24_B8_PS_R1F32", [(17, 16)], 6),
         ("dcscn_L7_F32to8_G1.20_Sc4_NIN_A24_B8_PS_DS_R1F32", [(48, 48), (48, 48)], 7),
         ("dcscn_L7_F32to8_G1.20_Sc4_NIN_A24_B8_PS_DS_R1F32", [(13, 70)], 8),
+        # round 2: the remaining shipped checkpoints (appended: cases 0..7 stay bit-identical)
+        ("dcscn_L12_F196to48_Sc3_NIN_A64_PS_R1F32", [(24, 31)], 9),
+        ("dcscn_L8_F96to48_NIN_A64_PS_R1F32", [(48, 48), (48, 48)], 10),
+        ("dcscn_L8_F96to48_Sc3_NIN_A64_PS_R1F32", [(21, 40)], 11),
+        ("dcscn_L8_F96to48_Sc4_NIN_A64_PS_R1F32", [(19, 23)], 12),
     ]
     for ci, (model, sizes, seed) in enumerate(cases):
         kw = MODEL_FLAGS[model]

@@ -31,6 +31,10 @@ MODEL_FLAGS = {
     # model name -> (oracle/engine config kwargs)
     "dcscn_L12_F196to48_NIN_A64_PS_R1F32": dict(),
     "dcscn_L12_F196to48_Sc4_NIN_A64_PS_R1F32": dict(scale=4),
+    "dcscn_L12_F196to48_Sc3_NIN_A64_PS_R1F32": dict(scale=3),
+    "dcscn_L8_F96to48_NIN_A64_PS_R1F32": dict(layers=8, filters=96),
+    "dcscn_L8_F96to48_Sc3_NIN_A64_PS_R1F32": dict(scale=3, layers=8, filters=96),
+    "dcscn_L8_F96to48_Sc4_NIN_A64_PS_R1F32": dict(scale=4, layers=8, filters=96),
     "dcscn_L7_F32to8_G1.20_NIN_A24_B8_PS_R1F32": dict(
         scale=2, layers=7, filters=32, min_filters=8, filters_decay_gamma=1.2, nin_filters=24, nin_filters2=8,
         reconstruct_layers=0, pixel_shuffler_filters=1),

@@ -118,7 +118,7 @@ def golden_cases():
     return d, n
 
 
-@pytest.mark.parametrize("ci", range(8))
+@pytest.mark.parametrize("ci", range(12))
 def test_golden_vectors(ci):
     """Committed fp64-oracle outputs for Set5 crops through the reference's own checkpoints."""
     d, n = golden_cases()

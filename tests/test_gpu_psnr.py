@@ -97,13 +97,46 @@ def test_set14_psnr(tmp_path, flag_args, model):
     assert abs(np.mean(ps) - case["readme"]) <= 0.021
 
 
+@pytest.mark.parametrize("flag_args,model", [
+    (["--scale=3"], "dcscn_L12_F196to48_Sc3_NIN_A64_PS_R1F32"),
+    (["--layers=8", "--filters=96"], "dcscn_L8_F96to48_NIN_A64_PS_R1F32"),
+    (["--layers=8", "--filters=96", "--scale=3"], "dcscn_L8_F96to48_Sc3_NIN_A64_PS_R1F32"),
+    (["--layers=8", "--filters=96", "--scale=4"], "dcscn_L8_F96to48_Sc4_NIN_A64_PS_R1F32"),
+], ids=["L12-x3", "L8-x2", "L8-x3", "L8-x4"])
+def test_remaining_shipped_checkpoints_set5(tmp_path, flag_args, model):
+    """SURVEY.md section 8 f4: the other checkpoints the reference ships (README.md:80,100,132 use --layers=8 --filters=96;
+    x3 is a single 3x pixel shuffle with 9 * 96 = 864 Up-PS channels, DCSCN.py:305-308).  Per image: PSNR within 0.01 dB
+    of the CPU oracle's recorded value, pixels within 1e-3 of the fp64 oracle on one image."""
+    m = build_model(tmp_path, flag_args, 1)
+    assert m.name == model
+    case = [c for c in KA["cases"] if c["model"] == model and c["ensemble"] == 1][0]
+    files = sorted(glob.glob(os.path.join(GOLDEN, "data", "set5", "*.png")))
+    ps = [m.do_for_evaluate(f)[0] for f in files]
+    for p, want in zip(ps, case["per_image"]):
+        assert abs(p - want) <= 0.01 + 5e-4, (model, ps, case["per_image"])
+    assert abs(np.mean(ps) - case["oracle"]) <= 0.01
+    lr, bic, _ = O.build_inputs_for_evaluate(files[3], m.scale)
+    orc64 = O.Oracle(O.OracleConfig(**MODEL_FLAGS[model]), load_golden_weights(model), torch.float64)
+    ref = O.do(orc64, lr.astype(np.float64), bic.astype(np.float64), 1)
+    assert np.abs(m.do(lr, bic) - ref).max() <= 1e-3
+
+
+def test_l12_x3_set5_ensemble8_matches_the_readme(tmp_path):
+    model = "dcscn_L12_F196to48_Sc3_NIN_A64_PS_R1F32"
+    m = build_model(tmp_path, ["--scale=3"], 8)
+    case = [c for c in KA["cases"] if c["model"] == model and c["ensemble"] == 8][0]
+    ps = [m.do_for_evaluate(f)[0] for f in sorted(glob.glob(os.path.join(GOLDEN, "data", "set5", "*.png")))]
+    assert abs(np.mean(ps) - case["oracle"]) <= 0.01
+    assert abs(np.mean(ps) - case["readme"]) <= 0.021          # README.md:58: 34.06
+
+
 def test_l12_x4_set5_ensemble8_psnr(tmp_path):
     """The x4 flagship (two pixel-shuffler stages) with the default self_ensemble = 8: Set5 average against the survey's
     known answer 31.703 dB (README: 31.72) and, on one image, pixels against the fp64 oracle's ensemble."""
     model = "dcscn_L12_F196to48_Sc4_NIN_A64_PS_R1F32"
     m = build_model(tmp_path, ["--scale=4"], 8)
     assert m.name == model
-    case = [c for c in KA["cases"] if c["model"] == model][0]
+    case = [c for c in KA["cases"] if c["model"] == model and c["ensemble"] == 8][0]
     files = sorted(glob.glob(os.path.join(GOLDEN, "data", "set5", "*.png")))
     ps = [m.do_for_evaluate(f)[0] for f in files]
     assert abs(np.mean(ps) - case["probe"]) <= 0.01

@@ -24,7 +24,8 @@ def test_model_psnr(case):
     orc = O.Oracle(cfg, load_golden_weights(case["model"]), torch.float32)
     ps = [O.do_for_evaluate(orc, f, case["ensemble"]) for f in files(case["dataset"])]
     mean = float(np.mean(ps))
-    assert abs(mean - case["probe"]) < 2e-3, (mean, case["probe"])
+    want = case["probe"] if case["probe"] is not None else case["oracle"]   # survey probe, else this oracle's recorded value
+    assert abs(mean - want) < 2e-3, (mean, want)
     if case["readme"] is not None:
         # README figures are 2-decimal and their provenance is loose; 0.02 dB covers all rows
         assert abs(mean - case["readme"]) < 0.021, (mean, case["readme"])

@@ -68,6 +68,11 @@ def test_adam_step_matches_oracle_and_loss_decreases():
     m = {k: np.zeros_like(v) for k, v in wts.items()}
     v = {k: np.zeros_like(v_) for k, v_ in wts.items()}
     losses = []
+    # Tolerance, derived instead of tuned: test_gradients_match_oracle grants every gradient tensor an absolute error
+    # delta = 2e-3 * max|g|.  Adam's update lr_t * m / (sqrt(v) + eps) is ~ lr * sign(g) where |g| >> delta (insensitive to
+    # the error) and flips sign - an error of up to 2 lr - where |g| <~ delta; in between its sensitivity to g is O(1/|g|).
+    # Allowed error of a weight after t steps: 2e-3 * lr * t  +  lr * sum_s min(2, 3 * delta_s / |g_s|).
+    slack = {k: np.zeros_like(v_) for k, v_ in wts.items()}
     for step in range(1, 4):
         seed = 100 + step
         loss, mse = eng.train_step_host(x, x2, y, lr=0.002, seed=seed)
@@ -77,8 +82,11 @@ def test_adam_step_matches_oracle_and_loss_decreases():
         clipped, _ = orc.clip_by_global_norm(grads)
         orc.adam_step(clipped, m, v, step, 0.002)
         for name in wts:
+            delta = 2e-3 * np.abs(grads[name]).max()
+            slack[name] += np.minimum(2.0, 3.0 * delta / (np.abs(grads[name]) + 1e-300))
+            tol = 2e-3 * 0.002 * step + 0.002 * slack[name]
             got = eng.get_param(name)
-            assert np.abs(got - orc.w[name]).max() <= 0.05 * 0.002 * step, (step, name)  # Adam steps are ~lr*sign(g): entries with |g| ~ eps are ill-conditioned
+            assert (np.abs(got - orc.w[name]) <= tol).all(), (step, name, float((np.abs(got - orc.w[name]) - tol).max()))
     # slots follow the reference's checkpoint convention (<var>/Adam, <var>/Adam_1)
     np.testing.assert_allclose(eng.get_adam_slot("CNN1/conv_W", 0), m["CNN1/conv_W"], rtol=0, atol=3e-3 * np.abs(m["CNN1/conv_W"]).max())
     # the forward pass uses the updated weights (re-packed tensor-core operand images)
@@ -170,6 +178,37 @@ def test_full_size_batch_gradient_is_mean_of_half_batch_gradients():
     for k in wts:
         want = 0.5 * (g_a[k] + g_b[k])
         assert np.abs(g_all[k] - want).max() <= 2e-4 * np.abs(want).max() + 1e-9, (k, float(np.abs(g_all[k] - want).max()), float(np.abs(want).max()))
+    eng.close()
+
+
+def test_full_width_l12_x4_gradients_match_oracle():
+    """The flagship train graph at full width (L12, 196..48 filters, 1301-channel concat, two pixel-shuffler stages, the
+    reference's own x4 checkpoint) on a batch small enough for the fp64 autograd oracle: loss and EVERY gradient, with
+    dropout 0.8 replayed through the engine's masks."""
+    from helper import engine as E
+    import conftest
+    model = "dcscn_L12_F196to48_Sc4_NIN_A64_PS_R1F32"
+    cfg = O.OracleConfig(scale=4)
+    wts = {k: v.astype(np.float64) for k, v in conftest.load_golden_weights(model).items()}
+    n, h, w = 2, 12, 10
+    g = np.random.RandomState(21)
+    x = (g.rand(n, h, w, 1) * 255).astype(np.float32)
+    x2 = (g.rand(n, 4 * h, 4 * w, 1) * 255).astype(np.float32)
+    y = np.clip(x2 + g.randn(n, 4 * h, 4 * w, 1) * 10, 0, 255).astype(np.float32)
+    eng = E.Engine(E.make_config(scale=4, dropout_keep=0.8))
+    eng.set_params({k: v.astype(np.float32) for k, v in wts.items()})
+    seed = 77
+    loss, mse = eng.train_step_host(x, x2, y, lr=0.002, seed=seed, apply_update=False)
+    masks = oracle_masks(eng, cfg, seed, n, h, w)
+    mse_ref, loss_ref, grads_ref = O.Oracle(cfg, wts, torch.float64).loss_and_grads(
+        x.astype(np.float64), x2.astype(np.float64), y.astype(np.float64), keep_prob=0.8, masks=masks)
+    assert mse == pytest.approx(mse_ref, rel=5e-5)
+    norm_ref = np.sqrt(sum(np.sum(v ** 2) for v in grads_ref.values()))
+    assert eng.last_grad_norm == pytest.approx(norm_ref, rel=2e-3)
+    for name, gref in grads_ref.items():
+        got = eng.get_grad(name)
+        tol = 2e-3 * np.abs(gref).max() + 1e-7
+        assert np.abs(got - gref).max() <= tol, (name, float(np.abs(got - gref).max()), float(np.abs(gref).max()))
     eng.close()
 
 

@@ -25,6 +25,7 @@
 #include "conv_tc_halo1.cuh"
 #include "conv_tc_halo2.cuh"
 #include "conv_ds.cuh"
+#include "conv_ds_tile.cuh"
 #include "train.cuh"
 #include "wgrad_tc.cuh"
 #include "wgrad_tc.cuh"
@@ -208,6 +209,8 @@ struct dcscn_handle {
   // depthwise-separable graphs: fp32 buffers + per-layer device filters
   struct DsDev { float *dw = nullptr, *pw = nullptr, *bias = nullptr, *alpha = nullptr; };
   std::vector<DsDev> ds;             // same order as `layers`
+  DsDev ds_ab;                       // fused A1 | B1 1x1 layer of the tile kernels: [concat positions][A1 cols | B1 cols], scales folded
+  int ds_impl = 0;                   // 0 = tile kernels (conv_ds_tile.cuh), 1 = first-generation kernels (cross-check)
   float *ds_feat = nullptr, *ds_b1 = nullptr, *ds_nin = nullptr, *ds_mid = nullptr, *ds_hr = nullptr;
   int ds_total = 0;                  // channels of the (unpadded) concat buffer
   int ds_n = 0, ds_h = 0, ds_w = 0;  // geometry of the last DS forward
@@ -561,22 +564,57 @@ static int finalize_params_ds(dcscn_handle* h) {
   for (auto& d : h->ds) {
     cudaFree(d.dw); cudaFree(d.pw); cudaFree(d.bias); cudaFree(d.alpha);
   }
+  cudaFree(h->ds_ab.pw); cudaFree(h->ds_ab.bias); cudaFree(h->ds_ab.alpha);
+  h->ds_ab = dcscn_handle::DsDev();
   h->ds.assign(h->layers.size(), dcscn_handle::DsDev());
-  for (size_t i = 0; i < h->layers.size(); ++i) {
-    const LayerDef& l = h->layers[i];
-    std::string base = l.scope.substr(l.scope.find_last_of('/') == std::string::npos ? 0 : l.scope.find_last_of('/') + 1);
-    if (upload(&h->ds[i].dw, P(h, l.scope + "/depthwise_W"), h)) return 1;   // [k,k,cin,1] == [taps][cin]
-    if (upload(&h->ds[i].pw, P(h, l.scope + "/pointwise_W"), h)) return 1;   // [1,1,cin,cout] == [cin][cout]
-    if (l.bias && upload(&h->ds[i].bias, P(h, l.scope + "/conv_B"), h)) return 1;
-    if (l.prelu && upload(&h->ds[i].alpha, P(h, l.scope + "/prelu/" + base + "_prelu"), h)) return 1;
-  }
+  // concat buffer: every CNNi slot starts on a multiple of 4 channels (16-byte loads / stores); the pad channels are never
+  // written (the buffer is zero-filled once) and meet zero rows in the A1 / B1 filters
   h->ds_off.clear();
   int off = 0;
   for (int f : h->filters) {
     h->ds_off.push_back(off);
-    off += f;
+    off += (f + 3) & ~3;
   }
   h->ds_total = off;
+  const int T = h->ds_total, L = h->cfg.layers;
+  std::vector<float> ab_pw, ab_bias, ab_alpha;
+  const int na = h->cfg.nin_filters, nb = h->cfg.nin_filters2;
+  ab_pw.assign((size_t)T * (na + nb), 0.f);
+  ab_bias.assign(na + nb, 0.f);
+  ab_alpha.assign(na + nb, 1.f);
+  for (size_t i = 0; i < h->layers.size(); ++i) {
+    const LayerDef& l = h->layers[i];
+    std::string base = l.scope.substr(l.scope.find_last_of('/') == std::string::npos ? 0 : l.scope.find_last_of('/') + 1);
+    const std::vector<float>& dwv = P(h, l.scope + "/depthwise_W");   // [k,k,cin,1] == [taps][cin]
+    const std::vector<float>& pwv = P(h, l.scope + "/pointwise_W");   // [1,1,cin,cout] == [cin][cout]
+    if (l.scope == "A1" || l.scope == "B1") {
+      // these read the whole concat buffer: spread their rows over the 4-aligned slot positions
+      std::vector<float> dwp((size_t)l.k * l.k * T, 0.f), pwp((size_t)T * l.cout, 0.f);
+      const int col0 = l.scope == "A1" ? 0 : na;
+      int ci = 0;
+      for (int li = 0; li < L; ++li)
+        for (int k = 0; k < h->filters[li]; ++k, ++ci) {
+          const int pos = h->ds_off[li] + k;
+          for (int t = 0; t < l.k * l.k; ++t) dwp[(size_t)t * T + pos] = dwv[(size_t)t * l.cin + ci];
+          for (int co = 0; co < l.cout; ++co) {
+            pwp[(size_t)pos * l.cout + co] = pwv[(size_t)ci * l.cout + co];
+            if (l.k == 1) ab_pw[(size_t)pos * (na + nb) + col0 + co] = dwv[ci] * pwv[(size_t)ci * l.cout + co];
+          }
+        }
+      const auto& B = P(h, l.scope + "/conv_B");
+      const auto& A = P(h, l.scope + "/prelu/" + base + "_prelu");
+      for (int co = 0; co < l.cout; ++co) {
+        ab_bias[col0 + co] = B[co];
+        ab_alpha[col0 + co] = A[co];
+      }
+      if (upload(&h->ds[i].dw, dwp, h) || upload(&h->ds[i].pw, pwp, h)) return 1;
+    } else {
+      if (upload(&h->ds[i].dw, dwv, h) || upload(&h->ds[i].pw, pwv, h)) return 1;
+    }
+    if (l.bias && upload(&h->ds[i].bias, P(h, l.scope + "/conv_B"), h)) return 1;
+    if (l.prelu && upload(&h->ds[i].alpha, P(h, l.scope + "/prelu/" + base + "_prelu"), h)) return 1;
+  }
+  if (upload(&h->ds_ab.pw, ab_pw, h) || upload(&h->ds_ab.bias, ab_bias, h) || upload(&h->ds_ab.alpha, ab_alpha, h)) return 1;
   h->params_dirty = false;
   return 0;
 }
@@ -726,7 +764,7 @@ static int ensure_workspace(dcscn_handle* h, size_t lr_px) {
     h->device_bytes = 0;
     const size_t s2 = (size_t)c.scale * c.scale;
     const int cps = c.nin_filters + c.nin_filters2;
-    if (dev_alloc(h, &h->ds_feat, lr_px * h->ds_total, false)) return 1;
+    if (dev_alloc(h, &h->ds_feat, lr_px * h->ds_total, true)) return 1;   // pad channels must stay zero
     if (dev_alloc(h, &h->ds_b1, lr_px * c.nin_filters2, false)) return 1;
     if (dev_alloc(h, &h->ds_nin, lr_px * cps, false)) return 1;
     if (c.scale == 4 && dev_alloc(h, &h->ds_mid, lr_px * 4 * cps, false)) return 1;
@@ -931,6 +969,11 @@ static int add_tc_launch(dcscn_handle* h, Plan* pl, const TcLayer& t, const __ha
     nb = std::min<long long>(nb, kH2MaxStages);
     if (nb >= 3) {
       int seg = h->seg_chunks > 0 ? h->seg_chunks : (t.n_pad >= 144 ? 1 : (t.n_pad >= 112 ? 2 : 3));
+      if (const char* ov = getenv("DCSCN_SEG")) {   // experiments: "CNN2=1,CNN5=2" overrides the promotion period per layer
+        const std::string key = t.name + "=";
+        const char* hit = strstr(ov, key.c_str());
+        if (hit && (hit == ov || hit[-1] == ',')) seg = std::max(1, atoi(hit + key.size()));
+      }
       seg = std::min(seg, 3 * ((t.cin_pad + 63) / 64));
       L.halo2 = true;
       L.halo2_seg = seg;
@@ -1297,8 +1340,137 @@ static int launch_ds(dcscn_handle* h, const LayerDef& l, const dcscn_handle::DsD
   return mark(h, st);
 }
 
+// ---- second-generation depthwise-separable kernels (conv_ds_tile.cuh) ----
+template <int KSZ>
+static int launch_ds_tile_k(dcscn_handle* h, const DsTileParams& p, unsigned grid, size_t smem, cudaStream_t st) {
+  const int cols = p.cout < 32 ? ((p.cout + 3) & ~3) : 32;
+  static size_t attr_dev[64][2] = {};
+  size_t& cur = attr_dev[h->cfg.device_id & 63][KSZ == 3 ? 1 : 0];
+  if (cur == 0) cur = 48 * 1024;
+  if (smem > cur) {
+    const int b = (int)smem;
+    CUDA_TRY(cudaFuncSetAttribute(ds_tile_kernel<KSZ, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    CUDA_TRY(cudaFuncSetAttribute(ds_tile_kernel<KSZ, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    CUDA_TRY(cudaFuncSetAttribute(ds_tile_kernel<KSZ, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    CUDA_TRY(cudaFuncSetAttribute(ds_tile_kernel<KSZ, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    CUDA_TRY(cudaFuncSetAttribute(ds_tile_kernel<KSZ, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, b));
+    cur = smem;
+  }
+  if (cols <= 4) ds_tile_kernel<KSZ, 1><<<grid, kDtThreads, smem, st>>>(p);
+  else if (cols <= 8) ds_tile_kernel<KSZ, 2><<<grid, kDtThreads, smem, st>>>(p);
+  else if (cols <= 16) ds_tile_kernel<KSZ, 4><<<grid, kDtThreads, smem, st>>>(p);
+  else if (cols <= 24) ds_tile_kernel<KSZ, 6><<<grid, kDtThreads, smem, st>>>(p);
+  else ds_tile_kernel<KSZ, 8><<<grid, kDtThreads, smem, st>>>(p);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+static int launch_ds_tile(dcscn_handle* h, DsTileParams p, int ksz, cudaStream_t st) {
+  if (ksz != 1 && ksz != 3) return fail("depthwise-separable layer: kernel size %d is not supported (1 or 3)", ksz);
+  if (p.cout > 32 && p.cin > kDtCC) return fail("depthwise-separable layer %d -> %d: more than 32 output columns need <= 32 input channels", p.cin, p.cout);
+  const int cols = p.cout < 32 ? ((p.cout + 3) & ~3) : 32;
+  // the kernel's shared-memory carve-up uses the per-pass column count of the instantiated template
+  const int tcols = cols <= 4 ? 4 : cols <= 8 ? 8 : cols <= 16 ? 16 : cols <= 24 ? 24 : 32;
+  const size_t in_px = ksz == 3 ? (size_t)(kDtT + 2) * kDtS : (size_t)kDtThreads;
+  const size_t smem = (in_px * kDtCP + (size_t)p.cin * tcols + (size_t)ksz * ksz * p.cin) * sizeof(float);
+  if (smem > 200 * 1024) return fail("depthwise-separable layer %d -> %d exceeds the kernel's shared memory", p.cin, p.cout);
+  unsigned grid;
+  if (ksz == 3) {
+    p.tiles_x = (p.W + kDtT - 1) / kDtT;
+    p.tiles_y = (p.H + kDtT - 1) / kDtT;
+    grid = (unsigned)((long long)p.n_img * p.tiles_x * p.tiles_y);
+  } else {
+    grid = (unsigned)(((long long)p.n_img * p.H * p.W + kDtThreads - 1) / kDtThreads);
+  }
+  const int rc = ksz == 3 ? launch_ds_tile_k<3>(h, p, grid, smem, st) : launch_ds_tile_k<1>(h, p, grid, smem, st);
+  if (rc) return rc;
+  h->launches++;
+  return mark(h, st);
+}
+
+static DsTileParams ds_tile_params(const LayerDef& l, const dcscn_handle::DsDev& d, const float* src, int src_pitch, float* dst,
+                                   int dst_pitch, int dst_off, int n, int H, int W) {
+  DsTileParams p;
+  memset(&p, 0, sizeof(p));
+  p.n_img = n; p.H = H; p.W = W; p.cin = l.cin; p.cout = l.cout;
+  p.src = src; p.src_pitch = src_pitch; p.dw = d.dw; p.pw = d.pw; p.bias = d.bias; p.alpha = d.alpha;
+  p.dst = dst; p.dst_pitch = dst_pitch; p.dst_off = dst_off;
+  return p;
+}
+
+static int forward_ds_tile(dcscn_handle* h, const float* x, const float* x2, float* y, int n, int H, int W, cudaStream_t st) {
+  const dcscn_config& c = h->cfg;
+  const int L = c.layers, T = h->ds_total, na = c.nin_filters, nb = c.nin_filters2, cps = na + nb;
+  h->ev_used = 0;
+  if (mark(h, st)) return 1;
+  size_t li = 0;
+  for (int i = 0; i < L; ++i, ++li) {
+    const float* src = i == 0 ? x : h->ds_feat + h->ds_off[i - 1];
+    DsTileParams p = ds_tile_params(h->layers[li], h->ds[li], src, i == 0 ? c.channels : T, h->ds_feat, T, h->ds_off[i], n, H, W);
+    if (launch_ds_tile(h, p, h->layers[li].k, st)) return 1;
+  }
+  {  // A1 | B1: both are 1x1 over the whole concat buffer -> ONE pass; the per-channel depthwise scales are folded into the
+     // pointwise rows.  Columns [0, na) = A1 -> [B2 | A1] buffer at channel nb; columns [na, na+nb) = B1 -> B1 buffer.
+    if (h->layers[li].k != 1 || h->layers[li + 1].k != 1) return fail("depthwise-separable A1 / B1 must be 1x1");
+    LayerDef ab = h->layers[li];
+    ab.k = 1; ab.cin = T; ab.cout = cps;
+    DsTileParams p = ds_tile_params(ab, h->ds_ab, h->ds_feat, T, h->ds_nin, cps, nb, n, H, W);
+    p.dw = nullptr;
+    p.split = na;
+    p.dst2 = h->ds_b1; p.dst2_pitch = nb; p.dst2_off = 0;
+    if (cps > 32) return fail("depthwise-separable graph: nin_filters + nin_filters2 = %d > 32 is not supported by the fused A1|B1 kernel", cps);
+    if (launch_ds_tile(h, p, 1, st)) return 1;
+    li += 2;
+  }
+  {  // B2
+    DsTileParams p = ds_tile_params(h->layers[li], h->ds[li], h->ds_b1, nb, h->ds_nin, cps, 0, n, H, W);
+    if (launch_ds_tile(h, p, h->layers[li].k, st)) return 1;
+    ++li;
+  }
+  int HH = H, WW = W;
+  if (c.scale == 4) {
+    DsTileParams p = ds_tile_params(h->layers[li], h->ds[li], h->ds_nin, cps, h->ds_mid, cps, 0, n, H, W);
+    p.d2s_r = 2; p.d2s_cout = cps;
+    if (launch_ds_tile(h, p, h->layers[li].k, st)) return 1;
+    ++li;
+    HH = 2 * H; WW = 2 * W;
+    DsTileParams q = ds_tile_params(h->layers[li], h->ds[li], h->ds_mid, cps, h->ds_hr, h->ps_out, 0, n, HH, WW);
+    q.d2s_r = 2; q.d2s_cout = h->ps_out;
+    if (launch_ds_tile(h, q, h->layers[li].k, st)) return 1;
+    ++li;
+    HH *= 2; WW *= 2;
+  } else {
+    DsTileParams p = ds_tile_params(h->layers[li], h->ds[li], h->ds_nin, cps, h->ds_hr, h->ps_out, 0, n, H, W);
+    p.d2s_r = c.scale; p.d2s_cout = h->ps_out;
+    if (launch_ds_tile(h, p, h->layers[li].k, st)) return 1;
+    ++li;
+    HH = c.scale * H; WW = c.scale * W;
+  }
+  if (h->wait_x2) {
+    CUDA_TRY(cudaStreamWaitEvent(st, h->x2_ready, 0));
+    h->wait_x2 = false;
+  }
+  // R-CNN1 (no bias / activation) + x2
+  const LayerDef& lr = h->layers[li];
+  const dcscn_handle::DsDev& d = h->ds[li];
+  const long long total = (long long)n * HH * WW;
+  if (lr.cin == 1 && lr.cout == 1 && lr.k == 3 && (WW & 3) == 0 && total < (1ll << 32) &&
+      ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(x2)) & 15) == 0) {
+    const int grid = (int)std::min<long long>((total / 4 + 255) / 256, (long long)h->sm_count * 16);
+    ds_single4_kernel<<<grid, 256, 0, st>>>(h->ds_hr, x2, y, n, HH, WW, d.dw, d.pw, d.bias, d.alpha);
+    CUDA_TRY(cudaGetLastError());
+    h->launches++;
+    return mark(h, st);
+  }
+  if (lr.cin == 1 && lr.cout == 1) return launch_ds(h, lr, d, h->ds_hr, h->ps_out, y, 1, 0, n, HH, WW, 0, 0, x2, st);
+  DsTileParams p = ds_tile_params(lr, d, h->ds_hr, h->ps_out, y, 1, 0, n, HH, WW);
+  p.add = x2;
+  return launch_ds_tile(h, p, lr.k, st);
+}
+
 // Depthwise-separable graph (DCSCN.py:246-249, 264-271, 318-320; tf_graph.py:240-243): fp32 NHWC, CUDA cores.
 static int forward_ds(dcscn_handle* h, const float* x, const float* x2, float* y, int n, int H, int W, cudaStream_t st) {
+  if (h->ds_impl == 0) return forward_ds_tile(h, x, x2, y, n, H, W, st);
   const dcscn_config& c = h->cfg;
   const int L = c.layers, T = h->ds_total, cps = c.nin_filters + c.nin_filters2;
   h->ev_used = 0;
@@ -1308,9 +1480,11 @@ static int forward_ds(dcscn_handle* h, const float* x, const float* x2, float* y
     const float* src = i == 0 ? x : h->ds_feat + h->ds_off[i - 1];
     if (launch_ds(h, h->layers[li], h->ds[li], src, i == 0 ? c.channels : T, h->ds_feat, T, h->ds_off[i], n, H, W, 0, 0, nullptr, st)) return 1;
   }
-  if (launch_ds(h, h->layers[li], h->ds[li], h->ds_feat, T, h->ds_nin, cps, c.nin_filters2, n, H, W, 0, 0, nullptr, st)) return 1;  // A1
+  LayerDef la = h->layers[li], lb = h->layers[li + 1];
+  la.cin = lb.cin = T;   // their filters are spread over the 4-aligned concat positions (finalize_params_ds)
+  if (launch_ds(h, la, h->ds[li], h->ds_feat, T, h->ds_nin, cps, c.nin_filters2, n, H, W, 0, 0, nullptr, st)) return 1;  // A1
   ++li;
-  if (launch_ds(h, h->layers[li], h->ds[li], h->ds_feat, T, h->ds_b1, c.nin_filters2, 0, n, H, W, 0, 0, nullptr, st)) return 1;     // B1
+  if (launch_ds(h, lb, h->ds[li], h->ds_feat, T, h->ds_b1, c.nin_filters2, 0, n, H, W, 0, 0, nullptr, st)) return 1;     // B1
   ++li;
   if (launch_ds(h, h->layers[li], h->ds[li], h->ds_b1, c.nin_filters2, h->ds_nin, cps, 0, n, H, W, 0, 0, nullptr, st)) return 1;     // B2
   ++li;
@@ -1464,6 +1638,7 @@ int dcscn_destroy(dcscn_handle* h) {
   cudaFree(h->vbuf);
   cudaFree(h->ds_feat); cudaFree(h->ds_b1); cudaFree(h->ds_nin); cudaFree(h->ds_mid); cudaFree(h->ds_hr);
   for (auto& d : h->ds) { cudaFree(d.dw); cudaFree(d.pw); cudaFree(d.bias); cudaFree(d.alpha); }
+  cudaFree(h->ds_ab.pw); cudaFree(h->ds_ab.bias); cudaFree(h->ds_ab.alpha);
   cudaFree(h->io_x);
   cudaFree(h->io_x2);
   cudaFree(h->io_y);
@@ -1723,6 +1898,9 @@ int dcscn_set_option(dcscn_handle* h, const char* key, int64_t value) {
       h->plans.clear();
       h->last_plan = nullptr;
     }
+  } else if (k == "ds_impl") {
+    if (value != 0 && value != 1) return fail("ds_impl must be 0 (tile kernels) or 1 (first-generation kernels)");
+    h->ds_impl = (int)value;
   } else if (k == "wmap_wide") {
     h->wmap_wide = value ? 1 : 0;
   } else if (k == "halo_base") {
@@ -1788,7 +1966,12 @@ int dcscn_get_timings(dcscn_handle* h, float* ms, int capacity, int* count, char
     std::string s = "CNN1";
     if (h->cfg.depthwise_separable) {
       s = "";
-      for (const LayerDef& l : h->layers) s += (s.empty() ? "" : ",") + l.scope.substr(0, l.scope.find('/'));
+      for (const LayerDef& l : h->layers) {
+        std::string nm = l.scope.substr(0, l.scope.find('/'));
+        if (h->ds_impl == 0 && nm == "B1") continue;          // the tile kernels run A1 | B1 as one launch
+        if (h->ds_impl == 0 && nm == "A1") nm = "A1+B1";
+        s += (s.empty() ? "" : ",") + nm;
+      }
     } else {
       for (const TcLayer& t : h->tcl) s += "," + t.name;
       s += ",R-CNN1";

@@ -367,7 +367,7 @@ __global__ void planes_to_f32_kernel(const __half* hi, const __half* lo, float* 
 // patches by index into fp32 NHWC tensors (x scale = max_value / 255, loader.py:251-255), optionally mirrored left-right
 // (bit 31 of the index; the augmentation of loader.py:318-319).
 __global__ void __launch_bounds__(256) patch_gather_kernel(const uint8_t* __restrict__ store, const int* __restrict__ idx,
-                                                           float* __restrict__ out, int n, int H, int W, float scale) {
+                                                           float* __restrict__ out, int n, int H, int W, double scale) {
   const long long per = (long long)H * W, total = per * n;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int i = (int)(e / per);
@@ -379,7 +379,8 @@ __global__ void __launch_bounds__(256) patch_gather_kernel(const uint8_t* __rest
       const int y = r / W, x = r - y * W;
       src = y * W + (W - 1 - x);
     }
-    out[e] = (float)__ldg(store + k * per + src) * scale;
+    // numpy's `np.multiply(uint8_patch, max_value / 255.0)` is a float64 product, rounded to fp32 at the feed
+    out[e] = (float)((double)__ldg(store + k * per + src) * scale);
   }
 }
 

@@ -22,8 +22,13 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t cta_rank
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta_rank));
   return r;
 }
+// Arrival on an mbarrier of (possibly) the peer CTA.  RELAXED on purpose: the callers are epilogue warps handing a TMEM
+// accumulator back to the MMA issuer after `tcgen05.wait::ld` + `tcgen05.fence::before_thread_sync` - the values are in
+// registers, there is nothing in memory to publish.  The default `.release.cluster` form costs a MEMBAR.ALL.GPU + ERRBAR
+// per arrival (it waits for the epilogue's own outstanding global stores): ncu showed 20 % of all epilogue-warp stall
+// samples there and the MMA issuer parked on acc_empty (profiles/r2b_*).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA loads whose completion is signalled on an mbarrier that may live in the peer CTA of the pair.
 __device__ __forceinline__ void tma_load_4d_2sm(void* smem_dst, const CUtensorMap* tm, uint32_t bar_cluster_addr, int c0,

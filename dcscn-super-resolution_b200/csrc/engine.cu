@@ -2056,7 +2056,7 @@ static int patch_gather(dcscn_handle* h, const int32_t* indices, int n, float ma
     h->ps_idx_cap = n;
   }
   CUDA_TRY(cudaMemcpyAsync(h->ps_idx, indices, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, st));
-  const float scale = max_value / 255.0f;
+  const double scale = (double)max_value / 255.0;
   const int grid_lr = (int)std::min<size_t>((lr_px + 255) / 256, (size_t)h->sm_count * 8);
   const int grid_hr = (int)std::min<size_t>((hr_px + 255) / 256, (size_t)h->sm_count * 8);
   patch_gather_kernel<<<grid_lr, 256, 0, st>>>(h->ps_lr, h->ps_idx, h->io_x, n, h->ps_h, h->ps_w, scale);

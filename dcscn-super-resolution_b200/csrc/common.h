@@ -74,6 +74,12 @@ struct ConvTCParams {
   int seg_chunks;        // pipeline stages per accumulation segment (fp32 promotion period)
   int cluster_size;      // CTAs per cluster sharing (multicasting) the weight tiles: 1, 2 or 4
   const __half* wpack;   // packed weights [n_tile][tap][chunk][plane][n_pad x KC] (pre-swizzled)
+  // streaming kernel (conv_tc_halo2.cuh): weight-stage table of one (pixel tile, column tile) item, see kH2* there
+  const uint32_t* h2_stages;
+  int h2_nstages;
+  int h2_nseg;           // fp32-promotion segments per item
+  int h2_resident;       // all stages fit in shared memory: loaded once per CTA
+  float h2_trunc_beta;   // expected truncation loss per dominant UMMA, in ulps of the slot value (0 = no compensation)
   EpiParams epi;
 };
 

@@ -23,9 +23,20 @@
 
 namespace dcscn {
 
-constexpr int kH2MaxStages = 24;
+constexpr int kH2MaxStages = 32;
 constexpr int kH2MaxAcc = 4;
-constexpr int kH2BarBytes = 1024;
+constexpr int kH2BarBytes = 2048;        // mbarriers (4 x 32 + 2 x 4) + TMEM slot + the stage table
+constexpr int kH2MaxTable = 64;          // weight stages of one item (9 taps x up to 4 channel chunks, packed tails fewer)
+constexpr int kH2TableOff = 1280;        // byte offset of the stage table inside the barrier block
+
+// One weight stage = one [n_pad/2 rows x 128 bytes] (x planes) operand tile per CTA = four 16-channel K slices.
+// A full 64-channel chunk uses one stage per filter tap (4 slices of that tap).  The LAST chunk of a layer often holds
+// only 16 or 32 valid channels (cin_pad % 64): its stages pack the slices of 4 (or 2) consecutive taps, so no zero
+// columns are streamed from L2 - 9 tail stages shrink to 3 (or 5).  Stage word (host: build_h2_stages in engine.cu):
+//   bits 0-7 channel chunk | 8-11 taps in the stage | 12-15 first tap (dx * 3 + dy) | 16-19 16-channel slices per tap |
+//   bit 20 first stage of its chunk (wait for the A box) | bit 21 last stage of its chunk (release the A box) |
+//   bit 22 last stage of an fp32-promotion segment.
+constexpr uint32_t kH2ChunkFirst = 1u << 20, kH2ChunkLast = 1u << 21, kH2SegEnd = 1u << 22;
 
 __host__ __device__ inline size_t tc_halo2_misc_bytes() { return 1024 + kH2BarBytes + kRdotSmemBytes; }
 
@@ -51,6 +62,8 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
   uint64_t* acc_full = b_empty + kH2MaxStages;
   uint64_t* acc_empty = acc_full + kH2MaxAcc;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kH2MaxAcc);
+  uint32_t* s_tab = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(a_full) + kH2TableOff);
+  float* s_comp = reinterpret_cast<float*>(s_tab + kH2MaxTable);   // per accumulation slot: truncation compensation factor
   float* s_rdot = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a_full) + kH2BarBytes);
 
   const int warp = threadIdx.x >> 5;
@@ -82,11 +95,28 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
   }
   if (p.epi.mode == EPI_D2S_RDOT)
     for (int i = threadIdx.x; i < p.epi.rdot_taps * p.epi.d2s_cout; i += blockDim.x) s_rdot[i] = p.epi.rdot_w[i];
+  const int nst = p.h2_nstages;
+  for (int i = threadIdx.x; i < nst; i += blockDim.x) s_tab[i] = p.h2_stages[i];
+  if (threadIdx.x == 0) {
+    // slot j holds the dominant UMMAs of segment j: each of them truncates the fp32 accumulator toward zero, losing half
+    // an ulp on average.  The promotion adds back  trunc_beta * (dominant UMMAs of the slot) * ulp(value)  (see below).
+    int j = 0, dom = 0;
+    for (int i = 0; i < nst; ++i) {
+      const uint32_t e = p.h2_stages[i];
+      dom += (int)((e >> 8) & 15u) * (int)((e >> 16) & 15u);
+      if (e & kH2SegEnd) {
+        s_comp[j++] = p.h2_trunc_beta * (float)dom * 1.1920929e-07f;     // * 2^-23: ulp of a value in [1, 2)
+        dom = 0;
+      }
+    }
+    s_comp[j] = 0.f;                                                      // corrections-only slot: tiny accumulator
+  }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::cluster_sync();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const bool resident = p.h2_resident != 0;           // every weight stage of the layer stays in shared memory
 
   const ConvGeom& g = p.g;
   const int tiles_per_img = g.tiles_x * g.tiles_y;
@@ -95,12 +125,11 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
   const int num_items = groups * p.n_tiles;
   const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
-  const int total_a = p.chunks * 3;                   // segment units per tile: (channel chunk, dx); one A slot per chunk
-  const int nseg = (total_a + p.seg_chunks - 1) / p.seg_chunks;
+  const int nseg = p.h2_nseg;                         // fp32-promotion segments per tile (kH2SegEnd flags of the table)
   const int nslots = nseg + (NPLANES == 2 ? 1 : 0);   // accumulation slots (= promotions) per tile
 
   if (warp < kEpiWarp0) {
-    ptx::setmaxnreg_dec<kRegsIssue>();
+    ptx::setmaxnreg_dec<48>();   // 128 x 48 + 256 x 232 = 64 K registers exactly
     if (warp == 0) {
       // ============================== TMA producer: A boxes (both CTAs) ==============================
       if (lane == 0) {
@@ -136,16 +165,14 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
         uint32_t phb = 0;
         for (int item = cluster_id; item < num_items; item += num_clusters) {
           const int n_tile = item % p.n_tiles;
-          for (int ai = 0; ai < total_a; ++ai) {
-            const int ch = ai / 3, dx = ai - ch * 3;
-            for (int dy = 0; dy < 3; ++dy) {
-              ptx::mbar_wait(&b_empty[b], phb ^ 1);
-              const uint32_t lead = ptx::mapa_shared(ptx::smem_u32(&b_full[b]), 0);
-              if (leader) ptx::mbar_arrive_expect_tx(&b_full[b], (uint32_t)(2 * B_STAGE));
-              const int wblock = ((n_tile * 9 + dy * 3 + dx) * p.chunks + ch) * 2 + (int)rank;
-              ptx::tma_load_2d_2sm(smem_b + (size_t)b * B_STAGE, &tm_w, lead, 0, wblock * wrows);
-              if (++b == num_b) { b = 0; phb ^= 1; }
-            }
+          if (resident && item != cluster_id) break;          // loaded once, used by every tile of this CTA
+          for (int st = 0; st < nst; ++st) {
+            ptx::mbar_wait(&b_empty[b], phb ^ 1);
+            const uint32_t lead = ptx::mapa_shared(ptx::smem_u32(&b_full[b]), 0);
+            if (leader) ptx::mbar_arrive_expect_tx(&b_full[b], (uint32_t)(2 * B_STAGE));
+            const int wblock = ((n_tile * nst + st) * 2 + (int)rank);
+            ptx::tma_load_2d_2sm(smem_b + (size_t)b * B_STAGE, &tm_w, lead, 0, wblock * wrows);
+            if (++b == num_b) { b = 0; phb ^= 1; }
           }
         }
       }
@@ -157,59 +184,71 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
       uint32_t spa = 0, spb = 0;
       uint32_t slot = 0;                                  // running accumulation-slot counter; buffer = slot % 3
       for (int item = cluster_id; item < num_items; item += num_clusters) {
-        {  // the slot that takes the dominant products of segment 0
-          ptx::mbar_wait(&acc_empty[slot % nbuf], ((slot / nbuf) & 1) ^ 1);
-        }
-        for (int s = 0; s < nseg; ++s) {
-          const uint32_t sd = slot + (uint32_t)s, sc = sd + 1;
-          if (NPLANES == 2) ptx::mbar_wait(&acc_empty[sc % nbuf], ((sc / nbuf) & 1) ^ 1);
+        ptx::mbar_wait(&acc_empty[slot % nbuf], ((slot / nbuf) & 1) ^ 1);   // takes the dominant products of segment 0
+        int s = 0;                                          // segment of the tile
+        bool seg_open = true;
+        uint32_t sd = slot, sc = slot + 1, tmem_d = 0, tmem_c = 0, acc_c = 0, acc_d = 0;
+        for (int st = 0; st < nst; ++st) {
+          const uint32_t e = s_tab[st];
+          const int ntaps = (int)((e >> 8) & 15u), tap0 = (int)((e >> 12) & 15u), kt = (int)((e >> 16) & 15u);
+          if (seg_open) {
+            sd = slot + (uint32_t)s;
+            sc = sd + 1;
+            if (NPLANES == 2) ptx::mbar_wait(&acc_empty[sc % nbuf], ((sc / nbuf) & 1) ^ 1);
+            tmem_d = tmem_base + (sd % nbuf) * (uint32_t)acc_stride;
+            tmem_c = tmem_base + (sc % nbuf) * (uint32_t)acc_stride;
+            acc_c = 0;                                              // corrections open their slot
+            acc_d = (NPLANES == 2 && s > 0) ? 1u : 0u;              // slot already holds the previous corrections
+            seg_open = false;
+          }
+          if (e & kH2ChunkFirst) ptx::mbar_wait(&a_full[sa], spa);  // the chunk's halo box serves all its stages
+          ptx::mbar_wait(&b_full[sb], spb);
           ptx::tc_fence_after();
-          const uint32_t tmem_d = tmem_base + (sd % nbuf) * (uint32_t)acc_stride;
-          const uint32_t tmem_c = tmem_base + (sc % nbuf) * (uint32_t)acc_stride;
-          uint32_t acc_c = 0;                                           // corrections open their slot
-          uint32_t acc_d = (NPLANES == 2 && s > 0) ? 1u : 0u;           // slot already holds the previous corrections
-          const int a0 = s * p.seg_chunks;
-          const int a1 = (a0 + p.seg_chunks < total_a) ? a0 + p.seg_chunks : total_a;
-          for (int ai = a0; ai < a1; ++ai) {
-            const int ch = ai / 3, dx = ai - ch * 3;
-            int ksteps = (p.cin_pad - ch * KC);
-            ksteps = (ksteps > KC ? KC : ksteps) >> 4;
-            if (dx == 0) ptx::mbar_wait(&a_full[sa], spa);   // a chunk's box serves its three dx units (any segment)
-            for (int dy = 0; dy < 3; ++dy) {
-              ptx::mbar_wait(&b_full[sb], spb);
-              ptx::tc_fence_after();
-              const uint32_t a_addr = sa_u32 + (uint32_t)sa * (uint32_t)A_SLOT + (uint32_t)(dy * kHalo1W + dx) * 128u;
-              const uint32_t b_addr = sb_u32 + (uint32_t)sb * (uint32_t)B_STAGE;
-              const uint32_t lb_hi = desc_lo_t<KC>(b_addr), lb_lo = desc_lo_t<KC>(b_addr + BH_BYTES);
-              if (ptx::elect_one()) {
-#pragma unroll 1
-                for (int ks = 0; ks < ksteps; ++ks) {
-                  const uint32_t kadd = (uint32_t)ks * 2u;
-                  const uint64_t da_hi = make_desc64_halo1(a_addr + ks * 32, 0);
-                  if (NPLANES == 2) {
-                    ptx::mma_f16_ss_2sm(tmem_c, make_desc64_halo1(a_addr + AH_BYTES + ks * 32, 0), make_desc64_t<KC>(lb_hi + kadd), idesc, acc_c);
-                    ptx::mma_f16_ss_2sm(tmem_c, da_hi, make_desc64_t<KC>(lb_lo + kadd), idesc, 1);
-                    acc_c = 1;
-                  }
-                  ptx::mma_f16_ss_2sm(tmem_d, da_hi, make_desc64_t<KC>(lb_hi + kadd), idesc, acc_d);
-                  acc_d = 1;
-                }
-                ptx::mma_commit_2sm(&b_empty[sb], 3);
-                if (dy == 2 && dx == 2) ptx::mma_commit_2sm(&a_empty[sa], 3);
-              }
-              acc_c = 1;
-              acc_d = 1;
-              __syncwarp();
-              if (++sb == num_b) { sb = 0; spb ^= 1; }
-            }
-            if (dx == 2 && ++sa == num_a) { sa = 0; spa ^= 1; }
-          }
+          const uint32_t a_base = sa_u32 + (uint32_t)sa * (uint32_t)A_SLOT;
+          const uint32_t b_addr = sb_u32 + (uint32_t)sb * (uint32_t)B_STAGE;
+          const uint32_t lb_hi = desc_lo_t<KC>(b_addr), lb_lo = desc_lo_t<KC>(b_addr + BH_BYTES);
           if (ptx::elect_one()) {
-            ptx::mma_commit_2sm(&acc_full[sd % nbuf], 3);
-            if (NPLANES == 2 && s == nseg - 1) ptx::mma_commit_2sm(&acc_full[sc % nbuf], 3);
+            uint32_t col = 0;                                       // 16-channel slice inside the stage's 128-byte rows
+#pragma unroll 1
+            for (int j = 0; j < ntaps; ++j) {
+              const int tap = tap0 + j, dx = tap / 3, dy = tap - dx * 3;
+              const uint32_t a_addr = a_base + (uint32_t)(dy * kHalo1W + dx) * 128u;
+#pragma unroll 1
+              for (int ks = 0; ks < kt; ++ks, ++col) {
+                const uint32_t kadd = col * 2u;
+                const uint64_t da_hi = make_desc64_halo1(a_addr + ks * 32, 0);
+                if (NPLANES == 2) {
+                  ptx::mma_f16_ss_2sm(tmem_c, make_desc64_halo1(a_addr + AH_BYTES + ks * 32, 0), make_desc64_t<KC>(lb_hi + kadd), idesc, acc_c);
+                  ptx::mma_f16_ss_2sm(tmem_c, da_hi, make_desc64_t<KC>(lb_lo + kadd), idesc, 1);
+                  acc_c = 1;
+                }
+                ptx::mma_f16_ss_2sm(tmem_d, da_hi, make_desc64_t<KC>(lb_hi + kadd), idesc, acc_d);
+                acc_d = 1;
+              }
+            }
+            if (!resident) ptx::mma_commit_2sm(&b_empty[sb], 3);
+            if (e & kH2ChunkLast) ptx::mma_commit_2sm(&a_empty[sa], 3);
+            if (e & kH2SegEnd) {
+              ptx::mma_commit_2sm(&acc_full[sd % nbuf], 3);
+              if (NPLANES == 2 && s == nseg - 1) ptx::mma_commit_2sm(&acc_full[sc % nbuf], 3);
+            }
           }
+          acc_c = 1;
+          acc_d = 1;
           __syncwarp();
+          if (resident) {
+            ++sb;                                             // stage st lives in ring slot st; phase 0 stays complete
+          } else if (++sb == num_b) {
+            sb = 0;
+            spb ^= 1;
+          }
+          if ((e & kH2ChunkLast) && ++sa == num_a) { sa = 0; spa ^= 1; }
+          if (e & kH2SegEnd) {
+            ++s;
+            seg_open = true;
+          }
         }
+        if (resident) sb = 0;
         slot += (uint32_t)nslots;
       }
     }
@@ -250,8 +289,10 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
         ptx::mbar_wait(&acc_full[buf], (slot / nbuf) & 1);
         ptx::tc_fence_after();
         const uint32_t taddr = taddr0 + buf * (uint32_t)acc_stride;
+        const float comp = s_comp[s];
         // fp32 round-to-nearest promotion of the slot: wide TMEM loads (64 / 32 columns per instruction); columns
         // past this thread's share may be read (they stay inside the 512 allocated columns) but are never stored.
+        // `h2_comp(v)` = v + sign(v) * 2^exponent(v) * comp: the expected truncation loss of the slot's UMMAs.
 #pragma unroll
         for (int j = 0; j < kMaxColChunks; j += 4) {
           if (j < my_chunks) {
@@ -259,12 +300,14 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
               float v[64];
               ptx::tmem_ld64(taddr + j * 16, v);
 #pragma unroll
-              for (int i = 0; i < 64; ++i) sum[j + (i >> 4)][i & 15] += v[i];
+              for (int i = 0; i < 64; ++i)
+                sum[j + (i >> 4)][i & 15] += fmaf(__uint_as_float(__float_as_uint(v[i]) & 0xFF800000u), comp, v[i]);
             } else {
               float v[32];
               ptx::tmem_ld32(taddr + j * 16, v);
 #pragma unroll
-              for (int i = 0; i < 32; ++i) sum[j + (i >> 4)][i & 15] += v[i];
+              for (int i = 0; i < 32; ++i)
+                sum[j + (i >> 4)][i & 15] += fmaf(__uint_as_float(__float_as_uint(v[i]) & 0xFF800000u), comp, v[i]);
             }
           }
         }

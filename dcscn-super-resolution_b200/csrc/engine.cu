@@ -96,6 +96,10 @@ struct TcLayer {
   CUtensorMap tm_w_wide;        // the same bytes as rows of 1024 bytes (fp32 elements, no swizzle): fewer, longer TMA rows
   bool has_wide = false;
   bool has_pair = false;
+  // streaming 3x3 kernel: weight-stage table of one item (conv_tc_halo2.cuh); non-empty = d_wpair is in stage order
+  std::vector<uint32_t> h2_stages;
+  int h2_nseg = 0;
+  uint32_t* d_h2_stages = nullptr;
   int* d_pair_src = nullptr;    // training: flat parameter index behind every hi-plane element of d_wpair (-1 = zero)
   size_t pair_src_n = 0;
 };
@@ -107,6 +111,8 @@ struct GatherJob {   // training: dst[i] = d_w[map[i]] where map[i] >= 0 (biases
 };
 
 struct TcLaunch {
+  int layer_index = -1;          // index into dcscn_handle::tcl (forward) or ::bwd (dgrad twins): the layer whose CURRENT
+  bool layer_bwd = false;        // power-of-two weight scale the epilogue has to undo (it changes when a layer is re-packed)
   CUtensorMap tm_hi, tm_lo, tm_w;
   bool pair = false;
   int pair_grid = 0, pair_stages = 0, pair_seg = 1;
@@ -227,6 +233,7 @@ struct dcscn_handle {
   int halo = 3;                      // 3x3 layers: halo-reuse CTA-pair kernel, 1 = three 18x8 boxes, 2 = one 18x10 box per chunk
                                      // (two-pass segments), 3 = the same box with streaming stages (conv_tc_halo2.cuh)
   int halo_base = 0;                 // single-box variant: set the descriptor base-offset field
+  float trunc_beta = 0.f;            // streaming kernel: truncation compensation per dominant UMMA, in ulps (option, x 1e-3)
   int wmap_wide = 0;                 // streaming kernel: fetch weight stages as rows of 1024 bytes instead of 128
   int timing = 0;
   int fuse_last = 1;                 // fold the per-pixel half of R-CNN1 into the last Up-PS epilogue
@@ -392,7 +399,80 @@ static void choose_tiling(int n_total_pad16, int* n_tiles, int* n_pad, int cap =
 
 // Values (unscaled fp32) of the CTA-pair operand image of a layer, one per hi-plane element, in image order:
 // [n_tile][tap][chunk][rank][n_pad/2 rows x 64 halves], each row 128-byte swizzled (16-byte chunk j of row r at j ^ (r & 7)).
+static int tile_cap(const dcscn_handle* h, int ksz);
+
+// Weight-stage table of the streaming 3x3 kernel (see conv_tc_halo2.cuh): full 64-channel chunks take one stage per tap,
+// a last chunk with 16 / 32 valid channels packs 4 / 2 taps per stage.  `seg_units` = promotion period in units of 12
+// dominant UMMAs (3 taps x 4 slices), like the (chunk, dx) units of the two-pass kernels.
+static void build_h2_stages(int cin_pad, int seg_units, std::vector<uint32_t>& tab, int* nseg) {
+  tab.clear();
+  const int chunks = (cin_pad + 63) / 64, target = 12 * std::max(1, seg_units);
+  int dom = 0, segs = 0;
+  for (int ch = 0; ch < chunks; ++ch) {
+    const int kt = std::min(64, cin_pad - ch * 64) / 16;            // 16-channel slices per tap in this chunk (1..4)
+    const int per = kt >= 3 ? 1 : 4 / kt;                           // taps per stage
+    for (int t0 = 0; t0 < 9; t0 += per) {
+      const int nt = std::min(per, 9 - t0);
+      uint32_t e = (uint32_t)ch | ((uint32_t)nt << 8) | ((uint32_t)t0 << 12) | ((uint32_t)kt << 16);
+      if (t0 == 0) e |= kH2ChunkFirst;
+      if (t0 + nt >= 9) e |= kH2ChunkLast;
+      dom += nt * kt;
+      const bool last = (ch == chunks - 1) && (t0 + nt >= 9);
+      if (dom >= target || last) {
+        e |= kH2SegEnd;
+        dom = 0;
+        ++segs;
+      }
+      tab.push_back(e);
+    }
+  }
+  *nseg = segs;
+}
+
+// Stage-ordered operand image of the streaming kernel: [n_tile][stage][rank][n_pad/2 rows x 64 halves]; the four
+// 16-channel slices of a row belong to (tap0 + q / kt, slice q % kt) of the stage's chunk.
+static void pair_image_h2(const TcLayer& t, std::vector<float>& img) {
+  const int n_total = t.n_tiles * t.n_pad, nst = (int)t.h2_stages.size();
+  std::vector<float> wq((size_t)9 * t.cin_pad * n_total, 0.f);     // dense, channel-position-indexed  Wq[tap][q][n]
+  for (int tp = 0; tp < 9; ++tp)
+    for (int ci = 0; ci < t.cin; ++ci) {
+      const int q = t.in_map[ci];
+      for (int co = 0; co < t.cout; ++co)
+        wq[((size_t)tp * t.cin_pad + q) * n_total + co] = t.w_host[((size_t)tp * t.cin + ci) * t.cout + co];
+    }
+  const int half_rows = t.n_pad / 2;
+  const size_t half_elems = (size_t)half_rows * 64;
+  img.assign((size_t)t.n_tiles * nst * 2 * half_elems, 0.f);
+  for (int nt = 0; nt < t.n_tiles; ++nt)
+    for (int st = 0; st < nst; ++st) {
+      const uint32_t e = t.h2_stages[st];
+      const int ch = (int)(e & 255u), ntaps = (int)((e >> 8) & 15u), tap0 = (int)((e >> 12) & 15u), kt = (int)((e >> 16) & 15u);
+      for (int rk = 0; rk < 2; ++rk) {
+        float* base = img.data() + (((size_t)nt * nst + st) * 2 + rk) * half_elems;
+        for (int r = 0; r < half_rows; ++r) {
+          const int n = nt * t.n_pad + rk * half_rows + r;
+          const int sw = r & 7;
+          for (int col = 0; col < ntaps * kt; ++col) {
+            const int tap = tap0 + col / kt, ks = col % kt;
+            const int dx = tap / 3, dy = tap % 3;                   // table order is dx-major; HWIO taps are ky * 3 + kx
+            const int hwio_tap = dy * 3 + dx;
+            for (int e16 = 0; e16 < 16; ++e16) {
+              const int q = ch * 64 + ks * 16 + e16;
+              if (q >= t.cin_pad) continue;
+              const int kk = col * 16 + e16;
+              base[(size_t)r * 64 + (size_t)((kk / 8) ^ sw) * 8 + (kk % 8)] = wq[((size_t)hwio_tap * t.cin_pad + q) * n_total + n];
+            }
+          }
+        }
+      }
+    }
+}
+
 static void pair_image(const TcLayer& t, std::vector<float>& img) {
+  if (!t.h2_stages.empty()) {
+    pair_image_h2(t, img);
+    return;
+  }
   const int taps = t.ksz * t.ksz, chunks = (t.cin_pad + 63) / 64, n_total = t.n_tiles * t.n_pad;
   std::vector<float> wq((size_t)taps * t.cin_pad * n_total, 0.f);   // dense, channel-position-indexed  Wq[tap][q][n]
   for (int tp = 0; tp < taps; ++tp)
@@ -469,6 +549,19 @@ static int pack_tc_layer(dcscn_handle* h, TcLayer& t) {
       }
   if (upload(&t.d_wpack, pack, h)) return 1;
   t.has_pair = false;
+  t.h2_stages.clear();
+  t.h2_nseg = 0;
+  if (need_pair && t.ksz == 3 && tile_cap(h, 3) < 256 && 3 * t.n_pad <= 512) {   // streaming kernel: stage-ordered image
+    int seg = h->seg_chunks > 0 ? h->seg_chunks : (t.n_pad >= 144 ? 1 : (t.n_pad >= 112 ? 2 : 3));
+    if (const char* ov = getenv("DCSCN_SEG")) {   // experiments: "CNN2=1,CNN5=2" overrides the promotion period per layer
+      const std::string key = t.name + "=";
+      const char* hit = strstr(ov, key.c_str());
+      if (hit && (hit == ov || hit[-1] == ',')) seg = std::max(1, atoi(hit + key.size()));
+    }
+    build_h2_stages(t.cin_pad, seg, t.h2_stages, &t.h2_nseg);
+    if ((int)t.h2_stages.size() > kH2MaxTable) return fail("layer %s: %zu weight stages exceed the kernel's table", t.name.c_str(), t.h2_stages.size());
+    if (upload(&t.d_h2_stages, t.h2_stages, h)) return 1;
+  }
   if (need_pair) {
     const int half_rows = t.n_pad / 2;
     const size_t half_elems = (size_t)half_rows * 64;
@@ -548,6 +641,8 @@ static void free_tc(TcLayer& t) {
   dev_free(t.d_wref);
   dev_free(t.d_in_map);
   dev_free(t.d_pair_src);
+  dev_free(t.d_h2_stages);
+  t.d_h2_stages = nullptr;
   t.d_pair_src = nullptr;
   t.d_wpack = t.d_wpair = nullptr;
   t.d_bias = t.d_alpha = t.d_wref = nullptr;
@@ -556,7 +651,7 @@ static void free_tc(TcLayer& t) {
 
 static void adopt_tc(TcLayer& t, const TcLayer& old) {  // keep the device allocations of the previous packing
   t.d_wpack = old.d_wpack; t.d_wpair = old.d_wpair; t.d_bias = old.d_bias; t.d_alpha = old.d_alpha;
-  t.d_wref = old.d_wref; t.d_in_map = old.d_in_map; t.d_pair_src = old.d_pair_src;
+  t.d_wref = old.d_wref; t.d_in_map = old.d_in_map; t.d_pair_src = old.d_pair_src; t.d_h2_stages = old.d_h2_stages;
 }
 
 // (Re)builds every device-side weight image from the host fp32 parameters.
@@ -853,7 +948,14 @@ static int add_tc_launch(dcscn_handle* h, Plan* pl, const TcLayer& t, const __ha
   L.p.epi = epi;
   L.p.epi.bias = t.d_bias;
   L.p.epi.alpha = t.d_alpha;
-  L.p.epi.out_scale = 1.0f / t.wscale;
+  L.p.epi.out_scale = 1.0f / t.wscale;   // refreshed at every launch (launch_tc): a re-pack may pick another scale
+  if (!h->tcl.empty() && &t >= h->tcl.data() && &t < h->tcl.data() + h->tcl.size()) {
+    L.layer_index = (int)(&t - h->tcl.data());
+    L.layer_bwd = false;
+  } else if (!h->bwd.empty() && &t >= h->bwd.data() && &t < h->bwd.data() + h->bwd.size()) {
+    L.layer_index = (int)(&t - h->bwd.data());
+    L.layer_bwd = true;
+  }
   L.p.epi.n_valid = t.n_valid;
   L.p.epi.drop_ntotal = pad16(t.cout);   // keep-mask index stride = slot width, whatever the column tiling
 
@@ -957,29 +1059,34 @@ static int add_tc_launch(dcscn_handle* h, Plan* pl, const TcLayer& t, const __ha
 
   // streaming halo kernel: every ring slot is prefetch depth; three (n_pad > 128) or four TMEM accumulation buffers
   L.halo2 = false;
-  if (pair3x3 && 3 * t.n_pad <= 512) {
+  if (pair3x3 && !t.h2_stages.empty()) {
     const size_t a_slot = tc_halo1_a_slot_bytes(planes(h)), b_stage = tc_halo_b_stage_bytes(planes(h), t.n_pad);
     const long long total = 227 * 1024 - (long long)tc_halo2_misc_bytes();
+    const int nst = (int)t.h2_stages.size();
     int na = 2;
     long long nb = (total - na * (long long)a_slot) / (long long)b_stage;
-    if ((total - 3 * (long long)a_slot) / (long long)b_stage >= 9) {   // thin layers: a third A slot, still >= 9 weight stages
+    bool resident = false;
+    if (t.n_tiles == 1 && nst <= kH2MaxStages && (long long)nst * (long long)b_stage + 2 * (long long)a_slot <= total) {
+      // thin layers: the whole weight image of this CTA half stays in shared memory, every other byte goes to A boxes
+      resident = true;
+      nb = nst;
+      na = (int)std::min<long long>(4, (total - (long long)nst * (long long)b_stage) / (long long)a_slot);
+    } else if ((total - 3 * (long long)a_slot) / (long long)b_stage >= 9) {   // a third A slot, still >= 9 weight stages
       na = 3;
       nb = (total - 3 * (long long)a_slot) / (long long)b_stage;
     }
     nb = std::min<long long>(nb, kH2MaxStages);
-    if (nb >= 3) {
-      int seg = h->seg_chunks > 0 ? h->seg_chunks : (t.n_pad >= 144 ? 1 : (t.n_pad >= 112 ? 2 : 3));
-      if (const char* ov = getenv("DCSCN_SEG")) {   // experiments: "CNN2=1,CNN5=2" overrides the promotion period per layer
-        const std::string key = t.name + "=";
-        const char* hit = strstr(ov, key.c_str());
-        if (hit && (hit == ov || hit[-1] == ',')) seg = std::max(1, atoi(hit + key.size()));
-      }
-      seg = std::min(seg, 3 * ((t.cin_pad + 63) / 64));
+    if (nb >= 3 || resident) {
       L.halo2 = true;
-      L.halo2_seg = seg;
+      L.halo2_seg = 0;
       L.halo2_na = na;
       L.halo2_nb = (int)nb;
       L.halo2_smem = na * a_slot + (size_t)nb * b_stage + tc_halo2_misc_bytes();
+      L.p.h2_stages = t.d_h2_stages;
+      L.p.h2_nstages = nst;
+      L.p.h2_nseg = t.h2_nseg;
+      L.p.h2_resident = resident ? 1 : 0;
+      L.p.h2_trunc_beta = h->trunc_beta;
       if (!L.halo1) {   // the A maps of the single-box variants are shared
         if (encode_map(h, &L.t1_hi, src_hi, t.cin_pad, src_pitch, n, H, W, kHaloTH + 2, kHalo1W, 64)) return 1;
         if (planes(h) == 2) {
@@ -1270,15 +1377,21 @@ static int launch_tc_halo2(dcscn_handle* h, const TcLaunch& L, cudaStream_t st) 
   ConvTCParams p = L.p;
   p.g = L.hg;
   p.cluster_size = 2;
-  p.seg_chunks = L.halo2_seg;
   const bool wide = h->wmap_wide && L.has_wide;
   CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc_halo2_kernel<NPL>, L.t1_hi, L.t1_lo, wide ? L.tm_w_wide : L.tm_w, p, L.halo2_na,
                               L.halo2_nb, wide ? 1 : 0));
   return 0;
 }
 
-static int launch_tc(dcscn_handle* h, const TcLaunch& L, cudaStream_t st) {
+static int launch_tc(dcscn_handle* h, const TcLaunch& Lc, cudaStream_t st) {
   h->launches++;
+  // Cached plans outlive weight re-packs.  A re-pack keeps the device allocations (so the plan's pointers stay valid) but
+  // may choose a different power-of-two weight scale: take the epilogue's 1 / scale from the layer as it is NOW.
+  TcLaunch& L = const_cast<TcLaunch&>(Lc);
+  if (L.layer_index >= 0) {
+    const std::vector<TcLayer>& ls = L.layer_bwd ? h->bwd : h->tcl;
+    if (L.layer_index < (int)ls.size()) L.p.epi.out_scale = 1.0f / ls[L.layer_index].wscale;
+  }
   if (h->conv_impl == 1) {
     const long long total = (long long)L.ref.g.n_img * L.ref.g.H * L.ref.g.W * (L.ref.n_total_pad >> 4);
     const int grid = (int)std::min<long long>((total + 127) / 128, (long long)h->sm_count * 16);
@@ -1288,6 +1401,8 @@ static int launch_tc(dcscn_handle* h, const TcLaunch& L, cudaStream_t st) {
   }
   const int npl = planes(h);
   if (h->pair && h->halo == 3 && L.halo2 && h->kc == 64) return npl == 2 ? launch_tc_halo2<2>(h, L, st) : launch_tc_halo2<1>(h, L, st);
+  if (h->pair && h->halo == 3 && L.p.ksz == 3 && L.pair && h->kc == 64)
+    return fail("internal: 3x3 layer packed for the streaming kernel has no streaming launch shape");
   if (h->pair && h->halo >= 2 && L.halo1 && h->kc == 64) return npl == 2 ? launch_tc_halo1<2>(h, L, st) : launch_tc_halo1<1>(h, L, st);
   if (h->pair && h->halo == 1 && L.halo && h->kc == 64) return npl == 2 ? launch_tc_halo<2>(h, L, st) : launch_tc_halo<1>(h, L, st);
   if (h->pair && L.pair && h->kc == 64) return npl == 2 ? launch_tc_pair<2>(h, L, st) : launch_tc_pair<1>(h, L, st);
@@ -1898,6 +2013,10 @@ int dcscn_set_option(dcscn_handle* h, const char* key, int64_t value) {
       h->plans.clear();
       h->last_plan = nullptr;
     }
+  } else if (k == "trunc_beta_milli") {
+    h->trunc_beta = (float)value * 1e-3f;
+    h->plans.clear();
+    h->last_plan = nullptr;
   } else if (k == "ds_impl") {
     if (value != 0 && value != 1) return fail("ds_impl must be 0 (tile kernels) or 1 (first-generation kernels)");
     h->ds_impl = (int)value;
@@ -1946,6 +2065,7 @@ int dcscn_set_option(dcscn_handle* h, const char* key, int64_t value) {
   } else if (k == "seg_chunks") {
     if (value < 0 || value > 4096) return fail("seg_chunks must be >= 0 (0 = automatic)");
     h->seg_chunks = (int)value;
+    h->params_dirty = true;     // the streaming kernel's stage tables carry the segment boundaries
     h->plans.clear();
     h->last_plan = nullptr;
   } else {

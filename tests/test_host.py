@@ -132,6 +132,49 @@ def test_split_images():
     assert util.get_split_images(img, 16) is None
 
 
+def test_sharded_patch_order_is_a_partition():
+    """Data-parallel training: every rank draws the same permutation and serves its own residue class, so the ranks'
+    patches are disjoint and together cover a pass (helper/loader.py: set_shard)."""
+    from helper import loader
+    world, count = 4, 37
+    served = []
+    for rank in range(world):
+        ds = loader._ShuffledOrder()
+        ds.count = count
+        ds.set_shard(rank, world, seed=99)
+        ds.init_batch_index()
+        got = []
+        while ds.index < ds.count:
+            got.append(ds.get_next_image_no())
+        served.append(got)
+    flat = [k for g in served for k in g]
+    assert sorted(flat) == list(range(count))
+    assert max(len(g) for g in served) - min(len(g) for g in served) <= 1
+    # a plain (unsharded) order is unchanged: one pass serves every index once
+    ds = loader._ShuffledOrder()
+    ds.count = count
+    ds.init_batch_index()
+    assert sorted(ds.get_next_image_no() for _ in range(count)) == list(range(count))
+
+
+def test_adam_step_is_recovered_from_beta2_power():
+    """beta1_power = 0.9^(t+1) underflows in float32 after ~980 updates; beta2_power = 0.999^(t+1) does not."""
+    import DCSCN
+    m = object.__new__(DCSCN.SuperResolution)
+    m.beta1, m.beta2 = 0.9, 0.999
+
+    class Reader:
+        def __init__(self, t):
+            self.v = {"beta1_power": np.float32(0.9) ** np.float32(t + 1), "beta2_power": np.float32(0.999 ** (t + 1))}
+        def has_tensor(self, k):
+            return k in self.v
+        def get_tensor(self, k):
+            return np.asarray(self.v[k], np.float32)
+    for t in (0, 3, 500, 2000, 40000):
+        assert abs(m._adam_step_from_powers(Reader(t)) - t) <= max(1, t // 2000), t
+    assert float(Reader(2000).v["beta1_power"]) == 0.0           # what the old beta1-only recovery saw
+
+
 def test_package_does_not_import_oracle():
     """The product path must never route through the oracle."""
     for path in glob.glob(os.path.join(PKG, "**", "*.py"), recursive=True) + glob.glob(os.path.join(PKG, "csrc", "*")):

@@ -590,11 +590,23 @@ class SuperResolution:
         """DCSCN.py:547-586: self-ensemble of up to 8 flips, float64 mean."""
         h, w = input_image.shape[:2]
         if bicubic_input_image is None:
-            bicubic_input_image = util.resize_image_by_pil(input_image, self.scale,
-                                                           resampling_method=self.resampling_method)
+            rank, world = _dist_rank_world()
+            on_device = (self.max_value == 255.0 and self.resampling_method == BICUBIC_METHOD_STRING and world == 1
+                         and input_image.dtype != np.uint8 and getattr(self, "engine", None) is not None
+                         and hasattr(self.engine, "forward_ensemble_host"))
+            if not on_device:
+                bicubic_input_image = util.resize_image_by_pil(input_image, self.scale,
+                                                               resampling_method=self.resampling_method)
+            # else: the engine forms Pillow's bicubic up-scale in HBM (bit for bit the same values) - only the LR image
+            # crosses PCIe and no host-side resize sits in front of the GPU
         if self.max_value != 255.0:
             input_image = np.multiply(input_image, self.max_value / 255.0)
             bicubic_input_image = np.multiply(bicubic_input_image, self.max_value / 255.0)
+        if bicubic_input_image is None:      # device-side bicubic (single process)
+            if self.self_ensemble > 1:
+                return self.engine.forward_ensemble_host(input_image, None, self.self_ensemble)
+            x = np.ascontiguousarray(input_image, dtype=np.float32).reshape(1, h, w, 1)
+            return self.engine.forward_host(x, None)[0]
 
         if self.self_ensemble > 1:
             # The flips are independent: rank r of a torch.distributed job computes flips r, r + world, ... and the

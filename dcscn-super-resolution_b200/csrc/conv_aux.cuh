@@ -361,6 +361,48 @@ __global__ void planes_to_f32_kernel(const __half* hi, const __half* lo, float* 
   }
 }
 
+// ------------------------------------------------------------- Pillow bicubic resize on the device ------------
+// Bit-exact restatement of `Image.resize(BICUBIC)` for mode 'F' images (reference helper/utilty.py:211-239 ->
+// Pillow src/libImaging/Resample.c, see helper/pil_resample.py): horizontal pass, float32 intermediate, vertical pass;
+// every sample is (float) sum_x (double)pixel * w[x] accumulated in window order.  __dmul_rn / __dadd_rn keep the
+// compiler from fusing the multiply-add (Pillow's x86-64 build has no FMA), which is what makes it bit-exact.
+struct PilAxis {
+  const double* k;     // [out][ksize] normalised weights
+  const int* bounds;   // [out][2] first input index, taps
+  int ksize;
+};
+
+__global__ void __launch_bounds__(256) pil_resample_h_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                             long long rows, int W, int OW, const PilAxis ax) {
+  const long long total = rows * OW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / OW;
+    const int xx = (int)(i - row * OW);
+    const int x0 = __ldg(ax.bounds + 2 * xx), cnt = __ldg(ax.bounds + 2 * xx + 1);
+    const double* k = ax.k + (size_t)xx * ax.ksize;
+    const float* p = src + row * W + x0;
+    double ss = 0.0;
+    for (int x = 0; x < cnt; ++x) ss = __dadd_rn(ss, __dmul_rn((double)__ldg(p + x), __ldg(k + x)));
+    dst[i] = (float)ss;
+  }
+}
+
+__global__ void __launch_bounds__(256) pil_resample_v_kernel(const float* __restrict__ src, float* __restrict__ dst, int n,
+                                                             int H, int OH, int OW, const PilAxis ax) {
+  const long long per = (long long)OH * OW, total = per * n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int img = (int)(i / per);
+    const int r = (int)(i - (long long)img * per);
+    const int yy = r / OW, xx = r - yy * OW;
+    const int y0 = __ldg(ax.bounds + 2 * yy), cnt = __ldg(ax.bounds + 2 * yy + 1);
+    const double* k = ax.k + (size_t)yy * ax.ksize;
+    const float* p = src + ((size_t)img * H + y0) * OW + xx;
+    double ss = 0.0;
+    for (int y = 0; y < cnt; ++y) ss = __dadd_rn(ss, __dmul_rn((double)__ldg(p + (size_t)y * OW), __ldg(k + y)));
+    dst[i] = (float)ss;
+  }
+}
+
 // ------------------------------------------------------------- training patch store ---------------------------
 // What `build_input_batch` + the feed of `train_batch` did on the host (DCSCN.py:186-190, 415-420; patches of
 // loader.BatchDataSets, loader.py:236-249): the uint8 patch arrays live in HBM, one launch gathers the mini-batch's

@@ -207,6 +207,11 @@ struct dcscn_handle {
   int ps_h = 0, ps_w = 0;
   int* ps_idx = nullptr;
   int ps_idx_cap = 0;
+  // Pillow-bicubic resampling tables per (input size, output size) and the float32 intermediate of the two passes
+  struct PilTable { int in = 0, out = 0, ksize = 0; double* k = nullptr; int* bounds = nullptr; };
+  std::vector<PilTable> pil_tables;
+  float* pil_tmp = nullptr;
+  size_t pil_tmp_cap = 0;
   cudaStream_t copy_stream = nullptr;  // forward_host: x2 (only read by the last kernel) rides in beside the conv stack
   cudaEvent_t x2_ready = nullptr;
   bool wait_x2 = false;                // the next forward's last kernel waits for x2_ready
@@ -1694,6 +1699,87 @@ static int forward_impl(dcscn_handle* h, const float* x, const float* x2, float*
   return 0;
 }
 
+// ------------------------------------------------------------------------- Pillow bicubic on the device ----
+static double pil_bicubic_filter(double x) {   // Pillow Resample.c bicubic_filter, a = -0.5
+  const double a = -0.5;
+  if (x < 0.0) x = -x;
+  if (x < 1.0) return ((a + 2.0) * x - (a + 3.0)) * x * x + 1;
+  if (x < 2.0) return (((x - 5) * x + 8) * x - 4) * a;
+  return 0.0;
+}
+
+// Pillow's precompute_coeffs for one axis (helper/pil_resample.py is the Python statement of the same arithmetic).
+static int pil_axis(dcscn_handle* h, int in_size, int out_size, PilAxis* ax) {
+  for (const auto& t : h->pil_tables)
+    if (t.in == in_size && t.out == out_size) {
+      *ax = PilAxis{t.k, t.bounds, t.ksize};
+      return 0;
+    }
+  double scale = (double)in_size / (double)out_size, filterscale = scale;
+  if (filterscale < 1.0) filterscale = 1.0;
+  const double support = 2.0 * filterscale;
+  const int ksize = (int)std::ceil(support) * 2 + 1;
+  std::vector<double> kk((size_t)out_size * ksize, 0.0);
+  std::vector<int> bounds((size_t)out_size * 2, 0);
+  const double ss = 1.0 / filterscale;
+  for (int xx = 0; xx < out_size; ++xx) {
+    const double center = (xx + 0.5) * scale;
+    int xmin = (int)(center - support + 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = (int)(center + support + 0.5);
+    if (xmax > in_size) xmax = in_size;
+    xmax -= xmin;
+    double* k = kk.data() + (size_t)xx * ksize;
+    double ww = 0.0;
+    for (int x = 0; x < xmax; ++x) {
+      const double w = pil_bicubic_filter((x + xmin - center + 0.5) * ss);
+      k[x] = w;
+      ww += w;
+    }
+    for (int x = 0; x < xmax; ++x)
+      if (ww != 0.0) k[x] /= ww;
+    bounds[2 * xx] = xmin;
+    bounds[2 * xx + 1] = xmax;
+  }
+  dcscn_handle::PilTable t;
+  t.in = in_size; t.out = out_size; t.ksize = ksize;
+  CUDA_TRY(cudaMalloc((void**)&t.k, kk.size() * sizeof(double)));
+  CUDA_TRY(cudaMalloc((void**)&t.bounds, bounds.size() * sizeof(int)));
+  CUDA_TRY(cudaMemcpy(t.k, kk.data(), kk.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(t.bounds, bounds.data(), bounds.size() * sizeof(int), cudaMemcpyHostToDevice));
+  if (h->pil_tables.size() >= 64) {
+    cudaFree(h->pil_tables.front().k);
+    cudaFree(h->pil_tables.front().bounds);
+    h->pil_tables.erase(h->pil_tables.begin());
+  }
+  h->pil_tables.push_back(t);
+  *ax = PilAxis{t.k, t.bounds, t.ksize};
+  return 0;
+}
+
+// dst [n, OH, OW] = Pillow-bicubic resize of src [n, H, W] (both fp32 device tensors), horizontal pass first.
+static int pil_resize_impl(dcscn_handle* h, const float* src, float* dst, int n, int H, int W, int OH, int OW, cudaStream_t st) {
+  if (n <= 0 || H <= 0 || W <= 0 || OH <= 0 || OW <= 0) return fail("bicubic_resize: bad shape");
+  PilAxis ax, ay;
+  if (pil_axis(h, W, OW, &ax) || pil_axis(h, H, OH, &ay)) return 1;
+  const size_t need = (size_t)n * H * OW;
+  if (need > h->pil_tmp_cap) {
+    cudaFree(h->pil_tmp);
+    h->pil_tmp = nullptr;
+    h->pil_tmp_cap = 0;
+    CUDA_TRY(cudaMalloc((void**)&h->pil_tmp, need * sizeof(float)));
+    h->pil_tmp_cap = need;
+  }
+  const long long t1 = (long long)need, t2 = (long long)n * OH * OW;
+  pil_resample_h_kernel<<<(int)std::min<long long>((t1 + 255) / 256, (long long)h->sm_count * 16), 256, 0, st>>>(
+      src, h->pil_tmp, (long long)n * H, W, OW, ax);
+  pil_resample_v_kernel<<<(int)std::min<long long>((t2 + 255) / 256, (long long)h->sm_count * 16), 256, 0, st>>>(
+      h->pil_tmp, dst, n, H, OH, OW, ay);
+  CUDA_TRY(cudaGetLastError());
+  h->launches += 2;
+  return 0;
+}
+
 #include "train_engine.inc"
 
 // --------------------------------------------------------------------------------------- C ABI ----
@@ -1757,6 +1843,8 @@ int dcscn_destroy(dcscn_handle* h) {
   cudaFree(h->io_x);
   cudaFree(h->io_x2);
   cudaFree(h->io_y);
+  for (auto& pt : h->pil_tables) { cudaFree(pt.k); cudaFree(pt.bounds); }
+  cudaFree(h->pil_tmp);
   cudaFree(h->ps_lr); cudaFree(h->ps_bic); cudaFree(h->ps_true); cudaFree(h->ps_idx);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->x2_ready) cudaEventDestroy(h->x2_ready);
@@ -1806,8 +1894,15 @@ int dcscn_forward(dcscn_handle* h, const float* x_dev, const float* x2_dev, floa
   return forward_impl(h, x_dev, x2_dev, y_dev, n, height, width, (cudaStream_t)stream);
 }
 
+int dcscn_bicubic_resize(dcscn_handle* h, const float* src_dev, float* dst_dev, int n, int height, int width, int out_height,
+                         int out_width, void* stream) {
+  if (!h || !src_dev || !dst_dev) return fail("dcscn_bicubic_resize: null argument");
+  CUDA_TRY(cudaSetDevice(h->cfg.device_id));
+  return pil_resize_impl(h, src_dev, dst_dev, n, height, width, out_height, out_width, (cudaStream_t)stream);
+}
+
 int dcscn_forward_host(dcscn_handle* h, const float* x, const float* x2, float* y, int n, int height, int width) {
-  if (!h || !x || !x2 || !y) return fail("dcscn_forward_host: null argument");
+  if (!h || !x || !y) return fail("dcscn_forward_host: null argument");
   CUDA_TRY(cudaSetDevice(h->cfg.device_id));
   const size_t lr = (size_t)n * height * width;
   const size_t hr = lr * h->cfg.scale * h->cfg.scale;
@@ -1829,9 +1924,15 @@ int dcscn_forward_host(dcscn_handle* h, const float* x, const float* x2, float* 
   // x feeds the first kernel; x2 (4x / 9x / 16x the bytes) is only read by the very last one, so it is copied on a second
   // stream while the conv stack runs and the last kernel waits for it
   CUDA_TRY(cudaMemcpyAsync(h->io_x, x, lr * sizeof(float), cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(h->io_x2, x2, hr * sizeof(float), cudaMemcpyHostToDevice, h->copy_stream));
-  CUDA_TRY(cudaEventRecord(h->x2_ready, h->copy_stream));
-  h->wait_x2 = true;
+  if (x2) {
+    CUDA_TRY(cudaMemcpyAsync(h->io_x2, x2, hr * sizeof(float), cudaMemcpyHostToDevice, h->copy_stream));
+    CUDA_TRY(cudaEventRecord(h->x2_ready, h->copy_stream));
+    h->wait_x2 = true;
+  } else {
+    // x2 = Pillow-bicubic up-scale of x, formed in HBM (what util.resize_image_by_pil does on the host, bit for bit)
+    const int s = h->cfg.scale;
+    if (pil_resize_impl(h, h->io_x, h->io_x2, n, height, width, s * height, s * width, st)) return 1;
+  }
   const int rc = forward_impl(h, h->io_x, h->io_x2, h->io_y, n, height, width, st);
   h->wait_x2 = false;
   if (rc) {
@@ -1898,7 +1999,7 @@ int dcscn_forward_ensemble_partial(dcscn_handle* h, const float* x_dev, const fl
 }
 
 int dcscn_forward_ensemble_host(dcscn_handle* h, const float* x, const float* x2, double* y, int height, int width, int flips) {
-  if (!h || !x || !x2 || !y) return fail("dcscn_forward_ensemble_host: null argument");
+  if (!h || !x || !y) return fail("dcscn_forward_ensemble_host: null argument");
   CUDA_TRY(cudaSetDevice(h->cfg.device_id));
   const size_t lr = (size_t)height * width;
   const size_t hr = lr * h->cfg.scale * h->cfg.scale;
@@ -1914,7 +2015,11 @@ int dcscn_forward_ensemble_host(dcscn_handle* h, const float* x, const float* x2
   }
   cudaStream_t st = 0;
   CUDA_TRY(cudaMemcpyAsync(h->ensio_x, x, lr * sizeof(float), cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(h->ensio_x2, x2, hr * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (x2) {
+    CUDA_TRY(cudaMemcpyAsync(h->ensio_x2, x2, hr * sizeof(float), cudaMemcpyHostToDevice, st));
+  } else if (pil_resize_impl(h, h->ensio_x, h->ensio_x2, 1, height, width, h->cfg.scale * height, h->cfg.scale * width, st)) {
+    return 1;
+  }
   if (flips < 1 || flips > 8) return fail("forward_ensemble: flips must be 1..8 (got %d)", flips);
   if (ensemble_impl(h, h->ensio_x, h->ensio_x2, h->ensio_y, height, width, (1 << flips) - 1, (double)flips, st)) return 1;
   CUDA_TRY(cudaMemcpyAsync(y, h->ensio_y, hr * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -2133,6 +2238,8 @@ int dcscn_patch_store_set(dcscn_handle* h, const uint8_t* lr, const uint8_t* bic
   if (!h || !lr || !bicubic || !truth) return fail("dcscn_patch_store_set: null argument");
   if (count <= 0 || count > 0x7FFFFFFF || patch_height <= 0 || patch_width <= 0) return fail("dcscn_patch_store_set: bad size");
   CUDA_TRY(cudaSetDevice(h->cfg.device_id));
+  for (auto& pt : h->pil_tables) { cudaFree(pt.k); cudaFree(pt.bounds); }
+  cudaFree(h->pil_tmp);
   cudaFree(h->ps_lr); cudaFree(h->ps_bic); cudaFree(h->ps_true);
   h->ps_lr = h->ps_bic = h->ps_true = nullptr;
   h->ps_count = 0;

@@ -50,7 +50,7 @@ class DcscnConfig(ctypes.Structure):
 
 EXPORTED_SYMBOLS = [
     "dcscn_create", "dcscn_destroy", "dcscn_last_error", "dcscn_num_params", "dcscn_param_info",
-    "dcscn_set_param", "dcscn_get_param", "dcscn_forward", "dcscn_forward_host", "dcscn_forward_ensemble", "dcscn_forward_ensemble_host", "dcscn_forward_ensemble_partial", "dcscn_get_activation",
+    "dcscn_set_param", "dcscn_get_param", "dcscn_forward", "dcscn_forward_host", "dcscn_bicubic_resize", "dcscn_forward_ensemble", "dcscn_forward_ensemble_host", "dcscn_forward_ensemble_partial", "dcscn_get_activation",
     "dcscn_set_option", "dcscn_get_timings", "dcscn_launch_count", "dcscn_device_bytes",
     "dcscn_train_step", "dcscn_train_step_host", "dcscn_get_grad", "dcscn_get_adam_slot", "dcscn_set_adam_slot", "dcscn_get_adam_step",
     "dcscn_set_adam_step", "dcscn_last_grad_norm",
@@ -85,6 +85,7 @@ def load_library(path=None):
     lib.dcscn_get_param.argtypes = [vp, ctypes.c_char_p, fp, c64]
     lib.dcscn_forward.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp]
     lib.dcscn_forward_host.argtypes = [vp, vp, vp, vp, ci, ci, ci]
+    lib.dcscn_bicubic_resize.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, vp]
     lib.dcscn_forward_ensemble.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp]
     lib.dcscn_forward_ensemble_host.argtypes = [vp, vp, vp, vp, ci, ci, ci]
     lib.dcscn_forward_ensemble_partial.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp]
@@ -210,29 +211,48 @@ class Engine:
         return y
 
     def forward_host(self, x, x2, y=None):
-        """numpy (or pinned torch CPU) fp32 arrays in, numpy out; H2D + forward + D2H, synchronous."""
-        xa, x2a = _host_array(x), _host_array(x2)
+        """numpy (or pinned torch CPU) fp32 arrays in, numpy out; H2D + forward + D2H, synchronous.  With x2 = None the
+        bicubic up-scale of x (util.resize_image_by_pil, bit-exact) is formed on the device and only x is copied."""
+        xa = _host_array(x)
         n, h, w = xa.shape[0], xa.shape[1], xa.shape[2]
         s = self.config.scale
-        assert tuple(x2a.shape[:3]) == (n, s * h, s * w)
+        x2p = None
+        if x2 is not None:
+            x2a = _host_array(x2)
+            assert tuple(x2a.shape[:3]) == (n, s * h, s * w)
+            x2p = x2a.ctypes.data
         if y is None:
             y = np.empty((n, s * h, s * w, 1), dtype=np.float32)
         ya = _host_array(y)
-        self._check(self.lib.dcscn_forward_host(self.handle, xa.ctypes.data, x2a.ctypes.data, ya.ctypes.data, n, h, w))
+        self._check(self.lib.dcscn_forward_host(self.handle, xa.ctypes.data, x2p, ya.ctypes.data, n, h, w))
         return y
+
+    def bicubic_resize(self, src, out_height, out_width, out=None, stream=None):
+        """Pillow's bicubic `Image.resize` of float images on the device: src [n,h,w] fp32 CUDA tensor -> [n,oh,ow]."""
+        import torch
+        n, h, w = int(src.shape[0]), int(src.shape[1]), int(src.shape[2])
+        assert src.is_cuda and src.dtype == torch.float32 and src.is_contiguous()
+        if out is None:
+            out = torch.empty((n, int(out_height), int(out_width)), dtype=torch.float32, device=src.device)
+        st = stream if stream is not None else torch.cuda.current_stream(src.device).cuda_stream
+        self._check(self.lib.dcscn_bicubic_resize(self.handle, src.data_ptr(), out.data_ptr(), n, h, w, int(out_height),
+                                                  int(out_width), ctypes.c_void_p(st)))
+        return out
 
     def forward_ensemble_host(self, x, x2, flips):
         """Self-ensemble of one image on the device (DCSCN.py:547-586): x [h,w,(1)], x2 [s*h,s*w,(1)] float32 ->
         float64 [s*h, s*w, 1] mean of the inverse-transformed outputs of the first `flips` transforms."""
         xa = np.ascontiguousarray(x, dtype=np.float32)
-        x2a = np.ascontiguousarray(x2, dtype=np.float32)
         h, w = xa.shape[:2]
         s = int(self.config.scale)
-        if x2a.shape[:2] != (s * h, s * w):
-            raise ValueError("x2 must be [%d,%d], got %s" % (s * h, s * w, x2a.shape[:2]))
+        x2p = None                      # None: the device forms the bicubic up-scale of x itself (bit-exact Pillow)
+        if x2 is not None:
+            x2a = np.ascontiguousarray(x2, dtype=np.float32)
+            if x2a.shape[:2] != (s * h, s * w):
+                raise ValueError("x2 must be [%d,%d], got %s" % (s * h, s * w, x2a.shape[:2]))
+            x2p = x2a.ctypes.data
         y = np.empty((s * h, s * w, 1), dtype=np.float64)
-        self._check(self.lib.dcscn_forward_ensemble_host(self.handle, xa.ctypes.data, x2a.ctypes.data, y.ctypes.data, h, w,
-                                                         int(flips)))
+        self._check(self.lib.dcscn_forward_ensemble_host(self.handle, xa.ctypes.data, x2p, y.ctypes.data, h, w, int(flips)))
         return y
 
     def forward_ensemble(self, x, x2, flips, out=None, stream=None):

@@ -79,8 +79,15 @@ int dcscn_get_param(dcscn_handle* h, const char* name, float* host_data, int64_t
  */
 int dcscn_forward(dcscn_handle* h, const float* x_dev, const float* x2_dev, float* y_dev, int n, int height,
                   int width, void* stream);
-/* Same call with HOST buffers (pinned or pageable): H2D, forward, D2H, synchronises before returning. */
+/* Same call with HOST buffers (pinned or pageable): H2D, forward, D2H, synchronises before returning.  x2 may be NULL:
+ * the bicubic up-scale of x is then formed on the device, bit for bit what `util.resize_image_by_pil(x, scale)` returns
+ * (dcscn_bicubic_resize), and only x crosses PCIe (the default of `SuperResolution.do`, DCSCN.py:551-553). */
 int dcscn_forward_host(dcscn_handle* h, const float* x, const float* x2, float* y, int n, int height, int width);
+/* `util.resize_image_by_pil` (helper/utilty.py:211-239) for single-channel float images on the device: Pillow's bicubic
+ * `Image.resize` of mode 'F' images restated bit-exactly (two passes, double accumulation, float32 intermediate; up- or
+ * down-scaling).  src [n, height, width] -> dst [n, out_height, out_width], fp32 device tensors. */
+int dcscn_bicubic_resize(dcscn_handle* h, const float* src_dev, float* dst_dev, int n, int height, int width, int out_height,
+                         int out_width, void* stream);
 
 /* The self-ensemble of `SuperResolution.do` (DCSCN.py:547-586) for ONE image, entirely on the device: the first `flips`
  * (1..8) transforms of helper/utilty.py:595-617 are applied to x [height,width] and x2 [scale*height, scale*width],
@@ -89,6 +96,7 @@ int dcscn_forward_host(dcscn_handle* h, const float* x, const float* x2, float* 
 int dcscn_forward_ensemble(dcscn_handle* h, const float* x_dev, const float* x2_dev, double* y_dev, int height, int width,
                            int flips, void* stream);
 int dcscn_forward_ensemble_host(dcscn_handle* h, const float* x, const float* x2, double* y, int height, int width, int flips);
+/* (x2 may be NULL in dcscn_forward_ensemble_host as well: formed on the device from x.) */
 /* One rank's share of the same ensemble when the 8 transforms are spread over several GPUs: bit t of
  * `transform_mask` selects transform t; y receives the float64 SUM of the selected inverse-transformed outputs (no
  * division), ready for one ncclAllReduce(sum) over the ranks followed by the division by the ensemble size. */

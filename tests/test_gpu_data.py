@@ -78,3 +78,41 @@ def test_indexed_train_step_equals_the_host_buffer_step():
     assert out[0][0] == out[1][0]
     for n in out[0][1]:
         np.testing.assert_allclose(out[0][1][n], out[1][1][n], rtol=0, atol=2e-6)   # fp32 atomics reorder a few sums
+
+
+@pytest.mark.parametrize("shape,scale", [((3, 48, 48), 2), ((1, 37, 53), 2), ((2, 24, 31), 3), ((1, 20, 22), 4), ((1, 96, 64), 0.5),
+                                         ((2, 99, 63), 1 / 3)])
+def test_device_bicubic_is_pillow_bit_for_bit(shape, scale):
+    """`util.resize_image_by_pil` (PIL Image.resize BICUBIC on mode-F images, reference
+    helper/utilty.py:211-239) restated on the device - identical bits, up- and down-scaling."""
+    import torch
+    import dcscn_oracle as O
+    from helper import engine as E, utilty as util
+    eng = E.Engine(E.make_config(**KW))
+    rs = np.random.RandomState(5)
+    n, h, w = shape
+    a = (rs.rand(n, h, w) * 255).astype(np.float32)
+    oh, ow = int(h * scale), int(w * scale)
+    got = eng.bicubic_resize(torch.from_numpy(a).cuda(), oh, ow).cpu().numpy()
+    for i in range(n):
+        ref = util.resize_image_by_pil(a[i].reshape(h, w, 1).astype(np.float64), scale)[:, :, 0]
+        assert ref.shape == (oh, ow)
+        np.testing.assert_array_equal(got[i], ref)
+    eng.close()
+
+
+def test_forward_without_x2_equals_forward_with_pil_bicubic():
+    """`SuperResolution.do(image)` without a bicubic argument (sr.py's path, DCSCN.py:551-553): the engine forms x2 in HBM;
+    the result must equal the call that is handed Pillow's bicubic, bit for bit, for the plain forward and the ensemble."""
+    import dcscn_oracle as O
+    from helper import engine as E, utilty as util
+    eng = E.Engine(E.make_config(**KW))
+    eng.set_params(O.he_init_weights(O.OracleConfig(**KW), seed=6))
+    rs = np.random.RandomState(6)
+    lr = rs.rand(21, 30, 1) * 255
+    bic = util.resize_image_by_pil(lr, 2)
+    x = np.ascontiguousarray(lr, np.float32).reshape(1, 21, 30, 1)
+    x2 = np.ascontiguousarray(bic, np.float32).reshape(1, 42, 60, 1)
+    np.testing.assert_array_equal(eng.forward_host(x, None), eng.forward_host(x, x2))
+    np.testing.assert_array_equal(eng.forward_ensemble_host(lr, None, 8), eng.forward_ensemble_host(lr, bic, 8))
+    eng.close()

@@ -175,6 +175,22 @@ def test_adam_step_is_recovered_from_beta2_power():
     assert float(Reader(2000).v["beta1_power"]) == 0.0           # what the old beta1-only recovery saw
 
 
+def test_pil_bicubic_restatement_is_bit_exact():
+    """helper/pil_resample.py (the tables the device resampler uses) against Pillow itself, up- and down-scaling."""
+    from PIL import Image
+    from helper import pil_resample as R
+    rs = np.random.RandomState(0)
+    for (h, w, s) in [(48, 48, 2), (37, 53, 2), (24, 31, 3), (20, 20, 4), (96, 64, 0.5), (99, 63, 1 / 3), (64, 128, 0.25), (1, 7, 2)]:
+        a = rs.rand(h, w) * 255
+        nw, nh = int(w * s), int(h * s)
+        ref = np.asarray(Image.fromarray(a).resize([nw, nh], resample=Image.BICUBIC))
+        got = R.resize_float(a, nw, nh)
+        assert ref.dtype == np.float32 and np.array_equal(ref, got), (h, w, s)
+    # and through the helper the model uses
+    a = rs.rand(19, 23, 1) * 255
+    assert np.array_equal(util.resize_image_by_pil(a, 2)[:, :, 0], R.resize_float(a[:, :, 0], 46, 38))
+
+
 def test_package_does_not_import_oracle():
     """The product path must never route through the oracle."""
     for path in glob.glob(os.path.join(PKG, "**", "*.py"), recursive=True) + glob.glob(os.path.join(PKG, "csrc", "*")):

@@ -30,6 +30,9 @@ struct EpiSegment {
   __half* dst_hi;      // plane base, already offset to the slot's first channel
   __half* dst_lo;      // may be null in single-plane (fast) mode
   int pitch;           // channels per pixel of the destination buffer (elements)
+  __half* dst_zneg;    // training only (else null): fp16 plane, same indexing, of min(z, 0) - the pre-activation's negative
+                       // part.  PReLU's backward needs sign(z) and, for d alpha, z itself where z < 0; the post-activation
+                       // output cannot give either when the slope alpha is <= 0 (trained checkpoints have many such).
 };
 
 struct EpiParams {
@@ -79,7 +82,6 @@ struct ConvTCParams {
   int h2_nstages;
   int h2_nseg;           // fp32-promotion segments per item
   int h2_resident;       // all stages fit in shared memory: loaded once per CTA
-  float h2_trunc_beta;   // expected truncation loss per dominant UMMA, in ulps of the slot value (0 = no compensation)
   EpiParams epi;
 };
 

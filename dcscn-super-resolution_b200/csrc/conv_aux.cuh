@@ -126,10 +126,11 @@ __global__ void __launch_bounds__(256, 2) conv_first3x3_kernel(const ConvFirstPa
           acc[i] = fmaf(c2v[r], w[3 * r + 2][i], acc[i]);
         }
       }
-      uint32_t ph[4], pl[4];
+      uint32_t ph[4], pl[4], pz[4];
 #pragma unroll
       for (int i = 0; i < 8; i += 2) {
         float t0 = acc[i] + bias[i], t1 = acc[i + 1] + bias[i + 1];
+        pz[i >> 1] = pack_h2(__float2half_rn(fmaxf(fminf(t0, 0.f), -65504.f)), __float2half_rn(fmaxf(fminf(t1, 0.f), -65504.f)));
         t0 = t0 > 0.f ? t0 : alpha[i] * t0;
         t1 = t1 > 0.f ? t1 : alpha[i + 1] * t1;
         if (keep < 1.0f) {
@@ -147,6 +148,7 @@ __global__ void __launch_bounds__(256, 2) conv_first3x3_kernel(const ConvFirstPa
         const size_t off = (size_t)pix * seg.pitch + c0;
         *reinterpret_cast<uint4*>(seg.dst_hi + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
         if (seg.dst_lo != nullptr) *reinterpret_cast<uint4*>(seg.dst_lo + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+        if (seg.dst_zneg != nullptr) *reinterpret_cast<uint4*>(seg.dst_zneg + off) = make_uint4(pz[0], pz[1], pz[2], pz[3]);
       }
       if (++x == W) {                                // next image row (or next image): rebuild the window
         x = 0;

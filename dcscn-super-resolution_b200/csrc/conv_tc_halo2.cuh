@@ -36,6 +36,8 @@ constexpr int kH2TableOff = 1280;        // byte offset of the stage table insid
 //   bits 0-7 channel chunk | 8-11 taps in the stage | 12-15 first tap (dx * 3 + dy) | 16-19 16-channel slices per tap |
 //   bit 20 first stage of its chunk (wait for the A box) | bit 21 last stage of its chunk (release the A box) |
 //   bit 22 last stage of an fp32-promotion segment.
+// A second word per stage carries, 8 bits per tap, the tap's first row inside the halo box (dy * 10 + dx): the issuing
+// thread does no division.
 constexpr uint32_t kH2ChunkFirst = 1u << 20, kH2ChunkLast = 1u << 21, kH2SegEnd = 1u << 22;
 
 __host__ __device__ inline size_t tc_halo2_misc_bytes() { return 1024 + kH2BarBytes + kRdotSmemBytes; }
@@ -63,7 +65,6 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
   uint64_t* acc_empty = acc_full + kH2MaxAcc;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kH2MaxAcc);
   uint32_t* s_tab = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(a_full) + kH2TableOff);
-  float* s_comp = reinterpret_cast<float*>(s_tab + kH2MaxTable);   // per accumulation slot: truncation compensation factor
   float* s_rdot = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a_full) + kH2BarBytes);
 
   const int warp = threadIdx.x >> 5;
@@ -96,26 +97,16 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
   if (p.epi.mode == EPI_D2S_RDOT)
     for (int i = threadIdx.x; i < p.epi.rdot_taps * p.epi.d2s_cout; i += blockDim.x) s_rdot[i] = p.epi.rdot_w[i];
   const int nst = p.h2_nstages;
-  for (int i = threadIdx.x; i < nst; i += blockDim.x) s_tab[i] = p.h2_stages[i];
-  if (threadIdx.x == 0) {
-    // slot j holds the dominant UMMAs of segment j: each of them truncates the fp32 accumulator toward zero, losing half
-    // an ulp on average.  The promotion adds back  trunc_beta * (dominant UMMAs of the slot) * ulp(value)  (see below).
-    int j = 0, dom = 0;
-    for (int i = 0; i < nst; ++i) {
-      const uint32_t e = p.h2_stages[i];
-      dom += (int)((e >> 8) & 15u) * (int)((e >> 16) & 15u);
-      if (e & kH2SegEnd) {
-        s_comp[j++] = p.h2_trunc_beta * (float)dom * 1.1920929e-07f;     // * 2^-23: ulp of a value in [1, 2)
-        dom = 0;
-      }
-    }
-    s_comp[j] = 0.f;                                                      // corrections-only slot: tiny accumulator
-  }
+  for (int i = threadIdx.x; i < 2 * nst; i += blockDim.x) s_tab[i] = p.h2_stages[i];
   ptx::tc_fence_before();
   __syncthreads();
   ptx::cluster_sync();
   ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  // All 512 columns are allocated, so the allocation starts at lane 0, column 0.  Using the literal 0 keeps every TMEM
+  // address warp-uniform for the compiler (uniform registers feed UTCHMMA directly; a value loaded from shared memory costs a
+  // vector->uniform move in front of every UMMA of the single issuing thread).
+  if (*tmem_slot != 0u) __trap();
+  constexpr uint32_t tmem_base = 0u;
   const bool resident = p.h2_resident != 0;           // every weight stage of the layer stays in shared memory
 
   const ConvGeom& g = p.g;
@@ -129,7 +120,7 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
   const int nslots = nseg + (NPLANES == 2 ? 1 : 0);   // accumulation slots (= promotions) per tile
 
   if (warp < kEpiWarp0) {
-    ptx::setmaxnreg_dec<48>();   // 128 x 48 + 256 x 232 = 64 K registers exactly
+    ptx::setmaxnreg_dec<kRegsIssue>();   // 168 x 384 registers at launch = 128 x 40 + 256 x 232: a larger issue budget would leave setmaxnreg.inc waiting forever
     if (warp == 0) {
       // ============================== TMA producer: A boxes (both CTAs) ==============================
       if (lane == 0) {
@@ -182,59 +173,75 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
       const uint32_t sa_u32 = ptx::smem_u32(smem_a), sb_u32 = ptx::smem_u32(smem_b);
       int sa = 0, sb = 0;
       uint32_t spa = 0, spb = 0;
-      uint32_t slot = 0;                                  // running accumulation-slot counter; buffer = slot % 3
+      // Accumulation slots rotate over the nbuf TMEM buffers: bd = buffer of the current dominant slot, bc = the next one;
+      // bit b of `phm` = completed uses of buffer b mod 2 (mbarrier phase parity).  Plain increments and selects instead
+      // of slot % nbuf keep all of it in uniform registers.
+      uint32_t bd = 0, bc = 0, phm = 0;
       for (int item = cluster_id; item < num_items; item += num_clusters) {
-        ptx::mbar_wait(&acc_empty[slot % nbuf], ((slot / nbuf) & 1) ^ 1);   // takes the dominant products of segment 0
+        ptx::mbar_wait(&acc_empty[bd], ((phm >> bd) & 1u) ^ 1u);   // takes the dominant products of segment 0
         int s = 0;                                          // segment of the tile
         bool seg_open = true;
-        uint32_t sd = slot, sc = slot + 1, tmem_d = 0, tmem_c = 0, acc_c = 0, acc_d = 0;
+        uint32_t tmem_d = 0, tmem_c = 0, acc_d0 = 0;
+        bool fresh = true;                                  // the next UMMA slice opens the segment's accumulation slots
         for (int st = 0; st < nst; ++st) {
-          const uint32_t e = s_tab[st];
-          const int ntaps = (int)((e >> 8) & 15u), tap0 = (int)((e >> 12) & 15u), kt = (int)((e >> 16) & 15u);
+          const uint32_t e = s_tab[2 * st];
+          uint32_t rows = s_tab[2 * st + 1];                        // 8 bits per tap: first halo-box row of the tap
+          const int ntaps = (int)((e >> 8) & 15u), kt = (int)((e >> 16) & 15u);
           if (seg_open) {
-            sd = slot + (uint32_t)s;
-            sc = sd + 1;
-            if (NPLANES == 2) ptx::mbar_wait(&acc_empty[sc % nbuf], ((sc / nbuf) & 1) ^ 1);
-            tmem_d = tmem_base + (sd % nbuf) * (uint32_t)acc_stride;
-            tmem_c = tmem_base + (sc % nbuf) * (uint32_t)acc_stride;
-            acc_c = 0;                                              // corrections open their slot
-            acc_d = (NPLANES == 2 && s > 0) ? 1u : 0u;              // slot already holds the previous corrections
+            bc = (bd + 1u == nbuf) ? 0u : bd + 1u;
+            if (NPLANES == 2) ptx::mbar_wait(&acc_empty[bc], ((phm >> bc) & 1u) ^ 1u);
+            tmem_d = tmem_base + bd * (uint32_t)acc_stride;
+            tmem_c = tmem_base + bc * (uint32_t)acc_stride;
+            fresh = true;                                           // corrections open their slot with the first slice
+            acc_d0 = (NPLANES == 2 && s > 0) ? 1u : 0u;             // the dominant slot already holds the previous corrections
             seg_open = false;
           }
           if (e & kH2ChunkFirst) ptx::mbar_wait(&a_full[sa], spa);  // the chunk's halo box serves all its stages
           ptx::mbar_wait(&b_full[sb], spb);
           ptx::tc_fence_after();
-          const uint32_t a_base = sa_u32 + (uint32_t)sa * (uint32_t)A_SLOT;
+          // low descriptor word (start address >> 4 | LBO) of the A slot's hi plane; slots are 1024-byte aligned
+          const uint32_t a_desc0 = (((sa_u32 + (uint32_t)sa * (uint32_t)A_SLOT) & 0x3FFFFu) >> 4) | (1u << 16);
           const uint32_t b_addr = sb_u32 + (uint32_t)sb * (uint32_t)B_STAGE;
           const uint32_t lb_hi = desc_lo_t<KC>(b_addr), lb_lo = desc_lo_t<KC>(b_addr + BH_BYTES);
           if (ptx::elect_one()) {
-            uint32_t col = 0;                                       // 16-channel slice inside the stage's 128-byte rows
+            // Descriptors are advanced by plain adds on their low words (start address >> 4, 16-byte units): +2 per
+            // 16-channel slice.  The single issuing thread is the scarce resource here - every scalar instruction between
+            // two UMMAs is time the tensor pipe's queue is not being fed (thin layers: 16-32 cycles per UMMA).
+            constexpr uint32_t kDescHiA = (uint32_t)((kHalo1W * 128) >> 4) | (1u << 14) | (2u << 29);          // SBO 1280, SW128
+            constexpr uint32_t kDescHiB = (uint32_t)(TcSmem<KC>::kSbo >> 4) | (1u << 14) | ((uint32_t)TcSmem<KC>::kLayout << 29);
+            uint32_t bh = lb_hi, bl = lb_lo;                        // weight slices walk through the stage's 128-byte rows
 #pragma unroll 1
-            for (int j = 0; j < ntaps; ++j) {
-              const int tap = tap0 + j, dx = tap / 3, dy = tap - dx * 3;
-              const uint32_t a_addr = a_base + (uint32_t)(dy * kHalo1W + dx) * 128u;
+            for (int j = 0; j < ntaps; ++j, rows >>= 8) {
+              uint32_t ah = a_desc0 + (rows & 255u) * 8u;           // 128-byte rows = 8 descriptor units each
+              uint32_t al = ah + (uint32_t)(AH_BYTES >> 4);
 #pragma unroll 1
-              for (int ks = 0; ks < kt; ++ks, ++col) {
-                const uint32_t kadd = col * 2u;
-                const uint64_t da_hi = make_desc64_halo1(a_addr + ks * 32, 0);
-                if (NPLANES == 2) {
-                  ptx::mma_f16_ss_2sm(tmem_c, make_desc64_halo1(a_addr + AH_BYTES + ks * 32, 0), make_desc64_t<KC>(lb_hi + kadd), idesc, acc_c);
-                  ptx::mma_f16_ss_2sm(tmem_c, da_hi, make_desc64_t<KC>(lb_lo + kadd), idesc, 1);
-                  acc_c = 1;
+              for (int ks = 0; ks < kt; ++ks) {
+                const uint64_t da_hi = ((uint64_t)kDescHiA << 32) | ah, db_hi = ((uint64_t)kDescHiB << 32) | bh;
+                if (fresh) {                                        // first slice of a segment: the slots may be opened here
+                  if (NPLANES == 2) {
+                    ptx::mma_f16_ss_2sm(tmem_c, ((uint64_t)kDescHiA << 32) | al, db_hi, idesc, 0);
+                    ptx::mma_f16_ss_2sm_acc(tmem_c, da_hi, ((uint64_t)kDescHiB << 32) | bl, idesc);
+                  }
+                  ptx::mma_f16_ss_2sm(tmem_d, da_hi, db_hi, idesc, acc_d0);
+                  fresh = false;
+                } else {
+                  if (NPLANES == 2) {
+                    ptx::mma_f16_ss_2sm_acc(tmem_c, ((uint64_t)kDescHiA << 32) | al, db_hi, idesc);
+                    ptx::mma_f16_ss_2sm_acc(tmem_c, da_hi, ((uint64_t)kDescHiB << 32) | bl, idesc);
+                  }
+                  ptx::mma_f16_ss_2sm_acc(tmem_d, da_hi, db_hi, idesc);
                 }
-                ptx::mma_f16_ss_2sm(tmem_d, da_hi, make_desc64_t<KC>(lb_hi + kadd), idesc, acc_d);
-                acc_d = 1;
+                ah += 2; al += 2; bh += 2; bl += 2;
               }
             }
             if (!resident) ptx::mma_commit_2sm(&b_empty[sb], 3);
             if (e & kH2ChunkLast) ptx::mma_commit_2sm(&a_empty[sa], 3);
             if (e & kH2SegEnd) {
-              ptx::mma_commit_2sm(&acc_full[sd % nbuf], 3);
-              if (NPLANES == 2 && s == nseg - 1) ptx::mma_commit_2sm(&acc_full[sc % nbuf], 3);
+              ptx::mma_commit_2sm(&acc_full[bd], 3);
+              if (NPLANES == 2 && s == nseg - 1) ptx::mma_commit_2sm(&acc_full[bc], 3);
             }
           }
-          acc_c = 1;
-          acc_d = 1;
+          fresh = false;                                          // (set by the elected lane; every stage has >= 1 slice)
           __syncwarp();
           if (resident) {
             ++sb;                                             // stage st lives in ring slot st; phase 0 stays complete
@@ -246,10 +253,15 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
           if (e & kH2SegEnd) {
             ++s;
             seg_open = true;
+            phm ^= 1u << bd;                                        // this use of the dominant buffer is complete
+            bd = bc;
           }
         }
+        if (NPLANES == 2) {                                         // the corrections-only slot of the last segment
+          phm ^= 1u << bd;
+          bd = (bd + 1u == nbuf) ? 0u : bd + 1u;
+        }
         if (resident) sb = 0;
-        slot += (uint32_t)nslots;
       }
     }
   } else {
@@ -268,7 +280,7 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
     const int col_base = first_chunk * 16;
     const uint32_t lead_acc_empty0 = ptx::mapa_shared(ptx::smem_u32(&acc_empty[0]), 0);
     const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)col_base;
-    uint32_t slot = 0;
+    uint32_t eb = 0, ephm = 0;                           // buffer of the next slot to drain, per-buffer phase parity
     for (int item = cluster_id; item < num_items; item += num_clusters) {
       const int n_tile = item % p.n_tiles;
       const int tile = (item / p.n_tiles) * 2 + (int)rank;
@@ -285,14 +297,12 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
 #pragma unroll
         for (int i = 0; i < 16; ++i) sum[j][i] = 0.f;
       for (int s = 0; s < nslots; ++s) {
-        const uint32_t buf = slot % nbuf;
-        ptx::mbar_wait(&acc_full[buf], (slot / nbuf) & 1);
+        const uint32_t buf = eb;
+        ptx::mbar_wait(&acc_full[buf], (ephm >> buf) & 1u);
         ptx::tc_fence_after();
         const uint32_t taddr = taddr0 + buf * (uint32_t)acc_stride;
-        const float comp = s_comp[s];
         // fp32 round-to-nearest promotion of the slot: wide TMEM loads (64 / 32 columns per instruction); columns
         // past this thread's share may be read (they stay inside the 512 allocated columns) but are never stored.
-        // `h2_comp(v)` = v + sign(v) * 2^exponent(v) * comp: the expected truncation loss of the slot's UMMAs.
 #pragma unroll
         for (int j = 0; j < kMaxColChunks; j += 4) {
           if (j < my_chunks) {
@@ -300,21 +310,20 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
               float v[64];
               ptx::tmem_ld64(taddr + j * 16, v);
 #pragma unroll
-              for (int i = 0; i < 64; ++i)
-                sum[j + (i >> 4)][i & 15] += fmaf(__uint_as_float(__float_as_uint(v[i]) & 0xFF800000u), comp, v[i]);
+              for (int i = 0; i < 64; ++i) sum[j + (i >> 4)][i & 15] += v[i];
             } else {
               float v[32];
               ptx::tmem_ld32(taddr + j * 16, v);
 #pragma unroll
-              for (int i = 0; i < 32; ++i)
-                sum[j + (i >> 4)][i & 15] += fmaf(__uint_as_float(__float_as_uint(v[i]) & 0xFF800000u), comp, v[i]);
+              for (int i = 0; i < 32; ++i) sum[j + (i >> 4)][i & 15] += v[i];
             }
           }
         }
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive_cluster(lead_acc_empty0 + (uint32_t)(buf * sizeof(uint64_t)));
-        ++slot;
+        ephm ^= 1u << buf;
+        eb = (eb + 1u == nbuf) ? 0u : eb + 1u;
       }
       if (p.epi.mode == EPI_D2S_RDOT) {
         float v[9];

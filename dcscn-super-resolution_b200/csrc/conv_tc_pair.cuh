@@ -69,6 +69,17 @@ __device__ __forceinline__ void mma_f16_ss_2sm(uint32_t tmem_d, uint64_t desc_a,
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same with the accumulate input always enabled (no runtime predicate to materialise in front of the instruction).
+__device__ __forceinline__ void mma_f16_ss_2sm_acc(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.eq.u32 p, 1, 1;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc)
+      : "memory");
+}
 __device__ __forceinline__ void mma_commit_2sm(uint64_t* bar, uint16_t cta_mask) {
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(

@@ -238,7 +238,6 @@ struct dcscn_handle {
   int halo = 3;                      // 3x3 layers: halo-reuse CTA-pair kernel, 1 = three 18x8 boxes, 2 = one 18x10 box per chunk
                                      // (two-pass segments), 3 = the same box with streaming stages (conv_tc_halo2.cuh)
   int halo_base = 0;                 // single-box variant: set the descriptor base-offset field
-  float trunc_beta = 0.f;            // streaming kernel: truncation compensation per dominant UMMA, in ulps (option, x 1e-3)
   int wmap_wide = 0;                 // streaming kernel: fetch weight stages as rows of 1024 bytes instead of 128
   int timing = 0;
   int fuse_last = 1;                 // fold the per-pixel half of R-CNN1 into the last Up-PS epilogue
@@ -411,14 +410,20 @@ static int tile_cap(const dcscn_handle* h, int ksz);
 // dominant UMMAs (3 taps x 4 slices), like the (chunk, dx) units of the two-pass kernels.
 static void build_h2_stages(int cin_pad, int seg_units, std::vector<uint32_t>& tab, int* nseg) {
   tab.clear();
+  static const bool pack_tails = !(getenv("DCSCN_H2_PACK") && atoi(getenv("DCSCN_H2_PACK")) == 0);   // A/B switch (default on)
   const int chunks = (cin_pad + 63) / 64, target = 12 * std::max(1, seg_units);
   int dom = 0, segs = 0;
   for (int ch = 0; ch < chunks; ++ch) {
     const int kt = std::min(64, cin_pad - ch * 64) / 16;            // 16-channel slices per tap in this chunk (1..4)
-    const int per = kt >= 3 ? 1 : 4 / kt;                           // taps per stage
+    const int per = (kt >= 3 || !pack_tails) ? 1 : 4 / kt;          // taps per stage
     for (int t0 = 0; t0 < 9; t0 += per) {
       const int nt = std::min(per, 9 - t0);
       uint32_t e = (uint32_t)ch | ((uint32_t)nt << 8) | ((uint32_t)t0 << 12) | ((uint32_t)kt << 16);
+      uint32_t rows = 0;                                           // first halo-box row (dy * 10 + dx) of each tap, 8 bits each
+      for (int j = 0; j < nt; ++j) {
+        const int tap = t0 + j, dx = tap / 3, dy = tap % 3;
+        rows |= (uint32_t)(dy * kHalo1W + dx) << (8 * j);
+      }
       if (t0 == 0) e |= kH2ChunkFirst;
       if (t0 + nt >= 9) e |= kH2ChunkLast;
       dom += nt * kt;
@@ -429,6 +434,7 @@ static void build_h2_stages(int cin_pad, int seg_units, std::vector<uint32_t>& t
         ++segs;
       }
       tab.push_back(e);
+      tab.push_back(rows);
     }
   }
   *nseg = segs;
@@ -437,7 +443,7 @@ static void build_h2_stages(int cin_pad, int seg_units, std::vector<uint32_t>& t
 // Stage-ordered operand image of the streaming kernel: [n_tile][stage][rank][n_pad/2 rows x 64 halves]; the four
 // 16-channel slices of a row belong to (tap0 + q / kt, slice q % kt) of the stage's chunk.
 static void pair_image_h2(const TcLayer& t, std::vector<float>& img) {
-  const int n_total = t.n_tiles * t.n_pad, nst = (int)t.h2_stages.size();
+  const int n_total = t.n_tiles * t.n_pad, nst = (int)t.h2_stages.size() / 2;
   std::vector<float> wq((size_t)9 * t.cin_pad * n_total, 0.f);     // dense, channel-position-indexed  Wq[tap][q][n]
   for (int tp = 0; tp < 9; ++tp)
     for (int ci = 0; ci < t.cin; ++ci) {
@@ -450,7 +456,7 @@ static void pair_image_h2(const TcLayer& t, std::vector<float>& img) {
   img.assign((size_t)t.n_tiles * nst * 2 * half_elems, 0.f);
   for (int nt = 0; nt < t.n_tiles; ++nt)
     for (int st = 0; st < nst; ++st) {
-      const uint32_t e = t.h2_stages[st];
+      const uint32_t e = t.h2_stages[2 * st];
       const int ch = (int)(e & 255u), ntaps = (int)((e >> 8) & 15u), tap0 = (int)((e >> 12) & 15u), kt = (int)((e >> 16) & 15u);
       for (int rk = 0; rk < 2; ++rk) {
         float* base = img.data() + (((size_t)nt * nst + st) * 2 + rk) * half_elems;
@@ -564,7 +570,7 @@ static int pack_tc_layer(dcscn_handle* h, TcLayer& t) {
       if (hit && (hit == ov || hit[-1] == ',')) seg = std::max(1, atoi(hit + key.size()));
     }
     build_h2_stages(t.cin_pad, seg, t.h2_stages, &t.h2_nseg);
-    if ((int)t.h2_stages.size() > kH2MaxTable) return fail("layer %s: %zu weight stages exceed the kernel's table", t.name.c_str(), t.h2_stages.size());
+    if ((int)t.h2_stages.size() / 2 > kH2MaxTable) return fail("layer %s: %zu weight stages exceed the kernel's table", t.name.c_str(), t.h2_stages.size());
     if (upload(&t.d_h2_stages, t.h2_stages, h)) return 1;
   }
   if (need_pair) {
@@ -1067,11 +1073,12 @@ static int add_tc_launch(dcscn_handle* h, Plan* pl, const TcLayer& t, const __ha
   if (pair3x3 && !t.h2_stages.empty()) {
     const size_t a_slot = tc_halo1_a_slot_bytes(planes(h)), b_stage = tc_halo_b_stage_bytes(planes(h), t.n_pad);
     const long long total = 227 * 1024 - (long long)tc_halo2_misc_bytes();
-    const int nst = (int)t.h2_stages.size();
+    const int nst = (int)t.h2_stages.size() / 2;
     int na = 2;
     long long nb = (total - na * (long long)a_slot) / (long long)b_stage;
     bool resident = false;
-    if (t.n_tiles == 1 && nst <= kH2MaxStages && (long long)nst * (long long)b_stage + 2 * (long long)a_slot <= total) {
+    static const bool allow_resident = !(getenv("DCSCN_H2_RESIDENT") && atoi(getenv("DCSCN_H2_RESIDENT")) == 0);   // A/B switch
+    if (allow_resident && t.n_tiles == 1 && nst <= kH2MaxStages && (long long)nst * (long long)b_stage + 2 * (long long)a_slot <= total) {
       // thin layers: the whole weight image of this CTA half stays in shared memory, every other byte goes to A boxes
       resident = true;
       nb = nst;
@@ -1091,7 +1098,6 @@ static int add_tc_launch(dcscn_handle* h, Plan* pl, const TcLayer& t, const __ha
       L.p.h2_nstages = nst;
       L.p.h2_nseg = t.h2_nseg;
       L.p.h2_resident = resident ? 1 : 0;
-      L.p.h2_trunc_beta = h->trunc_beta;
       if (!L.halo1) {   // the A maps of the single-box variants are shared
         if (encode_map(h, &L.t1_hi, src_hi, t.cin_pad, src_pitch, n, H, W, kHaloTH + 2, kHalo1W, 64)) return 1;
         if (planes(h) == 2) {
@@ -2118,10 +2124,6 @@ int dcscn_set_option(dcscn_handle* h, const char* key, int64_t value) {
       h->plans.clear();
       h->last_plan = nullptr;
     }
-  } else if (k == "trunc_beta_milli") {
-    h->trunc_beta = (float)value * 1e-3f;
-    h->plans.clear();
-    h->last_plan = nullptr;
   } else if (k == "ds_impl") {
     if (value != 0 && value != 1) return fail("ds_impl must be 0 (tile kernels) or 1 (first-generation kernels)");
     h->ds_impl = (int)value;

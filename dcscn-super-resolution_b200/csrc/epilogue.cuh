@@ -55,8 +55,10 @@ __device__ __forceinline__ void store_planes16(__half* dst_hi, __half* dst_lo, s
 __device__ __forceinline__ void epilogue_store16(const EpiParams& e, const ConvGeom& g, int n_total, int img, int y,
                                                  int x, int cg, const float (&acc)[16]) {
   float v[16];
+  uint32_t zn[8];      // fp16 pairs of min(z, 0), only formed when a training segment asks for them
   const float4* b4 = reinterpret_cast<const float4*>(e.bias + cg);
   const float4* a4 = reinterpret_cast<const float4*>(e.alpha + cg);
+  const bool want_zneg = e.mode == EPI_PLANES && (e.seg[0].dst_zneg != nullptr || (e.num_seg > 1 && e.seg[1].dst_zneg != nullptr));
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     float4 b = __ldg(b4 + q);
@@ -69,6 +71,10 @@ __device__ __forceinline__ void epilogue_store16(const EpiParams& e, const ConvG
     v[4 * q + 1] = t1 > 0.f ? t1 : a.y * t1;
     v[4 * q + 2] = t2 > 0.f ? t2 : a.z * t2;
     v[4 * q + 3] = t3 > 0.f ? t3 : a.w * t3;
+    if (want_zneg) {
+      zn[2 * q] = pack_h2(__float2half_rn(fmaxf(fminf(t0, 0.f), -65504.f)), __float2half_rn(fmaxf(fminf(t1, 0.f), -65504.f)));
+      zn[2 * q + 1] = pack_h2(__float2half_rn(fmaxf(fminf(t2, 0.f), -65504.f)), __float2half_rn(fmaxf(fminf(t3, 0.f), -65504.f)));
+    }
   }
   if (e.keep_prob < 1.0f) {
     const float inv_keep = 1.0f / e.keep_prob;
@@ -84,6 +90,11 @@ __device__ __forceinline__ void epilogue_store16(const EpiParams& e, const ConvG
       if (s < e.num_seg && cg >= e.seg[s].col_begin && cg < e.seg[s].col_end) {
         size_t off = ((size_t)((size_t)img * g.H + y) * g.W + x) * e.seg[s].pitch + (cg - e.seg[s].col_begin);
         store_planes16(e.seg[s].dst_hi, e.seg[s].dst_lo, off, v);
+        if (e.seg[s].dst_zneg != nullptr) {
+          uint4* qz = reinterpret_cast<uint4*>(e.seg[s].dst_zneg + off);
+          qz[0] = make_uint4(zn[0], zn[1], zn[2], zn[3]);
+          qz[1] = make_uint4(zn[4], zn[5], zn[6], zn[7]);
+        }
       }
     }
     return;

@@ -364,7 +364,7 @@ struct ActGradParams {
   int col0;              // first column of this tensor inside that GEMM (A1+B1 fusion)
   const __half *g1_hi, *g1_lo; int g1_pitch;   // gradient source 1 (already offset to channel 0 of this tensor)
   const __half *g2_hi, *g2_lo; int g2_pitch;   // optional source 2 (nullptr: none)
-  const __half *out_hi, *out_lo; int out_pitch;  // forward output (post activation / dropout)
+  const __half* zneg; int zneg_pitch;          // min(z, 0) of the forward pre-activation (EpiSegment::dst_zneg), fp16
   const float* alpha;    // [C] or nullptr
   float keep;
   uint32_t seed, layer;
@@ -417,14 +417,17 @@ __global__ void __launch_bounds__(256) act_grad_kernel(const ActGradParams p) {
           g.x = dropout_keep(p.seed, p.layer, e, p.keep) ? g.x * inv_keep : 0.f;
           g.y = dropout_keep(p.seed, p.layer, e + 1, p.keep) ? g.y * inv_keep : 0.f;
         }
-        const float2 out = load_planes2(p.out_hi, p.out_lo, q * p.out_pitch + c);
+        // PReLU backward from the pre-activation itself: z < 0 -> dz = g * alpha and d alpha += g * z.  (Deciding by the
+        // sign of the OUTPUT is wrong for alpha <= 0 - alpha * z is then >= 0 - and shipped checkpoints have many
+        // negative slopes; recovering z as output / alpha also breaks down as alpha -> 0.)
+        const float2 zn = __half22float2(*reinterpret_cast<const __half2*>(p.zneg + q * p.zneg_pitch + c));
         dz = g;
-        if (out.x < 0.f) {
-          sa0 = fmaf(g.x, out.x * p.keep / a0, sa0);
+        if (zn.x < 0.f) {
+          sa0 = fmaf(g.x, zn.x, sa0);
           dz.x = g.x * a0;
         }
-        if (out.y < 0.f) {
-          sa1 = fmaf(g.y, out.y * p.keep / a1, sa1);
+        if (zn.y < 0.f) {
+          sa1 = fmaf(g.y, zn.y, sa1);
           dz.y = g.y * a1;
         }
       }

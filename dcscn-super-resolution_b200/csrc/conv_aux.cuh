@@ -76,6 +76,8 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const ConvFirstParams p
 // 3x3 fast path: lane = 8 consecutive output channels (weights, bias, alpha live in registers for the whole kernel),
 // warp = one pixel at a time, so each pixel's 2 x n_pad fp16 values leave the SM as two contiguous, fully coalesced
 // rows.  HBM-write-bound by construction (CNN1 writes 2 x 208 fp16 per LR pixel and reads 4 bytes).
+// ZNEG: the training forward also stores min(z, 0) (fp16) for the PReLU backward.
+template <bool ZNEG>
 __global__ void __launch_bounds__(256, 2) conv_first3x3_kernel(const ConvFirstParams p) {
   const int lane = threadIdx.x & 31;
   const int lanes_used = p.n_pad >> 3;
@@ -130,7 +132,7 @@ __global__ void __launch_bounds__(256, 2) conv_first3x3_kernel(const ConvFirstPa
 #pragma unroll
       for (int i = 0; i < 8; i += 2) {
         float t0 = acc[i] + bias[i], t1 = acc[i + 1] + bias[i + 1];
-        pz[i >> 1] = pack_h2(__float2half_rn(fmaxf(fminf(t0, 0.f), -65504.f)), __float2half_rn(fmaxf(fminf(t1, 0.f), -65504.f)));
+        if (ZNEG) pz[i >> 1] = pack_h2(__float2half_rn(fmaxf(fminf(t0, 0.f), -65504.f)), __float2half_rn(fmaxf(fminf(t1, 0.f), -65504.f)));
         t0 = t0 > 0.f ? t0 : alpha[i] * t0;
         t1 = t1 > 0.f ? t1 : alpha[i + 1] * t1;
         if (keep < 1.0f) {
@@ -148,7 +150,7 @@ __global__ void __launch_bounds__(256, 2) conv_first3x3_kernel(const ConvFirstPa
         const size_t off = (size_t)pix * seg.pitch + c0;
         *reinterpret_cast<uint4*>(seg.dst_hi + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
         if (seg.dst_lo != nullptr) *reinterpret_cast<uint4*>(seg.dst_lo + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
-        if (seg.dst_zneg != nullptr) *reinterpret_cast<uint4*>(seg.dst_zneg + off) = make_uint4(pz[0], pz[1], pz[2], pz[3]);
+        if (ZNEG) *reinterpret_cast<uint4*>(seg.dst_zneg + off) = make_uint4(pz[0], pz[1], pz[2], pz[3]);
       }
       if (++x == W) {                                // next image row (or next image): rebuild the window
         x = 0;

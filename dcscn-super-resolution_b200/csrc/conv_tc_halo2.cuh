@@ -177,13 +177,95 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
       // bit b of `phm` = completed uses of buffer b mod 2 (mbarrier phase parity).  Plain increments and selects instead
       // of slot % nbuf keep all of it in uniform registers.
       uint32_t bd = 0, bc = 0, phm = 0;
+      // chunks with the regular one-tap-per-stage layout (all of them unless the packing experiment is on)
+      const int n_reg = p.h2_nreg;
+      const int seg_target = 12 * p.seg_chunks;             // promotion period in 16-channel slices (12 = one full (chunk, dx) unit)
       for (int item = cluster_id; item < num_items; item += num_clusters) {
         ptx::mbar_wait(&acc_empty[bd], ((phm >> bd) & 1u) ^ 1u);   // takes the dominant products of segment 0
         int s = 0;                                          // segment of the tile
+        int dom = 0;                                        // stage weight issued into the open segment (12 per unit)
         bool seg_open = true;
         uint32_t tmem_d = 0, tmem_c = 0, acc_d0 = 0;
         bool fresh = true;                                  // the next UMMA slice opens the segment's accumulation slots
-        for (int st = 0; st < nst; ++st) {
+        int st = 0;                                         // stage counter (= index into the table)
+
+        // ---- regular part: full 64-channel chunks, one stage per tap, taps in (dx, dy) order, structure known at
+        // compile time (no table reads, dy unrolled): the path almost every UMMA of a layer takes
+        for (int ch = 0; ch < n_reg; ++ch) {
+          const int kt = min(4, (p.cin_pad - (ch << 6)) >> 4);      // 16-channel slices per tap (3 in a 48-channel tail)
+          ptx::mbar_wait(&a_full[sa], spa);                         // the chunk's halo box serves all nine taps
+          const uint32_t a_desc0 = (((sa_u32 + (uint32_t)sa * (uint32_t)A_SLOT) & 0x3FFFFu) >> 4) | (1u << 16);
+          for (int dx = 0; dx < 3; ++dx) {
+            if (seg_open) {
+              bc = (bd + 1u == nbuf) ? 0u : bd + 1u;
+              if (NPLANES == 2) ptx::mbar_wait(&acc_empty[bc], ((phm >> bc) & 1u) ^ 1u);
+              tmem_d = tmem_base + bd * (uint32_t)acc_stride;
+              tmem_c = tmem_base + bc * (uint32_t)acc_stride;
+              fresh = true;
+              acc_d0 = (NPLANES == 2 && s > 0) ? 1u : 0u;
+              seg_open = false;
+            }
+            dom += 12;
+            const bool seg_end = (dom >= seg_target) || (st + 3 == nst);   // same rule as build_h2_stages
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy, ++st) {
+              ptx::mbar_wait(&b_full[sb], spb);
+              ptx::tc_fence_after();
+              const uint32_t b_addr = sb_u32 + (uint32_t)sb * (uint32_t)B_STAGE;
+              uint32_t bh = desc_lo_t<KC>(b_addr), bl = desc_lo_t<KC>(b_addr + BH_BYTES);
+              uint32_t ah = a_desc0 + (uint32_t)(dy * kHalo1W + dx) * 8u;
+              uint32_t al = ah + (uint32_t)(AH_BYTES >> 4);
+              if (ptx::elect_one()) {
+                constexpr uint32_t kDescHiA = (uint32_t)((kHalo1W * 128) >> 4) | (1u << 14) | (2u << 29);
+                constexpr uint32_t kDescHiB = (uint32_t)(TcSmem<KC>::kSbo >> 4) | (1u << 14) | ((uint32_t)TcSmem<KC>::kLayout << 29);
+#pragma unroll 1
+                for (int ks = 0; ks < kt; ++ks) {
+                  const uint64_t da_hi = ((uint64_t)kDescHiA << 32) | ah, db_hi = ((uint64_t)kDescHiB << 32) | bh;
+                  if (fresh) {
+                    if (NPLANES == 2) {
+                      ptx::mma_f16_ss_2sm(tmem_c, ((uint64_t)kDescHiA << 32) | al, db_hi, idesc, 0);
+                      ptx::mma_f16_ss_2sm_acc(tmem_c, da_hi, ((uint64_t)kDescHiB << 32) | bl, idesc);
+                    }
+                    ptx::mma_f16_ss_2sm(tmem_d, da_hi, db_hi, idesc, acc_d0);
+                    fresh = false;
+                  } else {
+                    if (NPLANES == 2) {
+                      ptx::mma_f16_ss_2sm_acc(tmem_c, ((uint64_t)kDescHiA << 32) | al, db_hi, idesc);
+                      ptx::mma_f16_ss_2sm_acc(tmem_c, da_hi, ((uint64_t)kDescHiB << 32) | bl, idesc);
+                    }
+                    ptx::mma_f16_ss_2sm_acc(tmem_d, da_hi, db_hi, idesc);
+                  }
+                  ah += 2; al += 2; bh += 2; bl += 2;
+                }
+                if (!resident) ptx::mma_commit_2sm(&b_empty[sb], 3);
+                if (dy == 2 && dx == 2) ptx::mma_commit_2sm(&a_empty[sa], 3);
+                if (dy == 2 && seg_end) {
+                  ptx::mma_commit_2sm(&acc_full[bd], 3);
+                  if (NPLANES == 2 && s == nseg - 1) ptx::mma_commit_2sm(&acc_full[bc], 3);
+                }
+              }
+              fresh = false;
+              __syncwarp();
+              if (resident) {
+                ++sb;
+              } else if (++sb == num_b) {
+                sb = 0;
+                spb ^= 1;
+              }
+            }
+            if (seg_end) {
+              ++s;
+              dom = 0;
+              seg_open = true;
+              phm ^= 1u << bd;
+              bd = bc;
+            }
+          }
+          if (++sa == num_a) { sa = 0; spa ^= 1; }
+        }
+
+        // ---- tail chunk (cin_pad % 64 channels): table-driven, several taps may share one packed stage
+        for (; st < nst; ++st) {
           const uint32_t e = s_tab[2 * st];
           uint32_t rows = s_tab[2 * st + 1];                        // 8 bits per tap: first halo-box row of the tap
           const int ntaps = (int)((e >> 8) & 15u), kt = (int)((e >> 16) & 15u);

@@ -99,6 +99,8 @@ struct TcLayer {
   // streaming 3x3 kernel: weight-stage table of one item (conv_tc_halo2.cuh); non-empty = d_wpair is in stage order
   std::vector<uint32_t> h2_stages;
   int h2_nseg = 0;
+  int h2_nreg = 0;                  // leading chunks with one tap per stage
+  int h2_seg_units = 1;             // promotion period of the regular (full-chunk) part, in (chunk, dx) units
   uint32_t* d_h2_stages = nullptr;
   int* d_pair_src = nullptr;    // training: flat parameter index behind every hi-plane element of d_wpair (-1 = zero)
   size_t pair_src_n = 0;
@@ -408,14 +410,19 @@ static int tile_cap(const dcscn_handle* h, int ksz);
 // Weight-stage table of the streaming 3x3 kernel (see conv_tc_halo2.cuh): full 64-channel chunks take one stage per tap,
 // a last chunk with 16 / 32 valid channels packs 4 / 2 taps per stage.  `seg_units` = promotion period in units of 12
 // dominant UMMAs (3 taps x 4 slices), like the (chunk, dx) units of the two-pass kernels.
-static void build_h2_stages(int cin_pad, int seg_units, std::vector<uint32_t>& tab, int* nseg) {
+static void build_h2_stages(int cin_pad, int seg_units, std::vector<uint32_t>& tab, int* nseg, int* nreg) {
   tab.clear();
-  static const bool pack_tails = !(getenv("DCSCN_H2_PACK") && atoi(getenv("DCSCN_H2_PACK")) == 0);   // A/B switch (default on)
+  // Packing several taps of a 16/32-channel tail chunk into one 64-half stage saves weight stages but sends those stages
+  // through the table-driven issue loop; measured on B200 it loses (B2 0.122 -> 0.151 ms, CNN9 0.248 -> 0.306 ms), so it
+  // is an experiment switch only.
+  static const bool pack_tails = getenv("DCSCN_H2_PACK") && atoi(getenv("DCSCN_H2_PACK")) == 1;
+  *nreg = 0;
   const int chunks = (cin_pad + 63) / 64, target = 12 * std::max(1, seg_units);
   int dom = 0, segs = 0;
   for (int ch = 0; ch < chunks; ++ch) {
     const int kt = std::min(64, cin_pad - ch * 64) / 16;            // 16-channel slices per tap in this chunk (1..4)
     const int per = (kt >= 3 || !pack_tails) ? 1 : 4 / kt;          // taps per stage
+    if (per == 1 && *nreg == ch) *nreg = ch + 1;
     for (int t0 = 0; t0 < 9; t0 += per) {
       const int nt = std::min(per, 9 - t0);
       uint32_t e = (uint32_t)ch | ((uint32_t)nt << 8) | ((uint32_t)t0 << 12) | ((uint32_t)kt << 16);
@@ -426,9 +433,12 @@ static void build_h2_stages(int cin_pad, int seg_units, std::vector<uint32_t>& t
       }
       if (t0 == 0) e |= kH2ChunkFirst;
       if (t0 + nt >= 9) e |= kH2ChunkLast;
-      dom += nt * kt;
+      dom += (per == 1) ? 4 : nt * kt;                            // a one-tap stage counts as a full one whatever its kt
       const bool last = (ch == chunks - 1) && (t0 + nt >= 9);
-      if (dom >= target || last) {
+      // one-tap stages end a segment only after a whole (chunk, dx) unit: the kernel's regular path issues those three
+      // stages as one block
+      const bool boundary = (per > 1) || (t0 % 3 == 2);
+      if ((dom >= target && boundary) || last) {
         e |= kH2SegEnd;
         dom = 0;
         ++segs;
@@ -569,7 +579,8 @@ static int pack_tc_layer(dcscn_handle* h, TcLayer& t) {
       const char* hit = strstr(ov, key.c_str());
       if (hit && (hit == ov || hit[-1] == ',')) seg = std::max(1, atoi(hit + key.size()));
     }
-    build_h2_stages(t.cin_pad, seg, t.h2_stages, &t.h2_nseg);
+    t.h2_seg_units = std::max(1, seg);
+    build_h2_stages(t.cin_pad, seg, t.h2_stages, &t.h2_nseg, &t.h2_nreg);
     if ((int)t.h2_stages.size() / 2 > kH2MaxTable) return fail("layer %s: %zu weight stages exceed the kernel's table", t.name.c_str(), t.h2_stages.size());
     if (upload(&t.d_h2_stages, t.h2_stages, h)) return 1;
   }
@@ -1090,7 +1101,7 @@ static int add_tc_launch(dcscn_handle* h, Plan* pl, const TcLayer& t, const __ha
     nb = std::min<long long>(nb, kH2MaxStages);
     if (nb >= 3 || resident) {
       L.halo2 = true;
-      L.halo2_seg = 0;
+      L.halo2_seg = t.h2_seg_units;
       L.halo2_na = na;
       L.halo2_nb = (int)nb;
       L.halo2_smem = na * a_slot + (size_t)nb * b_stage + tc_halo2_misc_bytes();
@@ -1098,6 +1109,7 @@ static int add_tc_launch(dcscn_handle* h, Plan* pl, const TcLayer& t, const __ha
       L.p.h2_nstages = nst;
       L.p.h2_nseg = t.h2_nseg;
       L.p.h2_resident = resident ? 1 : 0;
+      L.p.h2_nreg = t.h2_nreg;
       if (!L.halo1) {   // the A maps of the single-box variants are shared
         if (encode_map(h, &L.t1_hi, src_hi, t.cin_pad, src_pitch, n, H, W, kHaloTH + 2, kHalo1W, 64)) return 1;
         if (planes(h) == 2) {
@@ -1388,6 +1400,7 @@ static int launch_tc_halo2(dcscn_handle* h, const TcLaunch& L, cudaStream_t st) 
   ConvTCParams p = L.p;
   p.g = L.hg;
   p.cluster_size = 2;
+  p.seg_chunks = L.halo2_seg;
   const bool wide = h->wmap_wide && L.has_wide;
   CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc_halo2_kernel<NPL>, L.t1_hi, L.t1_lo, wide ? L.tm_w_wide : L.tm_w, p, L.halo2_na,
                               L.halo2_nb, wide ? 1 : 0));
@@ -1659,10 +1672,13 @@ static int forward_impl(dcscn_handle* h, const float* x, const float* x2, float*
     const long long total = (long long)n * H * W;
     const int grid = (int)std::min<long long>((total + 255) / 256, (long long)h->sm_count * 8);
     const size_t smem = (size_t)p.ksz * p.ksz * p.n_pad * sizeof(float);
-    if (p.ksz == 3 && p.n_pad <= 256)
-      conv_first3x3_kernel<<<(int)std::min<long long>((total + 7) / 8, (long long)h->sm_count * 8), 256, 0, st>>>(p);
-    else
+    if (p.ksz == 3 && p.n_pad <= 256) {
+      const int first_grid = (int)std::min<long long>((total + 7) / 8, (long long)h->sm_count * 8);
+      if (p.epi.seg[0].dst_zneg != nullptr) conv_first3x3_kernel<true><<<first_grid, 256, 0, st>>>(p);
+      else conv_first3x3_kernel<false><<<first_grid, 256, 0, st>>>(p);
+    } else {
       conv_first_kernel<<<grid, 256, smem, st>>>(p);
+    }
     CUDA_TRY(cudaGetLastError());
     h->launches++;
     if (mark(h, st)) return 1;

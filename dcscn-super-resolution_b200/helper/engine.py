@@ -13,7 +13,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "csrc", "libdcscn_b200.so")
+# DCSCN_B200_LIB points the binding at another build of the same C-ABI (kernel A/B runs); default: the in-tree library
+LIB_PATH = os.environ.get("DCSCN_B200_LIB") or os.path.join(os.path.dirname(_HERE), "csrc", "libdcscn_b200.so")
 
 PRECISION_F16X3 = 0
 PRECISION_F16X1 = 1

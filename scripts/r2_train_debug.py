@@ -41,6 +41,27 @@ if "A" in which:
                 print("     %-34s max|ref| %.3e  max|got| %.3e  rel err %.2e %s" % (name, np.abs(gr).max(), np.abs(got).max(), rel, "BAD" if rel > 2e-3 else ""), flush=True)
             eng.close()
 
+if "C" in which:
+    model = "dcscn_L12_F196to48_NIN_A64_PS_R1F32"
+    cfg = O.OracleConfig(scale=2)
+    wts = {k: v.astype(np.float64) for k, v in load_golden_weights(model).items()}
+    n, h, w = 2, 12, 10
+    g = np.random.RandomState(21)
+    x = (g.rand(n, h, w, 1) * 255).astype(np.float32)
+    x2 = (g.rand(n, 2 * h, 2 * w, 1) * 255).astype(np.float32)
+    y = np.clip(x2 + g.randn(n, 2 * h, 2 * w, 1) * 10, 0, 255).astype(np.float32)
+    _, _, gref = O.Oracle(cfg, wts, torch.float64).loss_and_grads(x.astype(np.float64), x2.astype(np.float64), y.astype(np.float64), keep_prob=1.0)
+    eng = E.Engine(E.make_config(scale=2, dropout_keep=1.0))
+    eng.set_params({k: v.astype(np.float32) for k, v in wts.items()})
+    eng.train_step_host(x, x2, y, lr=0.002, seed=1, apply_update=False)
+    for name in ("CNN7/conv_B", "CNN7/prelu/CNN7_prelu", "CNN8/conv_B", "CNN6/conv_B"):
+        got, ref = eng.get_grad(name), gref[name]
+        d = np.abs(got - ref) / (np.abs(ref).max() + 1e-30)
+        idx = np.argsort(-d)[:8]
+        al = wts[name.split("/")[0] + "/prelu/" + name.split("/")[0] + "_prelu"]
+        print("C", name, "worst channels:", [(int(i), "%.1e" % d[i], "ref %.3e got %.3e alpha %.3e" % (ref[i], got[i], al[i])) for i in idx], flush=True)
+    eng.close()
+
 if "B" in which:
     KW = dict(scale=2, layers=7, filters=32, min_filters=8, filters_decay_gamma=1.2, nin_filters=24, nin_filters2=8,
               reconstruct_layers=0, pixel_shuffler_filters=1)

@@ -94,6 +94,15 @@ __host__ __device__ inline size_t tc_pair_stage_bytes(int nplanes, int n_pad) {
   return (size_t)nplanes * ((size_t)kTileM * 64 * 2 + (size_t)(n_pad / 2) * 64 * 2);
 }
 
+constexpr int kPairAccBars = 4;          // accumulation barriers (two-pass mode uses 2, streaming mode 4 TMEM buffers)
+constexpr int kPairStreamStride = 128;   // TMEM columns between the four buffers of the streaming mode (n_pad <= 128)
+constexpr int kPairBarBytes = 512;       // barrier block in front of the R-CNN weight staging area
+
+// p.pair_stream != 0 (1x1 layers, NPLANES == 2, n_pad <= 128): the streaming accumulation of conv_tc_halo2.cuh - the
+// correction products of segment s go to slot s + 1 FIRST, the dominant products to slot s, slots rotate over four
+// TMEM buffers - so every stage is released by the commit behind its own UMMAs and the whole ring is prefetch depth.
+// A1|B1 reads 3.1 GB of concatenated features per 256-tile step: it is bound by HBM, and the two-pass form kept
+// seg_chunks of its five 44 KB stages parked until their second pass.
 template <int NPLANES>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
@@ -108,8 +117,8 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)num_stages * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* acc_full = empty_bar + kMaxStages;
-  uint64_t* acc_empty = acc_full + kAccStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kAccStages);
+  uint64_t* acc_empty = acc_full + kPairAccBars;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kPairAccBars);
   float* s_rdot = reinterpret_cast<float*>(tmem_slot + 4);   // 16-byte aligned (barriers start 1024-aligned)
 
   const int warp = threadIdx.x >> 5;
@@ -122,7 +131,7 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
       ptx::mbar_init(&full_bar[s], 1);                     // leader's producer arrive + both CTAs' TMA bytes
       ptx::mbar_init(&empty_bar[s], 1);                    // leader's tcgen05.commit (multicast to both CTAs)
     }
-    for (int s = 0; s < kAccStages; ++s) {
+    for (int s = 0; s < kPairAccBars; ++s) {
       ptx::mbar_init(&acc_full[s], 1);                     // leader's tcgen05.commit (multicast)
       ptx::mbar_init(&acc_empty[s], 2 * kEpiWarps);        // epilogue warps of both CTAs (used on the leader only)
     }
@@ -194,6 +203,56 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
       int stage = 0;
       uint32_t phase = 0;
       uint32_t seg_count = 0;
+      if (NPLANES == 2 && p.pair_stream) {
+        uint32_t bd = 0, phm = 0;                            // dominant buffer of the open segment, per-buffer phase bits
+        for (int item = cluster_id; item < num_items; item += num_clusters) {
+          ptx::mbar_wait(&acc_empty[bd], ((phm >> bd) & 1u) ^ 1u);
+          for (int c0 = 0; c0 < total_chunks; c0 += p.seg_chunks) {
+            const uint32_t bc = (bd + 1u) & 3u;
+            ptx::mbar_wait(&acc_empty[bc], ((phm >> bc) & 1u) ^ 1u);
+            ptx::tc_fence_after();
+            const uint32_t tmem_d = tmem_base + bd * (uint32_t)kPairStreamStride;
+            const uint32_t tmem_c = tmem_base + bc * (uint32_t)kPairStreamStride;
+            uint32_t acc_c = 0;                              // corrections open their slot
+            uint32_t acc_d = c0 > 0 ? 1u : 0u;               // the dominant slot already holds the previous corrections
+            const int c1 = (c0 + p.seg_chunks < total_chunks) ? c0 + p.seg_chunks : total_chunks;
+            for (int c = c0; c < c1; ++c) {
+              const int ch = c % p.chunks;
+              ptx::mbar_wait(&full_bar[stage], phase);
+              ptx::tc_fence_after();
+              const uint32_t st_addr = smem_base_u32 + (uint32_t)stage * (uint32_t)STAGE_BYTES;
+              uint32_t ah = desc_lo_t<KC>(st_addr), al = desc_lo_t<KC>(st_addr + A_BYTES);
+              uint32_t bh = desc_lo_t<KC>(st_addr + NPLANES * A_BYTES), bl = desc_lo_t<KC>(st_addr + NPLANES * A_BYTES + BH_BYTES);
+              int ksteps = (p.cin_pad - ch * KC);
+              ksteps = (ksteps > KC ? KC : ksteps) >> 4;
+              if (ptx::elect_one()) {
+#pragma unroll 1
+                for (int ks = 0; ks < ksteps; ++ks) {
+                  ptx::mma_f16_ss_2sm(tmem_c, make_desc64_t<KC>(al), make_desc64_t<KC>(bh), idesc, acc_c);
+                  ptx::mma_f16_ss_2sm_acc(tmem_c, make_desc64_t<KC>(ah), make_desc64_t<KC>(bl), idesc);
+                  ptx::mma_f16_ss_2sm(tmem_d, make_desc64_t<KC>(ah), make_desc64_t<KC>(bh), idesc, acc_d);
+                  acc_c = 1;
+                  acc_d = 1;
+                  ah += 2; al += 2; bh += 2; bl += 2;       // 32 bytes (16 fp16 along K) in 16-byte descriptor units
+                }
+                ptx::mma_commit_2sm(&empty_bar[stage], 3);   // the stage is free once these UMMAs have read it
+                if (c == c1 - 1) {
+                  ptx::mma_commit_2sm(&acc_full[bd], 3);
+                  if (c1 == total_chunks) ptx::mma_commit_2sm(&acc_full[bc], 3);   // corrections-only slot of the last segment
+                }
+              }
+              acc_c = 1;
+              acc_d = 1;
+              __syncwarp();
+              if (++stage == num_stages) { stage = 0; phase ^= 1; }
+            }
+            phm ^= 1u << bd;
+            bd = bc;
+          }
+          phm ^= 1u << bd;                                   // the corrections-only slot
+          bd = (bd + 1u) & 3u;
+        }
+      } else
       for (int item = cluster_id; item < num_items; item += num_clusters) {
         for (int c0 = 0; c0 < total_chunks; c0 += p.seg_chunks) {
           const int acc = seg_count & 1;
@@ -278,9 +337,12 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
     const int first_chunk = grp * per;
     const int my_chunks = (nch - first_chunk) < per ? ((nch - first_chunk) > 0 ? nch - first_chunk : 0) : per;
     const int col_base = first_chunk * 16;
-    const int nseg = (total_chunks + p.seg_chunks - 1) / p.seg_chunks;
+    const bool stream = NPLANES == 2 && p.pair_stream != 0;
+    const int nseg = (total_chunks + p.seg_chunks - 1) / p.seg_chunks + (stream ? 1 : 0);   // accumulation slots to drain
     const uint32_t lead_acc_empty0 = ptx::mapa_shared(ptx::smem_u32(&acc_empty[0]), 0);
     const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)col_base;
+    const uint32_t acc_mask = stream ? 3u : 1u, acc_stride = stream ? (uint32_t)kPairStreamStride : (uint32_t)kAccStride;
+    const int acc_shift = stream ? 2 : 1;
     uint32_t seg_count = 0;
     for (int item = cluster_id; item < num_items; item += num_clusters) {
       const int n_tile = item % p.n_tiles;
@@ -298,12 +360,12 @@ conv_tc_pair_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
 #pragma unroll
         for (int i = 0; i < 16; ++i) sum[j][i] = 0.f;
       for (int s = 0; s < nseg; ++s) {
-        const int acc = seg_count & 1;
-        ptx::mbar_wait(&acc_full[acc], (seg_count >> 1) & 1);
+        const uint32_t acc = seg_count & acc_mask;          // slots use the buffers round-robin in both modes
+        ptx::mbar_wait(&acc_full[acc], (seg_count >> acc_shift) & 1);
         ptx::tc_fence_after();
-        const uint32_t taddr = taddr0 + (uint32_t)(acc * kAccStride);
+        const uint32_t taddr = taddr0 + acc * acc_stride;
         // fp32 round-to-nearest promotion of the segment: wide TMEM loads (64 / 32 columns per instruction); columns
-        // past this thread's share may be read (they stay inside the accumulator stage) but are never stored.
+        // past this thread's share may be read (they stay inside the allocated columns) but are never stored.
 #pragma unroll
         for (int j = 0; j < kMaxColChunks; j += 4) {
           if (j < my_chunks) {

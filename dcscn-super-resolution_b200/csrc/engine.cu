@@ -118,6 +118,7 @@ struct TcLaunch {
   CUtensorMap tm_hi, tm_lo, tm_w;
   bool pair = false;
   int pair_grid = 0, pair_stages = 0, pair_seg = 1;
+  bool pair_stream = false;
   bool halo = false;             // 3x3 layers: halo-reuse CTA-pair kernel
   CUtensorMap th_hi, th_lo;      // A maps with box {64, 8, 18, 1}
   ConvGeom hg;
@@ -410,6 +411,16 @@ static int tile_cap(const dcscn_handle* h, int ksz);
 // Weight-stage table of the streaming 3x3 kernel (see conv_tc_halo2.cuh): full 64-channel chunks take one stage per tap,
 // a last chunk with 16 / 32 valid channels packs 4 / 2 taps per stage.  `seg_units` = promotion period in units of 12
 // dominant UMMAs (3 taps x 4 slices), like the (chunk, dx) units of the two-pass kernels.
+// Experiments: DCSCN_SEG="CNN2=1,A1=6" overrides the fp32-promotion period of single layers.
+static int seg_override(const std::string& name, int seg) {
+  if (const char* ov = getenv("DCSCN_SEG")) {
+    const std::string key = name + "=";
+    const char* hit = strstr(ov, key.c_str());
+    if (hit && (hit == ov || hit[-1] == ',')) seg = atoi(hit + key.size());
+  }
+  return std::max(1, seg);
+}
+
 static void build_h2_stages(int cin_pad, int seg_units, std::vector<uint32_t>& tab, int* nseg, int* nreg) {
   tab.clear();
   // Packing several taps of a 16/32-channel tail chunk into one 64-half stage saves weight stages but sends those stages
@@ -573,13 +584,11 @@ static int pack_tc_layer(dcscn_handle* h, TcLayer& t) {
   t.h2_stages.clear();
   t.h2_nseg = 0;
   if (need_pair && t.ksz == 3 && tile_cap(h, 3) < 256 && 3 * t.n_pad <= 512) {   // streaming kernel: stage-ordered image
-    int seg = h->seg_chunks > 0 ? h->seg_chunks : (t.n_pad >= 144 ? 1 : (t.n_pad >= 112 ? 2 : 3));
-    if (const char* ov = getenv("DCSCN_SEG")) {   // experiments: "CNN2=1,CNN5=2" overrides the promotion period per layer
-      const std::string key = t.name + "=";
-      const char* hit = strstr(ov, key.c_str());
-      if (hit && (hit == ov || hit[-1] == ',')) seg = std::max(1, atoi(hit + key.size()));
-    }
-    t.h2_seg_units = std::max(1, seg);
+    // Promotion period in (chunk, dx) units of K = 192.  Measured (gpurun_out/seg15.log): with three TMEM buffers
+    // (n_pad >= 144) a period of 1 leaves the epilogue one segment (~1.5 us) to drain a slot and the issuer stalls -
+    // CNN3 0.85 -> 0.63 ms, CNN4 0.74 -> 0.52 ms at 4; the noise-tile error is flat in this range (1.2-1.35e-3).
+    const int seg = seg_override(t.name, h->seg_chunks > 0 ? h->seg_chunks : (t.n_pad >= 144 ? 4 : 3));
+    t.h2_seg_units = seg;
     build_h2_stages(t.cin_pad, seg, t.h2_stages, &t.h2_nseg, &t.h2_nreg);
     if ((int)t.h2_stages.size() / 2 > kH2MaxTable) return fail("layer %s: %zu weight stages exceed the kernel's table", t.name.c_str(), t.h2_stages.size());
     if (upload(&t.d_h2_stages, t.h2_stages, h)) return 1;
@@ -1003,12 +1012,16 @@ static int add_tc_launch(dcscn_handle* h, Plan* pl, const TcLayer& t, const __ha
     L.has_wide = t.has_wide;
     const size_t pstage = tc_pair_stage_bytes(planes(h), t.n_pad);
     L.pair_stages = (int)std::min<size_t>(kMaxStages, budget / pstage);
-    L.pair_smem = L.pair_stages * pstage + 1024 + 256 + kRdotSmemBytes;
+    L.pair_smem = L.pair_stages * pstage + 1024 + kPairBarBytes + kRdotSmemBytes;
     const long long pitems = ((tiles + 1) / 2) * t.n_tiles;
     L.pair_grid = (int)std::min<long long>(pitems, h->sm_count / 2) * 2;
     if (L.pair_stages < 2) L.pair = false;
     int seg = h->seg_chunks > 0 ? h->seg_chunks : (t.n_pad >= 112 ? 2 : 3);
     L.pair_seg = std::max(1, std::min(seg, L.pair_stages - 1));
+    // 1x1 layers stream (split accumulators over four TMEM buffers): nothing is held, the promotion period is free
+    static const bool allow_stream = !(getenv("DCSCN_PAIR_STREAM") && atoi(getenv("DCSCN_PAIR_STREAM")) == 0);   // A/B switch
+    L.pair_stream = allow_stream && t.ksz == 1 && planes(h) == 2 && t.n_pad <= kPairStreamStride;
+    if (L.pair_stream) L.pair_seg = seg_override(t.name, h->seg_chunks > 0 ? h->seg_chunks : 4);
   }
 
   // halo-reuse launch shapes (3x3 layers, CTA pair, KC = 64): 16 x 8 pixel patches
@@ -1314,6 +1327,7 @@ static int launch_tc_pair(dcscn_handle* h, const TcLaunch& L, cudaStream_t st) {
   ConvTCParams p = L.p;
   p.cluster_size = 2;
   p.seg_chunks = L.pair_seg;
+  p.pair_stream = L.pair_stream ? 1 : 0;
   CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc_pair_kernel<NPL>, L.tm_hi, L.tm_lo, L.tm_w, p, L.pair_stages));
   return 0;
 }

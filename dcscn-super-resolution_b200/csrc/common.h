@@ -83,6 +83,7 @@ struct ConvTCParams {
   int h2_nseg;           // fp32-promotion segments per item
   int h2_resident;       // all stages fit in shared memory: loaded once per CTA
   int pair_stream;       // conv_tc_pair_kernel: streaming split-accumulator mode (1x1 layers)
+  unsigned long long* dbg;   // diagnostic builds (-DDCSCN_H2_DEBUG): per-cluster wait counters, else null
   int h2_nreg;           // leading chunks with one tap per stage (issued by the compile-time-structured loop)
   EpiParams epi;
 };

@@ -42,6 +42,16 @@ constexpr uint32_t kH2ChunkFirst = 1u << 20, kH2ChunkLast = 1u << 21, kH2SegEnd 
 
 __host__ __device__ inline size_t tc_halo2_misc_bytes() { return 1024 + kH2BarBytes + kRdotSmemBytes; }
 
+// -DDCSCN_H2_DEBUG builds a diagnostic library (scripts/r2_h2_timeline.sh): the issuing thread and one epilogue warp
+// count the cycles they spend waiting on each kind of barrier and write them to p.dbg[cluster][8].
+#ifdef DCSCN_H2_DEBUG
+#define H2_T0() const long long h2_t0_ = clock64()
+#define H2_ACC(var) var += clock64() - h2_t0_
+#else
+#define H2_T0()
+#define H2_ACC(var)
+#endif
+
 template <int NPLANES>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
@@ -180,8 +190,12 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
       // chunks with the regular one-tap-per-stage layout (all of them unless the packing experiment is on)
       const int n_reg = p.h2_nreg;
       const int seg_target = 12 * p.seg_chunks;             // promotion period in 16-channel slices (12 = one full (chunk, dx) unit)
+#ifdef DCSCN_H2_DEBUG
+      long long w_a = 0, w_b = 0, w_acc = 0;
+      const long long t_begin = clock64();
+#endif
       for (int item = cluster_id; item < num_items; item += num_clusters) {
-        ptx::mbar_wait(&acc_empty[bd], ((phm >> bd) & 1u) ^ 1u);   // takes the dominant products of segment 0
+        { H2_T0(); ptx::mbar_wait(&acc_empty[bd], ((phm >> bd) & 1u) ^ 1u); H2_ACC(w_acc); }   // takes the dominant products of segment 0
         int s = 0;                                          // segment of the tile
         int dom = 0;                                        // stage weight issued into the open segment (12 per unit)
         bool seg_open = true;
@@ -193,12 +207,12 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
         // compile time (no table reads, dy unrolled): the path almost every UMMA of a layer takes
         for (int ch = 0; ch < n_reg; ++ch) {
           const int kt = min(4, (p.cin_pad - (ch << 6)) >> 4);      // 16-channel slices per tap (3 in a 48-channel tail)
-          ptx::mbar_wait(&a_full[sa], spa);                         // the chunk's halo box serves all nine taps
+          { H2_T0(); ptx::mbar_wait(&a_full[sa], spa); H2_ACC(w_a); }   // the chunk's halo box serves all nine taps
           const uint32_t a_desc0 = (((sa_u32 + (uint32_t)sa * (uint32_t)A_SLOT) & 0x3FFFFu) >> 4) | (1u << 16);
           for (int dx = 0; dx < 3; ++dx) {
             if (seg_open) {
               bc = (bd + 1u == nbuf) ? 0u : bd + 1u;
-              if (NPLANES == 2) ptx::mbar_wait(&acc_empty[bc], ((phm >> bc) & 1u) ^ 1u);
+              if (NPLANES == 2) { H2_T0(); ptx::mbar_wait(&acc_empty[bc], ((phm >> bc) & 1u) ^ 1u); H2_ACC(w_acc); }
               tmem_d = tmem_base + bd * (uint32_t)acc_stride;
               tmem_c = tmem_base + bc * (uint32_t)acc_stride;
               fresh = true;
@@ -209,7 +223,7 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
             const bool seg_end = (dom >= seg_target) || (st + 3 == nst);   // same rule as build_h2_stages
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy, ++st) {
-              ptx::mbar_wait(&b_full[sb], spb);
+              { H2_T0(); ptx::mbar_wait(&b_full[sb], spb); H2_ACC(w_b); }
               ptx::tc_fence_after();
               const uint32_t b_addr = sb_u32 + (uint32_t)sb * (uint32_t)B_STAGE;
               uint32_t bh = desc_lo_t<KC>(b_addr), bl = desc_lo_t<KC>(b_addr + BH_BYTES);
@@ -218,8 +232,11 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
               if (ptx::elect_one()) {
                 constexpr uint32_t kDescHiA = (uint32_t)((kHalo1W * 128) >> 4) | (1u << 14) | (2u << 29);
                 constexpr uint32_t kDescHiB = (uint32_t)(TcSmem<KC>::kSbo >> 4) | (1u << 14) | ((uint32_t)TcSmem<KC>::kLayout << 29);
-#pragma unroll 1
-                for (int ks = 0; ks < kt; ++ks) {
+                // slice 0 may open the segment's accumulation slots; slices 1.. always accumulate.  Full chunks (kt == 4)
+                // run the remaining slices as straight-line code: the single issuing thread spends ~7 instructions per
+                // slice instead of ~20 (loop control + vector->uniform moves), which is what bounds the thin layers
+                // (N <= 64: a UMMA lasts 24-32 cycles).
+                {
                   const uint64_t da_hi = ((uint64_t)kDescHiA << 32) | ah, db_hi = ((uint64_t)kDescHiB << 32) | bh;
                   if (fresh) {
                     if (NPLANES == 2) {
@@ -227,7 +244,6 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
                       ptx::mma_f16_ss_2sm_acc(tmem_c, da_hi, ((uint64_t)kDescHiB << 32) | bl, idesc);
                     }
                     ptx::mma_f16_ss_2sm(tmem_d, da_hi, db_hi, idesc, acc_d0);
-                    fresh = false;
                   } else {
                     if (NPLANES == 2) {
                       ptx::mma_f16_ss_2sm_acc(tmem_c, ((uint64_t)kDescHiA << 32) | al, db_hi, idesc);
@@ -235,7 +251,28 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
                     }
                     ptx::mma_f16_ss_2sm_acc(tmem_d, da_hi, db_hi, idesc);
                   }
-                  ah += 2; al += 2; bh += 2; bl += 2;
+                }
+                if (kt == 4) {
+#pragma unroll
+                  for (int ks = 1; ks < 4; ++ks) {
+                    const uint64_t da_hi = ((uint64_t)kDescHiA << 32) | (ah + 2u * ks), db_hi = ((uint64_t)kDescHiB << 32) | (bh + 2u * ks);
+                    if (NPLANES == 2) {
+                      ptx::mma_f16_ss_2sm_acc(tmem_c, ((uint64_t)kDescHiA << 32) | (al + 2u * ks), db_hi, idesc);
+                      ptx::mma_f16_ss_2sm_acc(tmem_c, da_hi, ((uint64_t)kDescHiB << 32) | (bl + 2u * ks), idesc);
+                    }
+                    ptx::mma_f16_ss_2sm_acc(tmem_d, da_hi, db_hi, idesc);
+                  }
+                } else {
+#pragma unroll 1
+                  for (int ks = 1; ks < kt; ++ks) {
+                    ah += 2; al += 2; bh += 2; bl += 2;
+                    const uint64_t da_hi = ((uint64_t)kDescHiA << 32) | ah, db_hi = ((uint64_t)kDescHiB << 32) | bh;
+                    if (NPLANES == 2) {
+                      ptx::mma_f16_ss_2sm_acc(tmem_c, ((uint64_t)kDescHiA << 32) | al, db_hi, idesc);
+                      ptx::mma_f16_ss_2sm_acc(tmem_c, da_hi, ((uint64_t)kDescHiB << 32) | bl, idesc);
+                    }
+                    ptx::mma_f16_ss_2sm_acc(tmem_d, da_hi, db_hi, idesc);
+                  }
                 }
                 if (!resident) ptx::mma_commit_2sm(&b_empty[sb], 3);
                 if (dy == 2 && dx == 2) ptx::mma_commit_2sm(&a_empty[sa], 3);
@@ -345,6 +382,15 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
         }
         if (resident) sb = 0;
       }
+#ifdef DCSCN_H2_DEBUG
+      if (p.dbg != nullptr && lane == 0) {
+        unsigned long long* d = p.dbg + (size_t)cluster_id * 8;
+        d[0] = (unsigned long long)(clock64() - t_begin);
+        d[1] = (unsigned long long)w_a;
+        d[2] = (unsigned long long)w_b;
+        d[3] = (unsigned long long)w_acc;
+      }
+#endif
     }
   } else {
     ptx::setmaxnreg_inc<kRegsEpilogue>();
@@ -363,6 +409,10 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
     const uint32_t lead_acc_empty0 = ptx::mapa_shared(ptx::smem_u32(&acc_empty[0]), 0);
     const uint32_t taddr0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)col_base;
     uint32_t eb = 0, ephm = 0;                           // buffer of the next slot to drain, per-buffer phase parity
+#ifdef DCSCN_H2_DEBUG
+    long long w_full = 0, t_store = 0;
+    const long long t_begin = clock64();
+#endif
     for (int item = cluster_id; item < num_items; item += num_clusters) {
       const int n_tile = item % p.n_tiles;
       const int tile = (item / p.n_tiles) * 2 + (int)rank;
@@ -380,7 +430,7 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
         for (int i = 0; i < 16; ++i) sum[j][i] = 0.f;
       for (int s = 0; s < nslots; ++s) {
         const uint32_t buf = eb;
-        ptx::mbar_wait(&acc_full[buf], (ephm >> buf) & 1u);
+        { H2_T0(); ptx::mbar_wait(&acc_full[buf], (ephm >> buf) & 1u); H2_ACC(w_full); }
         ptx::tc_fence_after();
         const uint32_t taddr = taddr0 + buf * (uint32_t)acc_stride;
         // fp32 round-to-nearest promotion of the slot: wide TMEM loads (64 / 32 columns per instruction); columns
@@ -407,6 +457,7 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
         ephm ^= 1u << buf;
         eb = (eb + 1u == nbuf) ? 0u : eb + 1u;
       }
+      H2_T0();
       if (p.epi.mode == EPI_D2S_RDOT) {
         float v[9];
 #pragma unroll
@@ -430,7 +481,16 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
         for (int j = 0; j < kMaxColChunks; ++j)
           if (j < my_chunks) epilogue_store16(p.epi, g, n_total, img, y, x, n_tile * p.n_pad + col_base + j * 16, sum[j]);
       }
+      H2_ACC(t_store);
     }
+#ifdef DCSCN_H2_DEBUG
+    if (p.dbg != nullptr && leader && warp == kEpiWarp0 && lane == 0) {
+      unsigned long long* d = p.dbg + (size_t)cluster_id * 8;
+      d[4] = (unsigned long long)(clock64() - t_begin);
+      d[5] = (unsigned long long)w_full;
+      d[6] = (unsigned long long)t_store;
+    }
+#endif
   }
 
   ptx::tc_fence_before();

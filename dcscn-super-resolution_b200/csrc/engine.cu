@@ -236,6 +236,7 @@ struct dcscn_handle {
   int conv_impl = 0;
   int kc = 64;
   int seg_chunks = 0;                // pipeline stages per fp32-promotion segment; 0 = automatic
+  int act_grad_impl = 0;             // 0: 16-byte activation-gradient kernel, 1: channel-pair kernel (cross-check)
   int cluster = 1;                   // CTAs per cluster multicasting the weight tiles (single-CTA kernel)
   int pair = 1;                      // use the CTA-pair (tcgen05 cta_group::2) kernel when KC == 64
   int halo = 3;                      // 3x3 layers: halo-reuse CTA-pair kernel, 1 = three 18x8 boxes, 2 = one 18x10 box per chunk
@@ -1390,6 +1391,38 @@ static int launch_tc_halo1(dcscn_handle* h, const TcLaunch& L, cudaStream_t st) 
   return 0;
 }
 
+#ifdef DCSCN_H2_DEBUG
+static unsigned long long* g_h2_dbg = nullptr;
+static int g_h2_dbg_launch = 0;
+static std::string g_h2_dbg_names[64];
+// Prints, per launch since the last dump: issuer cycles (total / waiting for A boxes / weight stages / free TMEM buffers)
+// and epilogue cycles (total / waiting for full accumulators / bias-PReLU-store phase), averaged over clusters.
+extern "C" int dcscn_h2_debug_dump(void) {
+  if (!g_h2_dbg) return 0;
+  cudaDeviceSynchronize();
+  std::vector<unsigned long long> hbuf((size_t)8 * 128 * 64);
+  cudaMemcpy(hbuf.data(), g_h2_dbg, hbuf.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  for (int l = 0; l < std::min(g_h2_dbg_launch, 64); ++l) {
+    double a[8] = {0};
+    int n = 0;
+    for (int c = 0; c < 128; ++c) {
+      const unsigned long long* d = hbuf.data() + ((size_t)l * 128 + c) * 8;
+      if (d[0] == 0) continue;
+      for (int k = 0; k < 8; ++k) a[k] += (double)d[k];
+      ++n;
+    }
+    if (!n) continue;
+    for (int k = 0; k < 8; ++k) a[k] /= n;
+    printf("%-70s clusters %3d | issuer total %9.0f  wait A %5.1f%%  wait W %5.1f%%  wait TMEM %5.1f%% | epilogue total %9.0f  wait acc %5.1f%%  store %5.1f%%\n",
+           g_h2_dbg_names[l].c_str(), n, a[0], 100 * a[1] / a[0], 100 * a[2] / a[0], 100 * a[3] / a[0], a[4], 100 * a[5] / a[4], 100 * a[6] / a[4]);
+  }
+  cudaMemset(g_h2_dbg, 0, hbuf.size() * sizeof(unsigned long long));
+  g_h2_dbg_launch = 0;
+  fflush(stdout);
+  return 0;
+}
+#endif
+
 template <int NPL>
 static int launch_tc_halo2(dcscn_handle* h, const TcLaunch& L, cudaStream_t st) {
   static bool attr_set_dev[64] = {};   // function attributes are per device
@@ -1415,6 +1448,22 @@ static int launch_tc_halo2(dcscn_handle* h, const TcLaunch& L, cudaStream_t st) 
   p.g = L.hg;
   p.cluster_size = 2;
   p.seg_chunks = L.halo2_seg;
+#ifdef DCSCN_H2_DEBUG
+  {  // diagnostic build: one counter block per launch, dumped by h2_debug_dump() (scripts/r2_h2_timeline.sh)
+    static unsigned long long* d_dbg = nullptr;
+    if (!d_dbg) {
+      CUDA_TRY(cudaMalloc(&d_dbg, sizeof(unsigned long long) * 8 * 128 * 64));
+      CUDA_TRY(cudaMemset(d_dbg, 0, sizeof(unsigned long long) * 8 * 128 * 64));
+    }
+    g_h2_dbg = d_dbg;
+    p.dbg = d_dbg + (size_t)(g_h2_dbg_launch % 64) * 8 * 128;
+    const std::string lname = L.layer_index >= 0 ? (L.layer_bwd ? h->bwd : h->tcl)[L.layer_index].name : std::string("?");
+    g_h2_dbg_names[g_h2_dbg_launch % 64] = lname + (L.layer_bwd ? "(bwd)" : "") + " n_pad=" + std::to_string(L.p.n_pad) +
+        " cin_pad=" + std::to_string(L.p.cin_pad) + " nst=" + std::to_string(L.p.h2_nstages) + " res=" + std::to_string(L.p.h2_resident) +
+        " na=" + std::to_string(L.halo2_na) + " nb=" + std::to_string(L.halo2_nb) + " grid=" + std::to_string(L.halo_grid);
+    ++g_h2_dbg_launch;
+  }
+#endif
   const bool wide = h->wmap_wide && L.has_wide;
   CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc_halo2_kernel<NPL>, L.t1_hi, L.t1_lo, wide ? L.tm_w_wide : L.tm_w, p, L.halo2_na,
                               L.halo2_nb, wide ? 1 : 0));
@@ -2199,6 +2248,9 @@ int dcscn_set_option(dcscn_handle* h, const char* key, int64_t value) {
     h->wgrad_taps = (int)value;
   } else if (k == "host_repack") {
     h->host_repack = value ? 1 : 0;
+  } else if (k == "act_grad_impl") {
+    if (value < 0 || value > 1) return fail("act_grad_impl must be 0 or 1");
+    h->act_grad_impl = (int)value;
   } else if (k == "seg_chunks") {
     if (value < 0 || value > 4096) return fail("seg_chunks must be >= 0 (0 = automatic)");
     h->seg_chunks = (int)value;

@@ -152,6 +152,30 @@ def test_tensor_core_wgrad_matches_cuda_core_wgrad_full_model():
         assert np.abs(got - ref).max() <= 1e-4 * np.abs(ref).max() + 1e-12, (k, float(np.abs(got - ref).max()), float(np.abs(ref).max()))
 
 
+def test_activation_gradient_kernels_agree():
+    """act_grad_impl 0 (16-byte loads, 8 channels per thread, the default) against 1 (channel pairs): same element-wise
+    results, bias / alpha sums in a different order."""
+    from helper import engine as E
+    import conftest
+    wts = conftest.load_golden_weights("dcscn_L12_F196to48_NIN_A64_PS_R1F32")
+    g = np.random.RandomState(12)
+    n, h, w = 2, 19, 23
+    x = (g.rand(n, h, w, 1) * 255).astype(np.float32)
+    x2 = (g.rand(n, 2 * h, 2 * w, 1) * 255).astype(np.float32)
+    y = np.clip(x2 + g.randn(n, 2 * h, 2 * w, 1) * 10, 0, 255).astype(np.float32)
+    grads = []
+    for impl in (1, 0):
+        eng = E.Engine(E.make_config(scale=2, dropout_keep=0.8))
+        eng.set_params(wts)
+        eng.set_option("act_grad_impl", impl)
+        eng.train_step_host(x, x2, y, lr=0.002, seed=5, apply_update=False)
+        grads.append({k: eng.get_grad(k) for k in wts})
+        eng.close()
+    for k in wts:
+        ref, got = grads[0][k], grads[1][k]
+        assert np.abs(got - ref).max() <= 2e-5 * np.abs(ref).max() + 1e-12, (k, float(np.abs(got - ref).max()), float(np.abs(ref).max()))
+
+
 def test_full_size_batch_gradient_is_mean_of_half_batch_gradients():
     """BASELINE configs[3] size (L12 x4, 64 patches of 48x48 -> 192x192), where the CPU oracle would take minutes:
     with dropout off the loss is a mean over patches, so every gradient of the full batch must equal the mean of the

@@ -113,6 +113,29 @@ def test_validation_kernels_agree_with_tensor_core_path(small):
     assert np.abs(y_strict - y64).max() <= 1.5 * max(err_ref, 5e-4), (float(np.abs(y_strict - y64).max()), err_ref)
 
 
+@pytest.mark.parametrize("opts", [{"halo": 2}, {"halo": 1}, {"halo": 0}, {"pair": 0}, {"pair": 0, "cluster": 2}, {"pair": 0, "cluster": 4}],
+                         ids=["halo1-single-box", "halo-three-box", "pair-two-pass", "single-cta", "multicast-2", "multicast-4"])
+def test_earlier_kernel_generations_stay_correct(small, opts):
+    """The selectable predecessors of the streaming kernel (A/B baselines for the profiles under profiles/): every one
+    has to keep producing the same forward within the stress bound, or be deleted."""
+    cfg, wts, eng = small
+    g = np.random.RandomState(21)
+    x = (g.rand(2, 26, 35, 1) * 255).astype(np.float32)
+    x2 = (g.rand(2, 52, 70, 1) * 255).astype(np.float32)
+    y64 = O.Oracle(cfg, wts, torch.float64).forward(x.astype(np.float64), x2.astype(np.float64))
+    y32 = O.Oracle(cfg, wts, torch.float32).forward(x, x2)
+    defaults = {"halo": 3, "pair": 1, "cluster": 1}
+    try:
+        for k, v in opts.items():
+            eng.set_option(k, v)
+        y = gpu_forward(eng, x, x2)
+    finally:
+        for k in opts:
+            eng.set_option(k, defaults[k])
+    assert np.isfinite(y).all()
+    assert np.abs(y - y64).max() <= max(TOL_DEFAULT_STRESS, stress_bound(y32, y64))
+
+
 def test_kc32_pipeline_variant(small):
     cfg, wts, eng = small
     g = np.random.RandomState(8)

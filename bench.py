@@ -125,15 +125,51 @@ def ncu_traffic():
 
 
 # --------------------------------------------------------------------------------------------- CPU oracle ----
-def _pin_cpu_threads():
-    """torchrun exports OMP_NUM_THREADS=1; the CPU arm must use the whole box whatever launched it."""
-    import torch
+def _usable_cpus():
+    """Cores this process may really use: scheduler affinity capped by the cgroup CPU quota (a container that sees 128
+    CPUs but owns 16 of them runs 16x slower with 128 threads than with 16)."""
     n = os.cpu_count() or 1
     try:
         n = len(os.sched_getaffinity(0))
     except (AttributeError, OSError):
         pass
-    torch.set_num_threads(max(1, n))
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(int(txt[0]) / int(txt[1]) + 0.5)))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                    n = min(n, max(1, int(q / per + 0.5)))
+            break
+        except (OSError, ValueError, IndexError):
+            continue
+    return max(1, n)
+
+
+def _pin_cpu_threads(probe=None):
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm must use the whole box whatever launched it.  The thread count is
+    the fastest of a few candidates (usable cores, half, quarter, torch's own default) on a short probe run - more
+    threads than the box really gives is much slower, not faster."""
+    import torch
+    n = _usable_cpus()
+    cands = sorted({n, max(1, n // 2), max(1, n // 4), min(n, max(1, torch.get_num_threads()))}, reverse=True)
+    if probe is None or len(cands) == 1:
+        torch.set_num_threads(cands[0])
+        return torch.get_num_threads()
+    best, best_t = cands[0], None
+    for c in cands:
+        torch.set_num_threads(c)
+        probe()                                   # warm the pool at this size
+        t0 = time.perf_counter()
+        probe()
+        dt = time.perf_counter() - t0
+        if best_t is None or dt < best_t:
+            best, best_t = c, dt
+    torch.set_num_threads(best)
     return torch.get_num_threads()
 
 
@@ -144,11 +180,11 @@ def cpu_oracle_passes(passes, warm, tiles=CPU_TILES):
     import torch
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import dcscn_oracle as O
-    threads = _pin_cpu_threads()
     orc = O.Oracle(O.OracleConfig(), load_weights(), torch.float32)
     g = np.random.RandomState(0)
     x = (g.rand(tiles, TILE, TILE, 1) * 255).astype(np.float32)
     x2 = (g.rand(tiles, SCALE * TILE, SCALE * TILE, 1) * 255).astype(np.float32)
+    threads = _pin_cpu_threads(probe=lambda: orc.forward(x[:4], x2[:4]))
     for _ in range(max(1, warm)):
         orc.forward(x, x2)   # warm-up (thread pool, oneDNN primitive cache)
     secs = []

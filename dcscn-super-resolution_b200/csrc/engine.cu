@@ -28,7 +28,7 @@
 #include "conv_ds_tile.cuh"
 #include "train.cuh"
 #include "wgrad_tc.cuh"
-#include "wgrad_tc.cuh"
+#include "umma_probe.cuh"
 
 using namespace dcscn;
 
@@ -153,6 +153,16 @@ struct Plan {
   bool ran_fused = false;
   std::vector<TcLaunch> bwd;     // dgrad launches (built lazily by the train step)
   bool bwd_built = false;
+  // CUDA graph of CNN1 + the tensor-core layers (everything but the last kernel, the only one that reads x2 / writes y):
+  // instantiated after the plan ran eagerly once, replayed while the input pointer and the option epoch stay the same
+  cudaGraphExec_t gexec = nullptr;
+  const float* g_x = nullptr;
+  uint64_t g_epoch = 0;
+  bool g_fused = false;
+  int g_launches = 0;
+  int eager_runs = 0;
+  const float* last_x = nullptr; // input of the previous forward on this plan: a graph is only built for a pointer seen twice in a row
+  ~Plan() { if (gexec) cudaGraphExecDestroy(gexec); }
 };
 
 struct dcscn_handle {
@@ -232,6 +242,10 @@ struct dcscn_handle {
 
   std::vector<std::unique_ptr<Plan>> plans;
   Plan* last_plan = nullptr;
+  int use_graph = 1;                 // option "graph": replay the per-(n,h,w) launch sequence of a forward as one CUDA graph
+  uint64_t graph_epoch = 1;          // bumped by everything a captured launch bakes in (options, weight re-packs)
+  cudaStream_t cap_stream = nullptr; // capture happens on a private stream (the caller's may be the legacy default stream)
+  int64_t graph_replays = 0;
 
   int conv_impl = 0;
   int kc = 64;
@@ -858,6 +872,7 @@ static int finalize_params(dcscn_handle* h) {
     h->plans.clear();
     h->last_plan = nullptr;
   }
+  h->graph_epoch++;          // captured launches bake the epilogue's 1 / weight-scale
   h->params_dirty = false;
   return 0;
 }
@@ -1712,22 +1727,9 @@ static int forward_ds(dcscn_handle* h, const float* x, const float* x2, float* y
   return 0;
 }
 
-static int forward_impl(dcscn_handle* h, const float* x, const float* x2, float* y, int n, int H, int W,
-                        cudaStream_t st) {
-  if (n <= 0 || H <= 0 || W <= 0) return fail("forward: bad shape n=%d h=%d w=%d", n, H, W);
-  CUDA_TRY(cudaSetDevice(h->cfg.device_id));
-  if (h->params_dirty && finalize_params(h)) return 1;
-  if (ensure_workspace(h, (size_t)n * H * W)) return 1;
-  if (h->cfg.depthwise_separable) {
-    h->ds_n = n; h->ds_h = H; h->ds_w = W;
-    return forward_ds(h, x, x2, y, n, H, W, st);
-  }
-  Plan* pl = get_plan(h, n, H, W);
-  if (!pl) return 1;
-  h->last_plan = pl;
-  h->ev_used = 0;
-  if (mark(h, st)) return 1;
-
+// CNN1 and the tensor-core layers of one forward, in execution order, on `st` (a capturing stream when the plan's graph is
+// being built).  The last kernel (R-CNN1 gather / R-CNN1) is issued by forward_impl: it alone touches x2 and y.
+static int issue_front(dcscn_handle* h, Plan* pl, const float* x, int n, int H, int W, bool fused, cudaStream_t st) {
   {  // CNN1
     ConvFirstParams p = pl->first;
     p.x = x;
@@ -1746,12 +1748,61 @@ static int forward_impl(dcscn_handle* h, const float* x, const float* x2, float*
     h->launches++;
     if (mark(h, st)) return 1;
   }
-  const bool fused = pl->fused_last && h->fuse_last && h->conv_impl == 0;
   for (size_t i = 0; i < pl->tc.size(); ++i) {
     const TcLaunch& L = ((int)i == pl->fused_index && !fused) ? pl->unfused : pl->tc[i];
     if (launch_tc(h, L, st)) return 1;
     if (mark(h, st)) return 1;
   }
+  return 0;
+}
+
+static int forward_impl(dcscn_handle* h, const float* x, const float* x2, float* y, int n, int H, int W,
+                        cudaStream_t st) {
+  if (n <= 0 || H <= 0 || W <= 0) return fail("forward: bad shape n=%d h=%d w=%d", n, H, W);
+  CUDA_TRY(cudaSetDevice(h->cfg.device_id));
+  if (h->params_dirty && finalize_params(h)) return 1;
+  if (ensure_workspace(h, (size_t)n * H * W)) return 1;
+  if (h->cfg.depthwise_separable) {
+    h->ds_n = n; h->ds_h = H; h->ds_w = W;
+    return forward_ds(h, x, x2, y, n, H, W, st);
+  }
+  Plan* pl = get_plan(h, n, H, W);
+  if (!pl) return 1;
+  h->last_plan = pl;
+  h->ev_used = 0;
+  if (mark(h, st)) return 1;
+  const bool fused = pl->fused_last && h->fuse_last && h->conv_impl == 0;
+
+  // ---- graph replay / capture of the launches in front of the last kernel (15 launches per step)
+  const bool graphable = h->use_graph && !h->timing && h->conv_impl == 0;
+  if (graphable && pl->gexec && pl->g_x == x && pl->g_epoch == h->graph_epoch && pl->g_fused == fused) {
+    CUDA_TRY(cudaGraphLaunch(pl->gexec, st));
+    h->launches += pl->g_launches;
+    h->graph_replays++;
+  } else if (graphable && pl->eager_runs >= 1 && pl->last_x == x) {
+    if (!h->cap_stream) CUDA_TRY(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+    if (pl->gexec) { cudaGraphExecDestroy(pl->gexec); pl->gexec = nullptr; }
+    const int64_t before = h->launches;
+    CUDA_TRY(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = issue_front(h, pl, x, n, H, W, fused, h->cap_stream);
+    cudaGraph_t g = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(h->cap_stream, &g);
+    h->launches = before;
+    if (rc) { if (g) cudaGraphDestroy(g); return 1; }
+    if (ce != cudaSuccess || g == nullptr) return fail("forward: stream capture failed: %s", cudaGetErrorString(ce));
+    const cudaError_t ie = cudaGraphInstantiate(&pl->gexec, g, 0);
+    cudaGraphDestroy(g);
+    if (ie != cudaSuccess) { pl->gexec = nullptr; return fail("forward: cudaGraphInstantiate failed: %s", cudaGetErrorString(ie)); }
+    pl->g_x = x; pl->g_epoch = h->graph_epoch; pl->g_fused = fused;
+    pl->g_launches = 1 + (int)pl->tc.size();
+    CUDA_TRY(cudaGraphLaunch(pl->gexec, st));
+    h->launches += pl->g_launches;
+    h->graph_replays++;
+  } else {
+    if (issue_front(h, pl, x, n, H, W, fused, st)) return 1;
+    pl->eager_runs++;
+  }
+  pl->last_x = x;
   pl->ran_fused = fused;
   if (h->wait_x2) {  // forward_host: x2 was copied on the side stream
     CUDA_TRY(cudaStreamWaitEvent(st, h->x2_ready, 0));
@@ -1931,6 +1982,8 @@ int dcscn_destroy(dcscn_handle* h) {
   for (auto& pt : h->pil_tables) { cudaFree(pt.k); cudaFree(pt.bounds); }
   cudaFree(h->pil_tmp);
   cudaFree(h->ps_lr); cudaFree(h->ps_bic); cudaFree(h->ps_true); cudaFree(h->ps_idx);
+  h->plans.clear();
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->x2_ready) cudaEventDestroy(h->x2_ready);
   delete h;
@@ -2191,6 +2244,11 @@ int dcscn_get_activation(dcscn_handle* h, const char* tensor, float* host_data, 
 int dcscn_set_option(dcscn_handle* h, const char* key, int64_t value) {
   if (!h || !key) return fail("dcscn_set_option: null argument");
   const std::string k(key);
+  h->graph_epoch++;          // whatever changes, captured launch sequences are rebuilt
+  if (k == "graph") {
+    h->use_graph = value ? 1 : 0;
+    return 0;
+  }
   if (k == "conv_impl") {
     if (value != 0 && value != 1) return fail("conv_impl must be 0 (tcgen05) or 1 (CUDA-core validation)");
     h->conv_impl = (int)value;
@@ -2508,7 +2566,67 @@ int dcscn_dropout_mask(dcscn_handle* h, const char* tensor, uint32_t seed, int n
   return 0;
 }
 
+// Measurement entry (csrc/umma_probe.cuh): kind::f16 UMMA throughput with operands resident in shared memory.
+// group = 1 | 2 (cta_group), n = accumulator width of one product, mode 0 = three products per K slice (the scheme
+// of the conv kernels), 1 = stacked 2n + n (group 1 only), 2 = one product.  Returns the launch's duration and the
+// longest issuing-thread span in cycles.
+int dcscn_umma_probe(int device_id, int group, int n, int mode, int iters, float* out_ms, double* out_cycles) {
+  if ((group != 1 && group != 2) || n < 16 || n > 256 || (n & 15) || mode < 0 || mode > 2 || iters < 1)
+    return fail("dcscn_umma_probe: bad argument");
+  if (mode == 1 && (group != 1 || n > 128)) return fail("dcscn_umma_probe: the stacked form needs group 1 and n <= 128");
+  CUDA_TRY(cudaSetDevice(device_id));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device_id));
+  if (prop.major != 10) return fail("dcscn_umma_probe: device %d is not sm_100", device_id);
+  const int grid = (prop.multiProcessorCount / 2) * 2;
+  const int b_rows = group == 2 ? n / 2 : n;
+  const size_t smem = 2 * (size_t)(2 * 128 * 128 + 2 * b_rows * 128) + 1024 + 64;
+  CUDA_TRY(cudaFuncSetAttribute(umma_probe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CUDA_TRY(cudaFuncSetAttribute(umma_probe_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  unsigned long long* d_cyc = nullptr;
+  CUDA_TRY(cudaMalloc(&d_cyc, sizeof(unsigned long long) * grid));
+  CUDA_TRY(cudaMemset(d_cyc, 0, sizeof(unsigned long long) * grid));
+  UmmaProbeParams p{n, mode, iters, d_cyc};
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(128);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = group;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; ++rep) {          // first pass warms up; report the faster of the other two
+    CUDA_TRY(cudaEventRecord(e0, 0));
+    if (group == 2) CUDA_TRY(cudaLaunchKernelEx(&cfg, umma_probe_kernel<2>, p));
+    else CUDA_TRY(cudaLaunchKernelEx(&cfg, umma_probe_kernel<1>, p));
+    CUDA_TRY(cudaEventRecord(e1, 0));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  std::vector<unsigned long long> cyc(grid);
+  CUDA_TRY(cudaMemcpy(cyc.data(), d_cyc, sizeof(unsigned long long) * grid, cudaMemcpyDeviceToHost));
+  unsigned long long mx = 0;
+  for (auto c : cyc) mx = std::max(mx, c);
+  cudaFree(d_cyc);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (out_ms) *out_ms = best;
+  if (out_cycles) *out_cycles = (double)mx;
+  return 0;
+}
+
 int64_t dcscn_launch_count(dcscn_handle* h) { return h ? h->launches : 0; }
 int64_t dcscn_device_bytes(dcscn_handle* h) { return h ? h->device_bytes : 0; }
+int64_t dcscn_graph_replays(dcscn_handle* h) { return h ? h->graph_replays : 0; }
 
 }  // extern "C"

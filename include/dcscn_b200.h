@@ -174,6 +174,8 @@ int dcscn_get_activation(dcscn_handle* h, const char* tensor, float* host_data, 
  *          "cluster" 1 | 2 | 4 = CTAs per cluster multicasting weight tiles in the single-CTA kernel (default 1);
  *          "fuse_last" 1 | 0 = compute the per-pixel half of R-CNN1 inside the last Up-PS epilogue (default 1);
  *          "timing" 0 | 1 = record per-launch CUDA events (see dcscn_get_timings);
+ *          "graph" 1 | 0 = replay the launches of a forward (all but the last kernel) as one CUDA graph per (n, h, w) once
+ *          the same input pointer has been seen twice in a row (default 1; off while "timing" = 1 or "conv_impl" = 1);
  *          "l1_loss" 0 | 1 = image_loss of the train step is mean |y_ - y| instead of the MSE (--use_l1_loss,
  *          DCSCN.py:342-344; the returned mse stays the MSE);
  *          "wgrad_impl" 0 | 1 = filter gradients on tcgen05 (default) or on CUDA cores (cross-check);
@@ -186,8 +188,16 @@ int dcscn_set_option(dcscn_handle* h, const char* key, int64_t value);
 int dcscn_get_timings(dcscn_handle* h, float* ms, int capacity, int* count, char* names, int names_len);
 /* Number of kernels this handle has launched so far (bench.py "gpu_launches"). */
 int64_t dcscn_launch_count(dcscn_handle* h);
+/* Forwards served by a CUDA-graph replay so far (option "graph"). */
+int64_t dcscn_graph_replays(dcscn_handle* h);
 /* Bytes of device memory currently held by the handle. */
 int64_t dcscn_device_bytes(dcscn_handle* h);
+/* Measurement only (no reference counterpart; bench.py's roofline denominator): kind::f16 tcgen05.mma throughput with
+ * both operands resident in shared memory, every SM busy.  group = 1 | 2 (cta_group), n = accumulator width of one
+ * product (multiple of 16), mode 0 = the three hi/lo products of the conv kernels per K = 16 slice, 1 = the stacked
+ * form (one UMMA of width 2n + one of width n; group 1, n <= 128), 2 = a single product; iters x 4 slices are issued by
+ * each cluster.  Returns the launch duration (ms, CUDA events) and the longest issuing-thread span (SM cycles). */
+int dcscn_umma_probe(int device_id, int group, int n, int mode, int iters, float* out_ms, double* out_cycles);
 
 #ifdef __cplusplus
 }

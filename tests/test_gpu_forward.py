@@ -281,3 +281,39 @@ def test_errors_are_loud():
     with pytest.raises(E.EngineError):
         eng.set_option("conv_impl", 7)
     eng.close()
+
+
+def test_cuda_graph_replay_is_bit_identical_and_follows_weight_updates(small):
+    """Option "graph": the launches in front of the last kernel are replayed as one CUDA graph once the same input
+    pointer came twice in a row.  Replays must equal the eager launches bit for bit, and a graph must never outlive
+    what it baked in (weights re-packed with another power-of-two scale, options)."""
+    cfg, wts, eng = small
+    g = np.random.RandomState(11)
+    x = torch.from_numpy((g.rand(2, 40, 56, 1) * 255).astype(np.float32)).cuda()
+    x2 = torch.from_numpy((g.rand(2, 80, 112, 1) * 255).astype(np.float32)).cuda()
+    eng.set_option("graph", 0)
+    la = eng.launch_count
+    y_eager = eng.forward(x, x2).cpu().numpy()
+    per_forward = eng.launch_count - la
+    eng.set_option("graph", 1)
+    r0, l0 = eng.graph_replays, eng.launch_count
+    ys = [eng.forward(x, x2).cpu().numpy() for _ in range(4)]       # eager, capture + replay, replay, replay
+    assert eng.graph_replays - r0 >= 2
+    assert eng.launch_count - l0 == 4 * per_forward                 # kernels launched are counted the same, graph or not
+    for y in ys:
+        assert np.array_equal(y, y_eager)
+    # another x2 / y with the same x: the graph stays valid (it does not touch them)
+    x2b = x2 * 0.5
+    yb = eng.forward(x, x2b).cpu().numpy()
+    np.testing.assert_allclose(yb - 0.5 * x2.cpu().numpy(), y_eager - x2.cpu().numpy(), atol=1e-4)
+    # new weights (x 3: another power-of-two weight scale in every layer) through the same plan
+    w3 = {k: (v * 3.0 if k.endswith("conv_W") else v) for k, v in wts.items()}
+    eng.set_params(w3)
+    y3 = [eng.forward(x, x2).cpu().numpy() for _ in range(3)]
+    eng.set_option("graph", 0)
+    y3_eager = eng.forward(x, x2).cpu().numpy()
+    eng.set_option("graph", 1)
+    for y in y3:
+        assert np.array_equal(y, y3_eager)
+    assert not np.array_equal(y3_eager, y_eager)
+    eng.set_params(wts)

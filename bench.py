@@ -268,6 +268,31 @@ class Job:
             self.dist.destroy_process_group()
 
 
+def umma_isolated(device):
+    """kind::f16 tcgen05.mma throughput with operands resident in shared memory (dcscn_umma_probe, csrc/umma_probe.cuh),
+    measured in this run: the pipe's peak at N = 256 and the cost of one K = 16 slice of the three-product scheme for the
+    widths of the thin layers (a UMMA cannot go faster than its operands leave shared memory: ~40 cycles at N <= 80)."""
+    import ctypes
+    from helper import engine as E
+    lib = E.load_library()
+
+    def one(n, mode, iters=3000):
+        ms, cyc = ctypes.c_float(), ctypes.c_double()
+        if lib.dcscn_umma_probe(device, 2, n, mode, iters, ctypes.byref(ms), ctypes.byref(cyc)):
+            return None
+        prods = 3 if mode == 0 else 1
+        macs = 74 * iters * 4 * prods * 256 * n * 16
+        return {"tflops_issued": round(2 * macs / (ms.value * 1e-3) / 1e12, 1), "cycles_per_k16_slice": round(cyc.value / (iters * 4), 1)}
+    try:
+        out = {"what": "tcgen05.mma kind::f16 cta_group::2 M=256, both operands in shared memory, 74 CTA pairs, no loads / epilogue",
+               "n256_three_products": one(256, 0)}
+        for n in (48, 80, 112, 160):
+            out["n%d_three_products" % n] = one(n, 0)
+        return out
+    except Exception as e:  # noqa: BLE001
+        return {"error": "%s: %s" % (type(e).__name__, e)}
+
+
 def headline(job, args):
     import torch
     from helper import engine as E
@@ -522,12 +547,14 @@ def run_ours(args, rank, world, local_rank):
         achieved = tc_flops / (tc_ms / 1e3) / 1e12
         passes = 3 if args.precision == "f16x3" else 1
         traffic, traffic_src = ncu_traffic()
+        isolated = umma_isolated(job.local)
         roofline = {
             "bound": "tensor",
             "kernel": "conv_tc_halo2_kernel (3x3 layers) / conv_tc_pair_kernel (A1+B1): the %d tcgen05 conv launches of one step" % len(tc_names),
             "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
-            "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (%s); kind::f16 UMMAs issue at the bf16 rate, no separate "
-                           "fp16 peak was measured" % how,
+            "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (%s); kind::f16 UMMAs issue at the bf16 rate - the pipe "
+                           "measured in isolation in this run is `kind_f16_isolated`" % how,
+            "kind_f16_isolated": isolated,
             "algorithmic_flop_per_launch_set": tc_flops, "launch_set_ms": tc_ms,
             "launch_ms_method": "CUDA events around every launch on the launching stream, median of >= 5 steps",
             "mma_passes": passes, "frac_of_issued_mma": achieved * passes / sustained,

@@ -368,7 +368,7 @@ class SuperResolution:
             weights[var] = reader.get_tensor(var)
         self.engine.set_params(weights)
         self.engine.reset_optimizer()   # weights from a file never keep moments of whatever was trained before
-        if restore_optimizer and not self.depthwise_separable and reader.has_tensor("beta1_power"):
+        if restore_optimizer and reader.has_tensor("beta1_power"):
             for var in weights:
                 for slot, suffix in enumerate(("/Adam", "/Adam_1")):
                     if reader.has_tensor(var + suffix):
@@ -402,7 +402,7 @@ class SuperResolution:
             return      # data-parallel ranks hold identical weights: rank 0 writes the file
         shapes = self.engine.param_shapes()
         tensors = {var: self.engine.get_param(var) for var in shapes}
-        steps = 0 if self.depthwise_separable else self.engine.adam_step
+        steps = self.engine.adam_step
         for var, shape in shapes.items():
             for slot, suffix in enumerate(("/Adam", "/Adam_1")):
                 tensors[var + suffix] = (self.engine.get_adam_slot(var, slot) if steps > 0
@@ -451,8 +451,7 @@ class SuperResolution:
         # grid-patch data sets (--build_batch): the uint8 patch arrays move to HBM once and a mini-batch becomes an index
         # list + one gather launch per tensor (helper/engine.py: set_patch_store / train_step_indexed)
         self.batch_indices = None
-        if (isinstance(self.train, loader.BatchDataSets) and self.engine is not None and self.train.count > 0
-                and not self.depthwise_separable):
+        if isinstance(self.train, loader.BatchDataSets) and self.engine is not None and self.train.count > 0:
             if not getattr(self, "_patches_on_device", False):
                 self.engine.set_patch_store(self.train.input_images, self.train.input_interpolated_images,
                                             self.train.true_images)

@@ -59,6 +59,9 @@ struct EpiParams {
   uint32_t drop_seed;
   uint32_t drop_layer;
   int drop_ntotal;     // channel count the keep-mask index is built with (the slot width; 0 = the GEMM's padded N)
+  int store_mode;      // fp16 plane stores of the tensor-core epilogues: 0 = one 32-byte store per lane and plane (default),
+                       // 1 = two 16-byte stores (rounds 1-2), 2 = 32-byte stores with neighbouring lanes exchanging halves so
+                       // that one instruction covers 64 contiguous bytes of a pixel (streaming 3x3 kernel)
 };
 
 struct ConvGeom {
@@ -85,6 +88,7 @@ struct ConvTCParams {
   int pair_stream;       // conv_tc_pair_kernel: streaming split-accumulator mode (1x1 layers)
   unsigned long long* dbg;   // diagnostic builds (-DDCSCN_H2_DEBUG): per-cluster wait counters, else null
   int h2_nreg;           // leading chunks with one tap per stage (issued by the compile-time-structured loop)
+  int h2_probe;          // the issuing thread probes the next weight stage's barrier before each batch of UMMAs (option "h2_probe")
   EpiParams epi;
 };
 

@@ -183,6 +183,7 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
       const uint32_t sa_u32 = ptx::smem_u32(smem_a), sb_u32 = ptx::smem_u32(smem_b);
       int sa = 0, sb = 0;
       uint32_t spa = 0, spb = 0;
+      uint32_t b_ready = 0;                                 // the current weight stage was already seen complete (probe of the previous stage)
       // Accumulation slots rotate over the nbuf TMEM buffers: bd = buffer of the current dominant slot, bc = the next one;
       // bit b of `phm` = completed uses of buffer b mod 2 (mbarrier phase parity).  Plain increments and selects instead
       // of slot % nbuf keep all of it in uniform registers.
@@ -223,7 +224,11 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
             const bool seg_end = (dom >= seg_target) || (st + 3 == nst);   // same rule as build_h2_stages
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy, ++st) {
-              { H2_T0(); ptx::mbar_wait(&b_full[sb], spb); H2_ACC(w_b); }
+              if ((!resident || item == cluster_id) && !b_ready) { H2_T0(); ptx::mbar_wait(&b_full[sb], spb); H2_ACC(w_b); }   // resident stages landed during the first item
+              if (p.h2_probe && !resident) {     // look at the next stage's barrier now: the probe's latency hides behind this stage's UMMAs
+                const bool wrap = sb + 1 == num_b;
+                b_ready = ptx::mbar_test(&b_full[wrap ? 0 : sb + 1], wrap ? (spb ^ 1u) : spb);
+              }
               ptx::tc_fence_after();
               const uint32_t b_addr = sb_u32 + (uint32_t)sb * (uint32_t)B_STAGE;
               uint32_t bh = desc_lo_t<KC>(b_addr), bl = desc_lo_t<KC>(b_addr + BH_BYTES);
@@ -316,7 +321,8 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
             seg_open = false;
           }
           if (e & kH2ChunkFirst) ptx::mbar_wait(&a_full[sa], spa);  // the chunk's halo box serves all its stages
-          ptx::mbar_wait(&b_full[sb], spb);
+          if ((!resident || item == cluster_id) && !b_ready) ptx::mbar_wait(&b_full[sb], spb);
+          b_ready = 0;                                              // the table-driven tail does not probe ahead
           ptx::tc_fence_after();
           // low descriptor word (start address >> 4 | LBO) of the A slot's hi plane; slots are 1024-byte aligned
           const uint32_t a_desc0 = (((sa_u32 + (uint32_t)sa * (uint32_t)A_SLOT) & 0x3FFFFu) >> 4) | (1u << 16);
@@ -474,6 +480,65 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
               const bool last = (p.epi.rdot_parts > 1) ? (j == my_chunks - 1) : (c + 16 == p.epi.d2s_cout);
               if (last && valid) rdot_flush(p.epi, g, img, y, x, ij, p.epi.rdot_parts > 1 ? c / share : 0, v);
             }
+          }
+        }
+      } else if (p.epi.store_mode == 2 && p.epi.mode == EPI_PLANES && p.epi.num_seg == 1 && p.epi.seg[0].dst_zneg == nullptr) {
+        // Lane-pair stores.  Lanes 2k and 2k + 1 hold two horizontally adjacent pixels; for every PAIR of 16-column chunks
+        // they swap halves, so that one store instruction writes chunk j (even lane) and chunk j + 1 (odd lane) of the SAME
+        // pixel - 64 contiguous bytes, one 128-byte line per two lanes instead of one per lane.  All lanes take part in the
+        // shuffles; stores are predicated on the pixel they write.
+        const EpiSegment sg = p.epi.seg[0];
+        const bool odd = (lane & 1) != 0;
+        const bool pvalid = __shfl_xor_sync(0xffffffffu, valid ? 1 : 0, 1) != 0;
+        const bool valid_e = odd ? pvalid : valid, valid_o = odd ? valid : pvalid;   // the pair's even / odd pixel
+        const size_t pix = (size_t)((size_t)img * g.H + y) * g.W + x;
+        const size_t pix_e = odd ? pix - 1 : pix, pix_o = odd ? pix : pix + 1;
+        // (training forwards, which also store min(z, 0), take the per-lane path below)
+#pragma unroll
+        for (int j = 0; j < kMaxColChunks; j += 2) {
+          if (j + 1 < my_chunks) {
+            const int cg0 = n_tile * p.n_pad + col_base + j * 16;
+            float v0[16], v1[16];
+            uint32_t zdummy[8];
+            epilogue_values16(p.epi, g, n_total, img, y, x, cg0, sum[j], v0, zdummy, false);
+            epilogue_values16(p.epi, g, n_total, img, y, x, cg0 + 16, sum[j + 1], v1, zdummy, false);
+            const int colA = (cg0 - sg.col_begin) + (odd ? 16 : 0);        // this lane's column in both stores
+            const size_t offA = pix_e * sg.pitch + colA, offB = pix_o * sg.pitch + colA;
+            if (cg0 >= sg.col_begin && cg0 + 16 < sg.col_end) {
+              // one plane at a time (hi, then lo) keeps the live registers of the exchange small
+#pragma unroll
+              for (int pln = 0; pln < 2; ++pln) {
+                __half* dstp = pln == 0 ? sg.dst_hi : sg.dst_lo;
+                if (dstp == nullptr) continue;
+                uint32_t w0[8], w1[8];                                      // this plane's packed words of chunk j / j + 1
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  __half ha, la, hb, lb;
+                  split_f16(v0[2 * i], ha, la);
+                  split_f16(v0[2 * i + 1], hb, lb);
+                  w0[i] = pln == 0 ? pack_h2(ha, hb) : pack_h2(la, lb);
+                  split_f16(v1[2 * i], ha, la);
+                  split_f16(v1[2 * i + 1], hb, lb);
+                  w1[i] = pln == 0 ? pack_h2(ha, hb) : pack_h2(la, lb);
+                }
+                // even lane: keeps chunk j, sends chunk j + 1, receives the odd pixel's chunk j;
+                // odd lane:  keeps chunk j + 1, sends chunk j, receives the even pixel's chunk j + 1
+                uint32_t wa[8], wb[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const uint32_t r = __shfl_xor_sync(0xffffffffu, odd ? w0[i] : w1[i], 1);
+                  wa[i] = odd ? r : w0[i];        // the even pixel: own chunk j (even lane) | received chunk j + 1 (odd lane)
+                  wb[i] = odd ? w1[i] : r;        // the odd pixel: received chunk j (even lane) | own chunk j + 1 (odd lane)
+                }
+                if (valid_e) stg256(dstp + offA, wa);
+                if (valid_o) stg256(dstp + offB, wb);
+              }
+            } else if (valid) {                  // a pair that straddles the segment's end: plain per-lane stores
+              epilogue_store16(p.epi, g, n_total, img, y, x, cg0, sum[j]);
+              epilogue_store16(p.epi, g, n_total, img, y, x, cg0 + 16, sum[j + 1]);
+            }
+          } else if (j < my_chunks && valid) {
+            epilogue_store16(p.epi, g, n_total, img, y, x, n_tile * p.n_pad + col_base + j * 16, sum[j]);
           }
         }
       } else if (valid) {

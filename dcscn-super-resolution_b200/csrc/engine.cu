@@ -28,6 +28,7 @@
 #include "conv_ds_tile.cuh"
 #include "train.cuh"
 #include "wgrad_tc.cuh"
+#include "train_ds.cuh"
 #include "umma_probe.cuh"
 
 using namespace dcscn;
@@ -242,6 +243,9 @@ struct dcscn_handle {
 
   std::vector<std::unique_ptr<Plan>> plans;
   Plan* last_plan = nullptr;
+  int gather_impl = 0;               // option "gather_impl": 0 = four pixels per thread when the shape allows, 1 = generic kernel
+  int h2_probe = 1;                  // option "h2_probe": streaming 3x3 kernel probes the next weight stage's barrier ahead of the UMMAs
+  int store_mode = 2;                // option "store_mode": EpiParams::store_mode of every tensor-core launch
   int use_graph = 1;                 // option "graph": replay the per-(n,h,w) launch sequence of a forward as one CUDA graph
   uint64_t graph_epoch = 1;          // bumped by everything a captured launch bakes in (options, weight re-packs)
   cudaStream_t cap_stream = nullptr; // capture happens on a private stream (the caller's may be the legacy default stream)
@@ -1463,6 +1467,7 @@ static int launch_tc_halo2(dcscn_handle* h, const TcLaunch& L, cudaStream_t st) 
   p.g = L.hg;
   p.cluster_size = 2;
   p.seg_chunks = L.halo2_seg;
+  p.h2_probe = h->h2_probe;
 #ifdef DCSCN_H2_DEBUG
   {  // diagnostic build: one counter block per launch, dumped by h2_debug_dump() (scripts/r2_h2_timeline.sh)
     static unsigned long long* d_dbg = nullptr;
@@ -1494,6 +1499,7 @@ static int launch_tc(dcscn_handle* h, const TcLaunch& Lc, cudaStream_t st) {
     const std::vector<TcLayer>& ls = L.layer_bwd ? h->bwd : h->tcl;
     if (L.layer_index < (int)ls.size()) L.p.epi.out_scale = 1.0f / ls[L.layer_index].wscale;
   }
+  L.p.epi.store_mode = h->store_mode;
   if (h->conv_impl == 1) {
     const long long total = (long long)L.ref.g.n_img * L.ref.g.H * L.ref.g.W * (L.ref.n_total_pad >> 4);
     const int grid = (int)std::min<long long>((total + 127) / 128, (long long)h->sm_count * 16);
@@ -1813,8 +1819,14 @@ static int forward_impl(dcscn_handle* h, const float* x, const float* x2, float*
     p.x2 = x2;
     p.y = y;
     const size_t total = (size_t)p.n_img * p.H * p.W;
-    const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)h->sm_count * 16);
-    conv_last_gather_kernel<<<grid, 256, 0, st>>>(p);
+    const bool vec4 = p.ksz == 3 && (p.W & 3) == 0 && ((reinterpret_cast<uintptr_t>(x2) | reinterpret_cast<uintptr_t>(y)) & 15) == 0 && h->gather_impl == 0;
+    if (vec4) {
+      const int grid = (int)std::min<size_t>((total / 4 + 255) / 256, (size_t)h->sm_count * 16);
+      conv_last_gather4_kernel<<<grid, 256, 0, st>>>(p);
+    } else {
+      const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)h->sm_count * 16);
+      conv_last_gather_kernel<<<grid, 256, 0, st>>>(p);
+    }
     CUDA_TRY(cudaGetLastError());
     h->launches++;
     if (mark(h, st)) return 1;
@@ -1917,6 +1929,7 @@ static int pil_resize_impl(dcscn_handle* h, const float* src, float* dst, int n,
 }
 
 #include "train_engine.inc"
+#include "train_ds.inc"
 
 // --------------------------------------------------------------------------------------- C ABI ----
 extern "C" {
@@ -2249,6 +2262,19 @@ int dcscn_set_option(dcscn_handle* h, const char* key, int64_t value) {
     h->use_graph = value ? 1 : 0;
     return 0;
   }
+  if (k == "gather_impl") {
+    h->gather_impl = value ? 1 : 0;
+    return 0;
+  }
+  if (k == "h2_probe") {
+    h->h2_probe = value ? 1 : 0;
+    return 0;
+  }
+  if (k == "store_mode") {
+    if (value < 0 || value > 2) return fail("store_mode must be 0 (32-byte stores), 1 (16-byte stores) or 2 (lane-pair 64-byte runs)");
+    h->store_mode = (int)value;
+    return 0;
+  }
   if (k == "conv_impl") {
     if (value != 0 && value != 1) return fail("conv_impl must be 0 (tcgen05) or 1 (CUDA-core validation)");
     h->conv_impl = (int)value;
@@ -2558,6 +2584,10 @@ int dcscn_dropout_mask(dcscn_handle* h, const char* tensor, uint32_t seed, int n
   } else if (t == "B1") { C = c.nin_filters2; n_total = h->a1_w + h->b1_w; col0 = h->a1_w; layer = (uint32_t)(L + 1);
   } else if (t == "B2") { C = c.nin_filters2; n_total = h->b1_w; col0 = 0; layer = (uint32_t)(L + 2);
   } else return fail("dcscn_dropout_mask: tensor '%s' has no dropout", tensor);
+  if (c.depthwise_separable) {   // train_ds.inc: dense [pixel][channel] indexing, A1 / B2 / B1 are layers L+1 / L+2 / L+3
+    n_total = C; col0 = 0;
+    if (t == "B1") layer = (uint32_t)(L + 3);
+  }
   const size_t px = (size_t)n * height * width;
   if (numel != (int64_t)(px * C)) return fail("dcscn_dropout_mask: expected %lld elements", (long long)(px * C));
   for (size_t q = 0; q < px; ++q)

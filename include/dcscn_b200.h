@@ -174,6 +174,12 @@ int dcscn_get_activation(dcscn_handle* h, const char* tensor, float* host_data, 
  *          "cluster" 1 | 2 | 4 = CTAs per cluster multicasting weight tiles in the single-CTA kernel (default 1);
  *          "fuse_last" 1 | 0 = compute the per-pixel half of R-CNN1 inside the last Up-PS epilogue (default 1);
  *          "timing" 0 | 1 = record per-launch CUDA events (see dcscn_get_timings);
+ *          "store_mode" 2 | 0 | 1 = fp16 plane stores of the tensor-core epilogues: 32-byte stores with neighbouring lanes
+ *          exchanging halves so that each instruction writes 64 contiguous bytes of a pixel (default; streaming 3x3 kernel,
+ *          elsewhere like 0), one 32-byte store per lane and plane, or two 16-byte stores (the round-1/2 form, cross-check);
+ *          "h2_probe" 1 | 0 = the issuing thread of the streaming 3x3 kernel probes the next weight stage's barrier before
+ *          it issues a stage's UMMAs (hides the barrier round trip), or waits stage by stage;
+ *          "gather_impl" 0 | 1 = R-CNN1 gather with four pixels per thread (default where W % 4 == 0) or the generic kernel;
  *          "graph" 1 | 0 = replay the launches of a forward (all but the last kernel) as one CUDA graph per (n, h, w) once
  *          the same input pointer has been seen twice in a row (default 1; off while "timing" = 1 or "conv_impl" = 1);
  *          "l1_loss" 0 | 1 = image_loss of the train step is mean |y_ - y| instead of the MSE (--use_l1_loss,

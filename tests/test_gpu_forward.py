@@ -317,3 +317,26 @@ def test_cuda_graph_replay_is_bit_identical_and_follows_weight_updates(small):
         assert np.array_equal(y, y3_eager)
     assert not np.array_equal(y3_eager, y_eager)
     eng.set_params(wts)
+
+
+def test_store_modes_write_identical_planes(small):
+    """Option "store_mode": 32-byte stores (default), the 16-byte stores of rounds 1-2, and the lane-pair form (neighbouring
+    lanes exchange halves of a chunk pair) must leave bit-identical activations and outputs; shapes with odd widths and
+    partial tiles exercise the lane-pair predication."""
+    cfg, wts, eng = small
+    for n, h, w in [(2, 48, 48), (1, 17, 9), (1, 3, 130), (1, 1, 1)]:
+        g = np.random.RandomState(h * 7 + w)
+        x = (g.rand(n, h, w, 1) * 255).astype(np.float32)
+        x2 = (g.rand(n, 2 * h, 2 * w, 1) * 255).astype(np.float32)
+        ref, ref_act = None, None
+        for mode in (1, 0, 2):
+            eng.set_option("store_mode", mode)
+            y = gpu_forward(eng, x, x2)
+            act = {name: eng.get_activation(name, (n, h, w, c)) for name, c in (("CNN1", 40), ("CNN3", 27), ("A1", 24), ("B2", 16))}
+            if ref is None:
+                ref, ref_act = y, act
+            else:
+                assert np.array_equal(y, ref), (mode, n, h, w)
+                for k in act:
+                    assert np.array_equal(act[k], ref_act[k]), (mode, k)
+        eng.set_option("store_mode", 0)

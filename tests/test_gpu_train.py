@@ -252,3 +252,76 @@ def test_l1_loss_gradients_match_oracle():
         g = eng.get_grad(name)
         assert np.abs(g - gref).max() <= 2e-3 * np.abs(gref).max() + 1e-7, name
     eng.close()
+
+
+# ---------------------------------------------------------------- depthwise-separable graphs (tf_graph.py:155-216) ----
+DS2 = dict(scale=2, layers=3, filters=12, min_filters=6, filters_decay_gamma=1.5, nin_filters=10, nin_filters2=6,
+           pixel_shuffler_filters=1, depthwise_separable=True)
+DS4 = dict(scale=4, layers=4, filters=14, min_filters=5, filters_decay_gamma=1.2, nin_filters=9, nin_filters2=7,
+           pixel_shuffler_filters=1, depthwise_separable=True)
+DS4W = dict(scale=4, layers=3, filters=10, min_filters=6, filters_decay_gamma=1.5, nin_filters=8, nin_filters2=4,
+            pixel_shuffler_filters=0, depthwise_separable=True)    # pixel shuffler keeps all 12 channels: R-CNN1 12 -> 1
+
+
+@pytest.mark.parametrize("kw,keep,shape", [(DS2, 1.0, (2, 9, 7)), (DS2, 0.8, (2, 12, 10)), (DS4, 0.8, (2, 8, 11)),
+                                           (DS4, 1.0, (1, 1, 1)), (DS4W, 0.8, (1, 6, 5))],
+                         ids=["ds-x2-nodrop", "ds-x2-drop", "ds-x4-drop", "ds-x4-1x1", "ds-x4-wide"])
+def test_depthwise_separable_gradients_match_oracle(kw, keep, shape):
+    """The train step of --depthwise_separable graphs: loss, mse and EVERY gradient (depthwise_W, pointwise_W, conv_B, PReLU
+    slopes, and the dead conv_W whose only gradient is its L2 decay, tf_graph.py:183,212) against fp64 autograd with
+    the engine's dropout masks replayed.  All mismatches are reported at once."""
+    n, h, w = shape
+    cfg, wts, eng, x, x2, y = setup(kw, keep, n, h, w, seed=5)
+    seed = 4321
+    loss, mse = eng.train_step_host(x, x2, y, lr=0.002, seed=seed, apply_update=False)
+    orc = O.Oracle(cfg, wts, torch.float64)
+    masks = oracle_masks(eng, cfg, seed, n, h, w) if keep < 1.0 else None
+    mse_ref, loss_ref, grads_ref = orc.loss_and_grads(x.astype(np.float64), x2.astype(np.float64), y.astype(np.float64),
+                                                      keep_prob=keep, masks=masks)
+    bad = []
+    if not mse == pytest.approx(mse_ref, rel=2e-5):
+        bad.append(("mse", mse, mse_ref))
+    for name, gref in grads_ref.items():
+        g = eng.get_grad(name)
+        tol = 2e-4 * np.abs(gref).max() + 1e-7
+        err = float(np.abs(g - gref).max())
+        if not err <= tol:
+            bad.append((name, err, float(np.abs(gref).max())))
+    assert not bad, bad
+    # the dead variable: gradient = l2_decay * conv_W exactly
+    np.testing.assert_allclose(eng.get_grad("CNN2/conv_W"), cfg.l2_decay * wts["CNN2/conv_W"], rtol=1e-6, atol=1e-12)
+    norm_ref = np.sqrt(sum(np.sum(v ** 2) for v in grads_ref.values()))
+    assert eng.last_grad_norm == pytest.approx(norm_ref, rel=1e-3)
+    eng.close()
+
+
+def test_depthwise_separable_adam_steps_and_forward_follow():
+    """Three optimizer steps of a depthwise-separable graph against the oracle's clip + TF-Adam, then the inference
+    kernels (which hold their own filter copies) must see the updated weights, and the loss must go down."""
+    n, h, w = 2, 12, 12
+    cfg, wts, eng, x, x2, y = setup(DS4, 0.8, n, h, w, seed=9)
+    orc = O.Oracle(cfg, wts, torch.float64)
+    m = {k: np.zeros_like(v) for k, v in wts.items()}
+    v = {k: np.zeros_like(v_) for k, v_ in wts.items()}
+    slack = {k: np.zeros_like(v_) for k, v_ in wts.items()}
+    first = None
+    for step in range(1, 4):
+        seed = 300 + step
+        loss, mse = eng.train_step_host(x, x2, y, lr=0.002, seed=seed)
+        first = mse if first is None else first
+        masks = oracle_masks(eng, cfg, seed, n, h, w)
+        _, _, grads = orc.loss_and_grads(x.astype(np.float64), x2.astype(np.float64), y.astype(np.float64), keep_prob=0.8, masks=masks)
+        clipped, _ = orc.clip_by_global_norm(grads)
+        orc.adam_step(clipped, m, v, step, 0.002)
+        for name in wts:
+            delta = 2e-4 * np.abs(grads[name]).max()
+            slack[name] += np.minimum(2.0, 3.0 * delta / (np.abs(grads[name]) + 1e-300))
+            tol = 2e-3 * 0.002 * step + 0.002 * slack[name]
+            got = eng.get_param(name)
+            assert (np.abs(got - orc.w[name]) <= tol).all(), (step, name, float((np.abs(got - orc.w[name]) - tol).max()))
+    yy = eng.forward_host(x, x2)
+    ref = O.Oracle(cfg, {k: a.astype(np.float64) for k, a in orc.w.items()}, torch.float64).forward(x.astype(np.float64), x2.astype(np.float64))
+    assert np.abs(yy - ref).max() <= 5e-3
+    more = [eng.train_step_host(x, x2, y, lr=0.002, seed=400 + i)[1] for i in range(40)]
+    assert np.mean(more[-5:]) < first
+    eng.close()

@@ -45,10 +45,15 @@ constexpr int kDtS = 24;                 // shared-memory row stride in pixels (
 constexpr int kDtCC = 32;                // channels per staged chunk
 constexpr int kDtCP = 33;                // channel pitch of a staged pixel (odd: pixel index = bank offset)
 
+// Layers with several column groups (cout > 32: the pixel shufflers) and a single input chunk keep each thread's depthwise
+// values in a private shared-memory row after the first group instead of recomputing them (9 + 9 shared loads per value).
+inline bool ds_tile_caches_depthwise(int ksz, int cin, int cout) { return ksz == 3 && cout > 32 && cin <= kDtCC; }
+
 inline size_t ds_tile_smem_bytes(int ksz, int cin, int cout) {
   const int cols = cout < 32 ? ((cout + 3) & ~3) : 32;
   const size_t in_px = ksz == 3 ? (size_t)(kDtT + 2) * kDtS : (size_t)kDtThreads;
-  return (in_px * kDtCP + (size_t)cin * cols + (size_t)ksz * ksz * cin) * sizeof(float);
+  const size_t cache = ds_tile_caches_depthwise(ksz, cin, cout) ? (size_t)kDtThreads * kDtCP : 0;
+  return (in_px * kDtCP + (size_t)cin * cols + (size_t)ksz * ksz * cin + cache) * sizeof(float);
 }
 
 template <int KSZ, int CG4>
@@ -61,6 +66,8 @@ __global__ void __launch_bounds__(kDtThreads) ds_tile_kernel(const DsTileParams 
   float* s_pw = s_in + IN_PX * kDtCP;                              // [cin][COLS]  (current column group)
   float* s_dw = s_pw + p.cin * COLS;                               // [kk][cin]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool cache_u = KSZ == 3 && p.cout > COLS && p.cin <= kDtCC;  // == ds_tile_caches_depthwise (COLS is 32 whenever cout > 32)
+  float* s_u = s_dw + kk * p.cin + tid * kDtCP;                    // this thread's depthwise values [<= 32] (odd pitch: no bank conflicts)
 
   // ---- which pixels ----
   int img, y, x, hp0;                                              // hp0: this thread's centre pixel in the staged tile
@@ -167,10 +174,15 @@ __global__ void __launch_bounds__(kDtThreads) ds_tile_kernel(const DsTileParams 
       for (int c = 0; c < cc; ++c) {
         float d;
         if (KSZ == 3) {
-          d = 0.f;
+          if (cache_u && cg > 0) {
+            d = s_u[c];
+          } else {
+            d = 0.f;
 #pragma unroll
-          for (int t = 0; t < 9; ++t)
-            d = fmaf(sp[((t / 3 - 1) * kDtS + (t % 3 - 1)) * kDtCP + c], s_dw[t * p.cin + c0 + c], d);
+            for (int t = 0; t < 9; ++t)
+              d = fmaf(sp[((t / 3 - 1) * kDtS + (t % 3 - 1)) * kDtCP + c], s_dw[t * p.cin + c0 + c], d);
+            if (cache_u) s_u[c] = d;
+          }
         } else {
           d = sp[c] * s_dw[c0 + c];
         }

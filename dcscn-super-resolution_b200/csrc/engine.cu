@@ -244,7 +244,10 @@ struct dcscn_handle {
   std::vector<std::unique_ptr<Plan>> plans;
   Plan* last_plan = nullptr;
   int gather_impl = 0;               // option "gather_impl": 0 = four pixels per thread when the shape allows, 1 = generic kernel
-  int h2_probe = 1;                  // option "h2_probe": streaming 3x3 kernel probes the next weight stage's barrier ahead of the UMMAs
+  int rdot_const = 0;                // option "rdot_const": fused R-CNN1 epilogue reads its filter from the constant bank
+  RdotConst rdot_host;               // launch-time copy of R-CNN1/conv_W for that option
+  int wide_tiles = 0;                // option "wide_tiles": streaming 3x3 kernel with column tiles up to 256 (two TMEM buffers above 160)
+  int h2_probe = 0;                  // option "h2_probe": streaming 3x3 kernel probes the next weight stage's barrier ahead of the UMMAs
   int store_mode = 2;                // option "store_mode": EpiParams::store_mode of every tensor-core launch
   int use_graph = 1;                 // option "graph": replay the per-(n,h,w) launch sequence of a forward as one CUDA graph
   uint64_t graph_epoch = 1;          // bumped by everything a captured launch bakes in (options, weight re-packs)
@@ -426,6 +429,7 @@ static void choose_tiling(int n_total_pad16, int* n_tiles, int* n_pad, int cap =
 // Values (unscaled fp32) of the CTA-pair operand image of a layer, one per hi-plane element, in image order:
 // [n_tile][tap][chunk][rank][n_pad/2 rows x 64 halves], each row 128-byte swizzled (16-byte chunk j of row r at j ^ (r & 7)).
 static int tile_cap(const dcscn_handle* h, int ksz);
+static bool streaming3x3(const dcscn_handle* h);
 
 // Weight-stage table of the streaming 3x3 kernel (see conv_tc_halo2.cuh): full 64-channel chunks take one stage per tap,
 // a last chunk with 16 / 32 valid channels packs 4 / 2 taps per stage.  `seg_units` = promotion period in units of 12
@@ -602,7 +606,7 @@ static int pack_tc_layer(dcscn_handle* h, TcLayer& t) {
   t.has_pair = false;
   t.h2_stages.clear();
   t.h2_nseg = 0;
-  if (need_pair && t.ksz == 3 && tile_cap(h, 3) < 256 && 3 * t.n_pad <= 512) {   // streaming kernel: stage-ordered image
+  if (need_pair && t.ksz == 3 && streaming3x3(h) && (h->wide_tiles ? 2 : 3) * t.n_pad <= 512) {   // streaming kernel: stage-ordered image
     // Promotion period in (chunk, dx) units of K = 192.  Measured (gpurun_out/seg15.log): with three TMEM buffers
     // (n_pad >= 144) a period of 1 leaves the epilogue one segment (~1.5 us) to drain a slot and the issuer stalls -
     // CNN3 0.85 -> 0.63 ms, CNN4 0.74 -> 0.52 ms at 4; the noise-tile error is flat in this range (1.2-1.35e-3).
@@ -658,8 +662,13 @@ static int pack_tc_layer(dcscn_handle* h, TcLayer& t) {
 }
 
 // Column-tile cap of a layer: the streaming 3x3 kernel rotates three TMEM buffers of n_pad columns (3 * n_pad <= 512).
+static bool streaming3x3(const dcscn_handle* h) { return h->halo == 3 && h->pair && h->kc == 64 && h->sm_count % 2 == 0; }
+// Column-tile cap of the streaming 3x3 kernel: 160 keeps three TMEM buffers (3 * n_pad <= 512).  Option "wide_tiles" lifts
+// it to 256: layers wider than 160 columns then run with TWO buffers (the issuer waits for a drain at every segment end)
+// but read every A box once per pixel tile instead of once per column tile - CNN2 is one tile of 176 columns instead of
+// 2 x 96, Up-PS 2 x 192 instead of 4 x 96.
 static int tile_cap(const dcscn_handle* h, int ksz) {
-  return (ksz == 3 && h->halo == 3 && h->pair && h->kc == 64 && h->sm_count % 2 == 0) ? 160 : 256;
+  return (ksz == 3 && streaming3x3(h)) ? (h->wide_tiles ? 256 : 160) : 256;
 }
 
 static TcLayer make_tc(const dcscn_handle* h, const std::string& name, int ksz, int cin, int cout_cols, int cin_pad,
@@ -672,7 +681,7 @@ static TcLayer make_tc(const dcscn_handle* h, const std::string& name, int ksz, 
   t.cout = cout_cols;
   t.cin_pad = cin_pad;
   choose_tiling(pad16(cout_cols), &t.n_tiles, &t.n_pad, cap);
-  if (tile_unit > 0 && cap < 256 && t.n_tiles > 1 && tile_unit % 16 == 0 && tile_unit <= cap && cout_cols % tile_unit == 0) {
+  if (tile_unit > 0 && cap < 256 && ksz == 3 && streaming3x3(h) && t.n_tiles > 1 && tile_unit % 16 == 0 && tile_unit <= cap && cout_cols % tile_unit == 0) {
     t.n_pad = tile_unit;               // pixel-shuffler layers: one column tile per sub-pixel (fused R-CNN1 epilogue)
     t.n_tiles = cout_cols / tile_unit;
   }
@@ -1485,8 +1494,20 @@ static int launch_tc_halo2(dcscn_handle* h, const TcLaunch& L, cudaStream_t st) 
   }
 #endif
   const bool wide = h->wmap_wide && L.has_wide;
+  static const RdotConst zero_rc = {};
+  const RdotConst* rc = &zero_rc;
+  p.epi.rdot_const = 0;
+  if (h->rdot_const && p.epi.mode == EPI_D2S_RDOT && p.epi.rdot_taps * p.epi.d2s_cout <= 9 * 128) {
+    if (sync_host_params(h)) return 1;            // after device-side optimizer steps the host copy of R-CNN1/conv_W is refreshed first
+    const std::vector<float>& W = h->params[h->param_index.at("R-CNN1/conv_W")].host;   // [k,k,C,1] == [taps][C]
+    if ((int)W.size() == p.epi.rdot_taps * p.epi.d2s_cout) {
+      memcpy(h->rdot_host.w, W.data(), W.size() * sizeof(float));
+      rc = &h->rdot_host;
+      p.epi.rdot_const = 1;
+    }
+  }
   CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc_halo2_kernel<NPL>, L.t1_hi, L.t1_lo, wide ? L.tm_w_wide : L.tm_w, p, L.halo2_na,
-                              L.halo2_nb, wide ? 1 : 0));
+                              L.halo2_nb, wide ? 1 : 0, *rc));
   return 0;
 }
 
@@ -1595,7 +1616,8 @@ static int launch_ds_tile(dcscn_handle* h, DsTileParams p, int ksz, cudaStream_t
   // the kernel's shared-memory carve-up uses the per-pass column count of the instantiated template
   const int tcols = cols <= 4 ? 4 : cols <= 8 ? 8 : cols <= 16 ? 16 : cols <= 24 ? 24 : 32;
   const size_t in_px = ksz == 3 ? (size_t)(kDtT + 2) * kDtS : (size_t)kDtThreads;
-  const size_t smem = (in_px * kDtCP + (size_t)p.cin * tcols + (size_t)ksz * ksz * p.cin) * sizeof(float);
+  const size_t cache = ds_tile_caches_depthwise(ksz, p.cin, p.cout) ? (size_t)kDtThreads * kDtCP : 0;   // private depthwise rows
+  const size_t smem = (in_px * kDtCP + (size_t)p.cin * tcols + (size_t)ksz * ksz * p.cin + cache) * sizeof(float);
   if (smem > 200 * 1024) return fail("depthwise-separable layer %d -> %d exceeds the kernel's shared memory", p.cin, p.cout);
   unsigned grid;
   if (ksz == 3) {
@@ -2264,6 +2286,20 @@ int dcscn_set_option(dcscn_handle* h, const char* key, int64_t value) {
   }
   if (k == "gather_impl") {
     h->gather_impl = value ? 1 : 0;
+    return 0;
+  }
+  if (k == "rdot_const") {
+    h->rdot_const = value ? 1 : 0;
+    return 0;
+  }
+  if (k == "wide_tiles") {
+    if (h->wide_tiles != (value ? 1 : 0)) {
+      h->wide_tiles = value ? 1 : 0;
+      h->params_dirty = true;               // other column tiles: re-tile and re-pack
+      h->cap_px = 0;                        // the fused R-CNN1 partial planes change size
+      h->plans.clear();
+      h->last_plan = nullptr;
+    }
     return 0;
   }
   if (k == "h2_probe") {

@@ -59,7 +59,6 @@ struct EpiParams {
   uint32_t drop_seed;
   uint32_t drop_layer;
   int drop_ntotal;     // channel count the keep-mask index is built with (the slot width; 0 = the GEMM's padded N)
-  int rdot_const;      // EPI_D2S_RDOT: read the R-CNN1 filter from the kernel-parameter copy (constant cache), not shared memory
   int store_mode;      // fp16 plane stores of the tensor-core epilogues: 0 = one 32-byte store per lane and plane (default),
                        // 1 = two 16-byte stores (rounds 1-2), 2 = 32-byte stores with neighbouring lanes exchanging halves so
                        // that one instruction covers 64 contiguous bytes of a pixel (streaming 3x3 kernel)

@@ -37,6 +37,7 @@ struct DsTileParams {
   int d2s_r, d2s_cout;       // depth_to_space scatter (DCR) into dst [N, r*H, r*W, dst_pitch]
   const float* add;          // + x2 on channel 0 (cout == 1)
   int tiles_x, tiles_y;      // 3x3: 16 x 16 tiles per image
+  int cache_u;               // keep the depthwise values of a thread across column groups (host: ds_tile_caches_depthwise)
 };
 
 constexpr int kDtThreads = 256;
@@ -66,7 +67,7 @@ __global__ void __launch_bounds__(kDtThreads) ds_tile_kernel(const DsTileParams 
   float* s_pw = s_in + IN_PX * kDtCP;                              // [cin][COLS]  (current column group)
   float* s_dw = s_pw + p.cin * COLS;                               // [kk][cin]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const bool cache_u = KSZ == 3 && p.cout > COLS && p.cin <= kDtCC;  // == ds_tile_caches_depthwise (COLS is 32 whenever cout > 32)
+  const bool cache_u = KSZ == 3 && p.cache_u != 0 && p.cout > COLS && p.cin <= kDtCC;
   float* s_u = s_dw + kk * p.cin + tid * kDtCP;                    // this thread's depthwise values [<= 32] (odd pitch: no bank conflicts)
 
   // ---- which pixels ----

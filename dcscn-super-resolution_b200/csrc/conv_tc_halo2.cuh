@@ -52,15 +52,11 @@ __host__ __device__ inline size_t tc_halo2_misc_bytes() { return 1024 + kH2BarBy
 #define H2_ACC(var)
 #endif
 
-// R-CNN1's filter [taps][channels] as a kernel parameter (constant bank): with option "rdot_const" the fused R-CNN1 epilogue
-// reads its weights through the constant cache instead of shared memory, whose bandwidth the UMMA operand reads already use up.
-struct RdotConst { float w[9 * 128]; };
-
 template <int NPLANES>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
                      const __grid_constant__ CUtensorMap tm_w, const ConvTCParams p, const int num_a, const int num_b,
-                     const int wide_w, const __grid_constant__ RdotConst rc) {
+                     const int wide_w) {
   constexpr int KC = 64;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -481,8 +477,7 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
             const int cg = n_tile * p.n_pad + col_base + j * 16;
             if (cg < p.epi.n_valid) {
               const int ij = cg / p.epi.d2s_cout, c = cg - ij * p.epi.d2s_cout;
-              if (p.epi.rdot_const) rdot_accumulate16(p.epi, rc.w, cg, c, sum[j], v);
-              else rdot_accumulate16(p.epi, s_rdot, cg, c, sum[j], v);
+              rdot_accumulate16(p.epi, s_rdot, cg, c, sum[j], v);
               // flush when this thread has seen its whole part of the sub-pixel (all of it when rdot_parts == 1)
               const bool last = (p.epi.rdot_parts > 1) ? (j == my_chunks - 1) : (c + 16 == p.epi.d2s_cout);
               if (last && valid) rdot_flush(p.epi, g, img, y, x, ij, p.epi.rdot_parts > 1 ? c / share : 0, v);

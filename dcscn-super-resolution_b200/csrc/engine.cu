@@ -236,6 +236,7 @@ struct dcscn_handle {
   std::vector<DsDev> ds;             // same order as `layers`
   DsDev ds_ab;                       // fused A1 | B1 1x1 layer of the tile kernels: [concat positions][A1 cols | B1 cols], scales folded
   int ds_impl = 0;                   // 0 = tile kernels (conv_ds_tile.cuh), 1 = first-generation kernels (cross-check)
+  int ds_cache = 1;                  // option "ds_cache": pixel-shuffler layers keep their depthwise values across column groups
   float *ds_feat = nullptr, *ds_b1 = nullptr, *ds_nin = nullptr, *ds_mid = nullptr, *ds_hr = nullptr;
   int ds_total = 0;                  // channels of the (unpadded) concat buffer
   int ds_n = 0, ds_h = 0, ds_w = 0;  // geometry of the last DS forward
@@ -244,9 +245,7 @@ struct dcscn_handle {
   std::vector<std::unique_ptr<Plan>> plans;
   Plan* last_plan = nullptr;
   int gather_impl = 0;               // option "gather_impl": 0 = four pixels per thread when the shape allows, 1 = generic kernel
-  int rdot_const = 0;                // option "rdot_const": fused R-CNN1 epilogue reads its filter from the constant bank
-  RdotConst rdot_host;               // launch-time copy of R-CNN1/conv_W for that option
-  int wide_tiles = 0;                // option "wide_tiles": streaming 3x3 kernel with column tiles up to 256 (two TMEM buffers above 160)
+  int wide_tiles = 1;                // option "wide_tiles": streaming 3x3 kernel with column tiles up to 256 (two TMEM buffers above 160)
   int h2_probe = 0;                  // option "h2_probe": streaming 3x3 kernel probes the next weight stage's barrier ahead of the UMMAs
   int store_mode = 2;                // option "store_mode": EpiParams::store_mode of every tensor-core launch
   int use_graph = 1;                 // option "graph": replay the per-(n,h,w) launch sequence of a forward as one CUDA graph
@@ -610,7 +609,9 @@ static int pack_tc_layer(dcscn_handle* h, TcLayer& t) {
     // Promotion period in (chunk, dx) units of K = 192.  Measured (gpurun_out/seg15.log): with three TMEM buffers
     // (n_pad >= 144) a period of 1 leaves the epilogue one segment (~1.5 us) to drain a slot and the issuer stalls -
     // CNN3 0.85 -> 0.63 ms, CNN4 0.74 -> 0.52 ms at 4; the noise-tile error is flat in this range (1.2-1.35e-3).
-    const int seg = seg_override(t.name, h->seg_chunks > 0 ? h->seg_chunks : (t.n_pad >= 144 ? 4 : 3));
+    // Two-buffer tiles (3 * n_pad > 512, option "wide_tiles") keep the period of the narrow tiles they replace: CNN2's
+    // K = 1872 is the layer most sensitive to it (4 units: 1.84e-3 on the noise tiles, 3 units: identical planes to 2 x 96).
+    const int seg = seg_override(t.name, h->seg_chunks > 0 ? h->seg_chunks : ((t.n_pad >= 144 && 3 * t.n_pad <= 512) ? 4 : 3));
     t.h2_seg_units = seg;
     build_h2_stages(t.cin_pad, seg, t.h2_stages, &t.h2_nseg, &t.h2_nreg);
     if ((int)t.h2_stages.size() / 2 > kH2MaxTable) return fail("layer %s: %zu weight stages exceed the kernel's table", t.name.c_str(), t.h2_stages.size());
@@ -1494,20 +1495,8 @@ static int launch_tc_halo2(dcscn_handle* h, const TcLaunch& L, cudaStream_t st) 
   }
 #endif
   const bool wide = h->wmap_wide && L.has_wide;
-  static const RdotConst zero_rc = {};
-  const RdotConst* rc = &zero_rc;
-  p.epi.rdot_const = 0;
-  if (h->rdot_const && p.epi.mode == EPI_D2S_RDOT && p.epi.rdot_taps * p.epi.d2s_cout <= 9 * 128) {
-    if (sync_host_params(h)) return 1;            // after device-side optimizer steps the host copy of R-CNN1/conv_W is refreshed first
-    const std::vector<float>& W = h->params[h->param_index.at("R-CNN1/conv_W")].host;   // [k,k,C,1] == [taps][C]
-    if ((int)W.size() == p.epi.rdot_taps * p.epi.d2s_cout) {
-      memcpy(h->rdot_host.w, W.data(), W.size() * sizeof(float));
-      rc = &h->rdot_host;
-      p.epi.rdot_const = 1;
-    }
-  }
   CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_tc_halo2_kernel<NPL>, L.t1_hi, L.t1_lo, wide ? L.tm_w_wide : L.tm_w, p, L.halo2_na,
-                              L.halo2_nb, wide ? 1 : 0, *rc));
+                              L.halo2_nb, wide ? 1 : 0));
   return 0;
 }
 
@@ -1616,7 +1605,8 @@ static int launch_ds_tile(dcscn_handle* h, DsTileParams p, int ksz, cudaStream_t
   // the kernel's shared-memory carve-up uses the per-pass column count of the instantiated template
   const int tcols = cols <= 4 ? 4 : cols <= 8 ? 8 : cols <= 16 ? 16 : cols <= 24 ? 24 : 32;
   const size_t in_px = ksz == 3 ? (size_t)(kDtT + 2) * kDtS : (size_t)kDtThreads;
-  const size_t cache = ds_tile_caches_depthwise(ksz, p.cin, p.cout) ? (size_t)kDtThreads * kDtCP : 0;   // private depthwise rows
+  p.cache_u = (h->ds_cache && ds_tile_caches_depthwise(ksz, p.cin, p.cout)) ? 1 : 0;
+  const size_t cache = p.cache_u ? (size_t)kDtThreads * kDtCP : 0;   // private depthwise rows
   const size_t smem = (in_px * kDtCP + (size_t)p.cin * tcols + (size_t)ksz * ksz * p.cin + cache) * sizeof(float);
   if (smem > 200 * 1024) return fail("depthwise-separable layer %d -> %d exceeds the kernel's shared memory", p.cin, p.cout);
   unsigned grid;
@@ -2288,8 +2278,8 @@ int dcscn_set_option(dcscn_handle* h, const char* key, int64_t value) {
     h->gather_impl = value ? 1 : 0;
     return 0;
   }
-  if (k == "rdot_const") {
-    h->rdot_const = value ? 1 : 0;
+  if (k == "ds_cache") {
+    h->ds_cache = value ? 1 : 0;
     return 0;
   }
   if (k == "wide_tiles") {

@@ -179,7 +179,10 @@ __device__ __forceinline__ void rdot_accumulate16(const EpiParams& e, const floa
     if (tap < e.rdot_taps) {
       // filter taps staged in shared memory: every lane reads the same address (broadcast, one wavefront)
       const float4* w4 = reinterpret_cast<const float4*>(w_smem + tap * e.d2s_cout + c);
-      float s = v[tap];
+      // The 16 products are summed on their own and added to the running value once: one long fmaf chain over all the
+      // channels of a sub-pixel (96 with the 192-column tiles) lets the rounding error of a partial sum of magnitude ~1e3
+      // accumulate 96 times - on the uniform-noise tiles that alone was ~1e-3 of output error.
+      float s = 0.f;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         float4 w = w4[q];
@@ -188,7 +191,7 @@ __device__ __forceinline__ void rdot_accumulate16(const EpiParams& e, const floa
         s = fmaf(t[4 * q + 2], w.z, s);
         s = fmaf(t[4 * q + 3], w.w, s);
       }
-      v[tap] = s;
+      v[tap] += s;
     }
   }
 }

@@ -177,9 +177,9 @@ int dcscn_get_activation(dcscn_handle* h, const char* tensor, float* host_data, 
  *          "store_mode" 2 | 0 | 1 = fp16 plane stores of the tensor-core epilogues: 32-byte stores with neighbouring lanes
  *          exchanging halves so that each instruction writes 64 contiguous bytes of a pixel (default; streaming 3x3 kernel,
  *          elsewhere like 0), one 32-byte store per lane and plane, or two 16-byte stores (the round-1/2 form, cross-check);
- *          "wide_tiles" 0 | 1 = column tiles of the streaming 3x3 kernel capped at 160 (three TMEM buffers) or at 256 (layers
- *          wider than 160 columns use two buffers and read each input box once per pixel tile);
- *          "rdot_const" 0 | 1 = the fused R-CNN1 epilogue reads its filter from shared memory or from the constant bank;
+ *          "wide_tiles" 1 | 0 = column tiles of the streaming 3x3 kernel capped at 256 (default: layers wider than 160
+ *          columns use two TMEM buffers and read each input box once per pixel tile) or at 160 (three buffers);
+ *          "ds_cache" 1 | 0 = depthwise-separable pixel-shuffler layers keep their depthwise values across column groups;
  *          "h2_probe" 0 | 1 = the issuing thread of the streaming 3x3 kernel probes the next weight stage's barrier before
  *          it issues a stage's UMMAs (hides the barrier round trip), or waits stage by stage;
  *          "gather_impl" 0 | 1 = R-CNN1 gather with four pixels per thread (default where W % 4 == 0) or the generic kernel;

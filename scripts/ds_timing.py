@@ -12,8 +12,9 @@ g = torch.Generator().manual_seed(2)
 x = (torch.rand(256, 48, 48, 1, generator=g) * 255).cuda(); x2 = (torch.rand(256, 192, 192, 1, generator=g) * 255).cuda()
 y = torch.empty_like(x2)
 eng.set_option("timing", 1)
-for _ in range(3): eng.forward(x, x2, y)
-torch.cuda.synchronize()
-tm = eng.timings()
-print("total %.3f ms" % sum(t for _, t in tm))
-for name, t in tm: print("%-24s %.3f" % (name, t))
+for cache in (1, 0, 1, 0):
+    eng.set_option("ds_cache", cache)
+    for _ in range(3): eng.forward(x, x2, y)
+    torch.cuda.synchronize()
+    tm = eng.timings()
+    print("ds_cache=%d total %.3f ms  " % (cache, sum(t for _, t in tm)) + " ".join("%s=%.3f" % (name, t) for name, t in tm))

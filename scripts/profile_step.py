@@ -15,6 +15,10 @@ batch = int(sys.argv[2]) if len(sys.argv) > 2 else bench.BATCH
 prec = E.PRECISION_F16X1 if (len(sys.argv) > 3 and sys.argv[3] == "f16x1") else E.PRECISION_F16X3
 eng = E.Engine(E.make_config(precision=prec))
 eng.set_params(bench.load_weights())
+eng.set_option("graph", 0)                      # one kernel launch per layer for ncu's -k / -s / -c filters
+for kv in filter(None, os.environ.get("DCSCN_OPTS", "").split(",")):   # e.g. DCSCN_OPTS=wide_tiles=1,store_mode=0
+    k, v = kv.split("=")
+    eng.set_option(k, int(v))
 g = torch.Generator().manual_seed(0)
 x = (torch.rand(batch, 48, 48, 1, generator=g) * 255).cuda()
 x2 = (torch.rand(batch, 96, 96, 1, generator=g) * 255).cuda()

@@ -342,11 +342,11 @@ def test_store_modes_write_identical_planes(small):
         eng.set_option("store_mode", 0)
 
 
-def test_wide_tiles_and_constant_bank_rdot_match_the_default_path():
-    """Options "wide_tiles" (CNN2 as one 176-column tile, Up-PS as 2 x 192 on two TMEM buffers) and "rdot_const" (fused
-    R-CNN1 weights from the constant bank) on the L12 x2 checkpoint: same per-column arithmetic, so every layer's planes
-    are bit-identical to the default tiling; the output may differ only by the fp32 summation order of the R-CNN1 partial
-    sums (one partial plane set per sub-pixel instead of two)."""
+def test_wide_tiles_match_the_default_tiling():
+    """Option "wide_tiles" (CNN2 as one 176-column tile, Up-PS as 2 x 192, on two TMEM buffers) on the L12 x2 checkpoint:
+    same per-column arithmetic and the same promotion period, so every layer's planes are bit-identical to the default
+    tiling; the output may differ only by the fp32 summation order of the R-CNN1 partial sums (one partial plane set per
+    sub-pixel instead of two)."""
     w = load_golden_weights("dcscn_L12_F196to48_NIN_A64_PS_R1F32")
     cfg = O.OracleConfig()
     g = torch.Generator().manual_seed(3)
@@ -355,17 +355,18 @@ def test_wide_tiles_and_constant_bank_rdot_match_the_default_path():
     x2 = (torch.rand(n, 2 * h, 2 * wd, 1, generator=g) * 255).numpy()
     y64 = O.Oracle(cfg, w, torch.float64).forward(x.astype(np.float64), x2.astype(np.float64))
     eng = make_engine({}, w)
+    eng.set_option("wide_tiles", 0)
     y0 = gpu_forward(eng, x, x2)
     a0 = {k: eng.get_activation(k, (n, h, wd, c)) for k, c in (("CNN2", 166), ("CNN3", 148), ("B2", 32))}
     err0 = float(np.abs(y0 - y64).max())
-    for opts in ({"wide_tiles": 1}, {"wide_tiles": 1, "rdot_const": 1}, {"wide_tiles": 0, "rdot_const": 1}):
-        for k, v in opts.items():
-            eng.set_option(k, v)
-        y1 = gpu_forward(eng, x, x2)
-        y1b = gpu_forward(eng, x, x2)          # second call: graph replay
-        assert np.array_equal(y1, y1b), opts
-        for k, ref in a0.items():
-            assert np.array_equal(eng.get_activation(k, ref.shape), ref), (opts, k)
-        assert np.abs(y1 - y0).max() <= 2e-4, (opts, float(np.abs(y1 - y0).max()))
-        assert float(np.abs(y1 - y64).max()) <= max(TOL_DEFAULT_STRESS, 1.2 * err0), opts
+    eng.set_option("wide_tiles", 1)
+    y1 = gpu_forward(eng, x, x2)
+    y1b = gpu_forward(eng, x, x2)
+    assert np.array_equal(y1, y1b)
+    for k, ref in a0.items():
+        assert np.array_equal(eng.get_activation(k, ref.shape), ref), k
+    # R-CNN1 sums 864 fp32 products of magnitude up to ~1e3 per pixel on these noise tiles: two summation orders differ by
+    # a few ulp of that magnitude
+    assert np.abs(y1 - y0).max() <= 6e-4, float(np.abs(y1 - y0).max())
+    assert float(np.abs(y1 - y64).max()) <= max(TOL_DEFAULT_STRESS, 1.2 * err0), (float(np.abs(y1 - y64).max()), err0)
     eng.close()

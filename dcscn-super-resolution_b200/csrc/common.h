@@ -88,7 +88,6 @@ struct ConvTCParams {
   int pair_stream;       // conv_tc_pair_kernel: streaming split-accumulator mode (1x1 layers)
   unsigned long long* dbg;   // diagnostic builds (-DDCSCN_H2_DEBUG): per-cluster wait counters, else null
   int h2_nreg;           // leading chunks with one tap per stage (issued by the compile-time-structured loop)
-  int h2_probe;          // the issuing thread probes the next weight stage's barrier before each batch of UMMAs (option "h2_probe")
   EpiParams epi;
 };
 

@@ -140,11 +140,7 @@ __global__ void __launch_bounds__(256, 2) conv_first3x3_kernel(const ConvFirstPa
           t0 = dropout_keep(p.epi.drop_seed, p.epi.drop_layer, base, keep) ? t0 * inv_keep : 0.f;
           t1 = dropout_keep(p.epi.drop_seed, p.epi.drop_layer, base + 1, keep) ? t1 * inv_keep : 0.f;
         }
-        __half h0, l0, h1, l1;
-        split_f16(t0, h0, l0);
-        split_f16(t1, h1, l1);
-        ph[i >> 1] = pack_h2(h0, h1);
-        pl[i >> 1] = pack_h2(l0, l1);
+        split_f16x2(t0, t1, ph[i >> 1], pl[i >> 1]);
       }
       if (active) {
         const size_t off = (size_t)pix * seg.pitch + c0;

@@ -185,7 +185,6 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
       const uint32_t sa_u32 = ptx::smem_u32(smem_a), sb_u32 = ptx::smem_u32(smem_b);
       int sa = 0, sb = 0;
       uint32_t spa = 0, spb = 0;
-      uint32_t b_ready = 0;                                 // the current weight stage was already seen complete (probe of the previous stage)
       // Accumulation slots rotate over the nbuf TMEM buffers: bd = buffer of the current dominant slot, bc = the next one;
       // bit b of `phm` = completed uses of buffer b mod 2 (mbarrier phase parity).  Plain increments and selects instead
       // of slot % nbuf keep all of it in uniform registers.
@@ -226,11 +225,7 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
             const bool seg_end = (dom >= seg_target) || (st + 3 == nst);   // same rule as build_h2_stages
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy, ++st) {
-              if ((!resident || item == cluster_id) && !b_ready) { H2_T0(); ptx::mbar_wait(&b_full[sb], spb); H2_ACC(w_b); }   // resident stages landed during the first item
-              if (p.h2_probe && !resident) {     // look at the next stage's barrier now: the probe's latency hides behind this stage's UMMAs
-                const bool wrap = sb + 1 == num_b;
-                b_ready = ptx::mbar_test(&b_full[wrap ? 0 : sb + 1], wrap ? (spb ^ 1u) : spb);
-              }
+              if (!resident || item == cluster_id) { H2_T0(); ptx::mbar_wait(&b_full[sb], spb); H2_ACC(w_b); }   // resident stages landed during the first item
               ptx::tc_fence_after();
               const uint32_t b_addr = sb_u32 + (uint32_t)sb * (uint32_t)B_STAGE;
               uint32_t bh = desc_lo_t<KC>(b_addr), bl = desc_lo_t<KC>(b_addr + BH_BYTES);
@@ -259,28 +254,22 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
                     ptx::mma_f16_ss_2sm_acc(tmem_d, da_hi, db_hi, idesc);
                   }
                 }
-                if (kt == 4) {
-#pragma unroll
-                  for (int ks = 1; ks < 4; ++ks) {
-                    const uint64_t da_hi = ((uint64_t)kDescHiA << 32) | (ah + 2u * ks), db_hi = ((uint64_t)kDescHiB << 32) | (bh + 2u * ks);
-                    if (NPLANES == 2) {
-                      ptx::mma_f16_ss_2sm_acc(tmem_c, ((uint64_t)kDescHiA << 32) | (al + 2u * ks), db_hi, idesc);
-                      ptx::mma_f16_ss_2sm_acc(tmem_c, da_hi, ((uint64_t)kDescHiB << 32) | (bl + 2u * ks), idesc);
-                    }
-                    ptx::mma_f16_ss_2sm_acc(tmem_d, da_hi, db_hi, idesc);
-                  }
-                } else {
-#pragma unroll 1
-                  for (int ks = 1; ks < kt; ++ks) {
-                    ah += 2; al += 2; bh += 2; bl += 2;
-                    const uint64_t da_hi = ((uint64_t)kDescHiA << 32) | ah, db_hi = ((uint64_t)kDescHiB << 32) | bh;
-                    if (NPLANES == 2) {
-                      ptx::mma_f16_ss_2sm_acc(tmem_c, ((uint64_t)kDescHiA << 32) | al, db_hi, idesc);
-                      ptx::mma_f16_ss_2sm_acc(tmem_c, da_hi, ((uint64_t)kDescHiB << 32) | bl, idesc);
-                    }
-                    ptx::mma_f16_ss_2sm_acc(tmem_d, da_hi, db_hi, idesc);
-                  }
-                }
+                // slices 1 .. kt - 1 as straight-line code for EVERY kt: almost every layer ends in a 16 / 32 / 48-channel tail
+                // chunk (kt = 1 / 2 / 3), and a counted loop costs the single issuing thread ~20 instructions per slice
+                // (loop control, vector -> uniform moves of the advancing descriptors) against ~7 here
+#define H2_SLICE(KS)                                                                                                       \
+  {                                                                                                                        \
+    const uint64_t da_hi = ((uint64_t)kDescHiA << 32) | (ah + 2u * (KS)), db_hi = ((uint64_t)kDescHiB << 32) | (bh + 2u * (KS)); \
+    if (NPLANES == 2) {                                                                                                    \
+      ptx::mma_f16_ss_2sm_acc(tmem_c, ((uint64_t)kDescHiA << 32) | (al + 2u * (KS)), db_hi, idesc);                       \
+      ptx::mma_f16_ss_2sm_acc(tmem_c, da_hi, ((uint64_t)kDescHiB << 32) | (bl + 2u * (KS)), idesc);                       \
+    }                                                                                                                      \
+    ptx::mma_f16_ss_2sm_acc(tmem_d, da_hi, db_hi, idesc);                                                                 \
+  }
+                if (kt >= 2) H2_SLICE(1)
+                if (kt >= 3) H2_SLICE(2)
+                if (kt == 4) H2_SLICE(3)
+#undef H2_SLICE
                 if (!resident) ptx::mma_commit_2sm(&b_empty[sb], 3);
                 if (dy == 2 && dx == 2) ptx::mma_commit_2sm(&a_empty[sa], 3);
                 if (dy == 2 && seg_end) {
@@ -323,8 +312,7 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
             seg_open = false;
           }
           if (e & kH2ChunkFirst) ptx::mbar_wait(&a_full[sa], spa);  // the chunk's halo box serves all its stages
-          if ((!resident || item == cluster_id) && !b_ready) ptx::mbar_wait(&b_full[sb], spb);
-          b_ready = 0;                                              // the table-driven tail does not probe ahead
+          if (!resident || item == cluster_id) ptx::mbar_wait(&b_full[sb], spb);
           ptx::tc_fence_after();
           // low descriptor word (start address >> 4 | LBO) of the A slot's hi plane; slots are 1024-byte aligned
           const uint32_t a_desc0 = (((sa_u32 + (uint32_t)sa * (uint32_t)A_SLOT) & 0x3FFFFu) >> 4) | (1u << 16);
@@ -515,13 +503,11 @@ conv_tc_halo2_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_con
                 uint32_t w0[8], w1[8];                                      // this plane's packed words of chunk j / j + 1
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                  __half ha, la, hb, lb;
-                  split_f16(v0[2 * i], ha, la);
-                  split_f16(v0[2 * i + 1], hb, lb);
-                  w0[i] = pln == 0 ? pack_h2(ha, hb) : pack_h2(la, lb);
-                  split_f16(v1[2 * i], ha, la);
-                  split_f16(v1[2 * i + 1], hb, lb);
-                  w1[i] = pln == 0 ? pack_h2(ha, hb) : pack_h2(la, lb);
+                  uint32_t hh, ll;
+                  split_f16x2(v0[2 * i], v0[2 * i + 1], hh, ll);
+                  w0[i] = pln == 0 ? hh : ll;
+                  split_f16x2(v1[2 * i], v1[2 * i + 1], hh, ll);
+                  w1[i] = pln == 0 ? hh : ll;
                 }
                 // even lane: keeps chunk j, sends chunk j + 1, receives the odd pixel's chunk j;
                 // odd lane:  keeps chunk j + 1, sends chunk j, receives the even pixel's chunk j + 1

@@ -246,7 +246,6 @@ struct dcscn_handle {
   Plan* last_plan = nullptr;
   int gather_impl = 0;               // option "gather_impl": 0 = four pixels per thread when the shape allows, 1 = generic kernel
   int wide_tiles = 1;                // option "wide_tiles": streaming 3x3 kernel with column tiles up to 256 (two TMEM buffers above 160)
-  int h2_probe = 0;                  // option "h2_probe": streaming 3x3 kernel probes the next weight stage's barrier ahead of the UMMAs
   int store_mode = 2;                // option "store_mode": EpiParams::store_mode of every tensor-core launch
   int use_graph = 1;                 // option "graph": replay the per-(n,h,w) launch sequence of a forward as one CUDA graph
   uint64_t graph_epoch = 1;          // bumped by everything a captured launch bakes in (options, weight re-packs)
@@ -609,9 +608,9 @@ static int pack_tc_layer(dcscn_handle* h, TcLayer& t) {
     // Promotion period in (chunk, dx) units of K = 192.  Measured (gpurun_out/seg15.log): with three TMEM buffers
     // (n_pad >= 144) a period of 1 leaves the epilogue one segment (~1.5 us) to drain a slot and the issuer stalls -
     // CNN3 0.85 -> 0.63 ms, CNN4 0.74 -> 0.52 ms at 4; the noise-tile error is flat in this range (1.2-1.35e-3).
-    // Two-buffer tiles (3 * n_pad > 512, option "wide_tiles") keep the period of the narrow tiles they replace: CNN2's
-    // K = 1872 is the layer most sensitive to it (4 units: 1.84e-3 on the noise tiles, 3 units: identical planes to 2 x 96).
-    const int seg = seg_override(t.name, h->seg_chunks > 0 ? h->seg_chunks : ((t.n_pad >= 144 && 3 * t.n_pad <= 512) ? 4 : 3));
+    // Two-buffer tiles (3 * n_pad > 512, option "wide_tiles") stall the issuer at every segment end, so the longer period
+    // pays twice there: CNN2 as one 176-column tile 0.93 -> 0.88 ms at 4 units, noise-tile error unchanged (1.27 -> 1.28e-3).
+    const int seg = seg_override(t.name, h->seg_chunks > 0 ? h->seg_chunks : (t.n_pad >= 144 ? 4 : 3));
     t.h2_seg_units = seg;
     build_h2_stages(t.cin_pad, seg, t.h2_stages, &t.h2_nseg, &t.h2_nreg);
     if ((int)t.h2_stages.size() / 2 > kH2MaxTable) return fail("layer %s: %zu weight stages exceed the kernel's table", t.name.c_str(), t.h2_stages.size());
@@ -1477,7 +1476,6 @@ static int launch_tc_halo2(dcscn_handle* h, const TcLaunch& L, cudaStream_t st) 
   p.g = L.hg;
   p.cluster_size = 2;
   p.seg_chunks = L.halo2_seg;
-  p.h2_probe = h->h2_probe;
 #ifdef DCSCN_H2_DEBUG
   {  // diagnostic build: one counter block per launch, dumped by h2_debug_dump() (scripts/r2_h2_timeline.sh)
     static unsigned long long* d_dbg = nullptr;
@@ -2290,10 +2288,6 @@ int dcscn_set_option(dcscn_handle* h, const char* key, int64_t value) {
       h->plans.clear();
       h->last_plan = nullptr;
     }
-    return 0;
-  }
-  if (k == "h2_probe") {
-    h->h2_probe = value ? 1 : 0;
     return 0;
   }
   if (k == "store_mode") {

@@ -75,22 +75,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
-// Non-blocking probe: has the phase with this parity completed?  Used to look at the NEXT stage's barrier before a batch
-// of UMMAs is issued, so that the ~70 cycles a (successful) try_wait costs the single issuing thread overlap the issue.
-__device__ __forceinline__ uint32_t mbar_test(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, P1;\n\t"
-      "}\n"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok;
-}
-
 // --------------------------------------------------------------------- TMA ----
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");

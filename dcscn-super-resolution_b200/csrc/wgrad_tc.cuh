@@ -148,7 +148,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_consta
       const uint32_t z_hi = st_addr + Z_OFF, z_lo = z_hi + ZP_BYTES;
       const uint32_t keep = (c == c_begin) ? 0u : 1u;      // every tap's accumulator starts from zero in the first chunk
       if (ptx::elect_one()) {
-        for (int j = 0; j < ntap; ++j) {
+        // (up to three taps per CTA: unrolled, so that the descriptor arithmetic of a tap is straight-line uniform code for
+        // the single issuing thread instead of a counted loop with vector -> uniform moves in front of every UMMA)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          if (j >= ntap) break;
           const uint32_t d = tmem_base + (uint32_t)(j * p.n_pad);
           // 16 pixels (rows of 128 bytes) per UMMA; the two small products first, the dominant one last
           if (p.halo) {

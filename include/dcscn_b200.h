@@ -180,8 +180,6 @@ int dcscn_get_activation(dcscn_handle* h, const char* tensor, float* host_data, 
  *          "wide_tiles" 1 | 0 = column tiles of the streaming 3x3 kernel capped at 256 (default: layers wider than 160
  *          columns use two TMEM buffers and read each input box once per pixel tile) or at 160 (three buffers);
  *          "ds_cache" 1 | 0 = depthwise-separable pixel-shuffler layers keep their depthwise values across column groups;
- *          "h2_probe" 0 | 1 = the issuing thread of the streaming 3x3 kernel probes the next weight stage's barrier before
- *          it issues a stage's UMMAs (hides the barrier round trip), or waits stage by stage;
  *          "gather_impl" 0 | 1 = R-CNN1 gather with four pixels per thread (default where W % 4 == 0) or the generic kernel;
  *          "graph" 1 | 0 = replay the launches of a forward (all but the last kernel) as one CUDA graph per (n, h, w) once
  *          the same input pointer has been seen twice in a row (default 1; off while "timing" = 1 or "conv_impl" = 1);

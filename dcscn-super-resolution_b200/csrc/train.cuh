@@ -212,11 +212,7 @@ __global__ void __launch_bounds__(256) last_dgrad_s2d_kernel(const LastDgradPara
             a0 = fmaf(w2.x, dy[t], a0);
             a1 = fmaf(w2.y, dy[t], a1);
           }
-        __half h0, l0, h1, l1;
-        split_f16(a0, h0, l0);
-        split_f16(a1, h1, l1);
-        ph[k] = pack_h2(h0, h1);
-        pl[k] = pack_h2(l0, l1);
+        split_f16x2(a0, a1, ph[k], pl[k]);
       }
       *reinterpret_cast<uint4*>(p.dz_hi + o + c) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
       if (p.dz_lo != nullptr) *reinterpret_cast<uint4*>(p.dz_lo + o + c) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
@@ -288,13 +284,11 @@ __global__ void __launch_bounds__(256) last_dgrad_s2d_rows_kernel(const LastDgra
       if (active) {
         const int x = X / p.r, j = X - x * p.r;
         const size_t o = (orow + x) * p.pitch + (size_t)(i * p.r + j) * p.C + 4 * lane;
-        __half h0, l0, h1, l1, h2, l2, h3, l3;
-        split_f16(a0, h0, l0);
-        split_f16(a1, h1, l1);
-        split_f16(a2, h2, l2);
-        split_f16(a3, h3, l3);
-        *reinterpret_cast<uint2*>(p.dz_hi + o) = make_uint2(pack_h2(h0, h1), pack_h2(h2, h3));
-        if (p.dz_lo != nullptr) *reinterpret_cast<uint2*>(p.dz_lo + o) = make_uint2(pack_h2(l0, l1), pack_h2(l2, l3));
+        uint32_t h01, l01, h23, l23;
+        split_f16x2(a0, a1, h01, l01);
+        split_f16x2(a2, a3, h23, l23);
+        *reinterpret_cast<uint2*>(p.dz_hi + o) = make_uint2(h01, h23);
+        if (p.dz_lo != nullptr) *reinterpret_cast<uint2*>(p.dz_lo + o) = make_uint2(l01, l23);
       }
 #pragma unroll
       for (int rr = 0; rr < 3; ++rr) {
@@ -535,11 +529,7 @@ __global__ void __launch_bounds__(256) act_grad8_kernel(const ActGradParams p) {
         if (c + i + 1 >= p.C) dz[i + 1] = 0.f;
         sb[i] += dz[i];
         sb[i + 1] += dz[i + 1];
-        __half h0, l0, h1, l1;
-        split_f16(dz[i], h0, l0);
-        split_f16(dz[i + 1], h1, l1);
-        ph[i >> 1] = pack_h2(h0, h1);
-        pl[i >> 1] = pack_h2(l0, l1);
+        split_f16x2(dz[i], dz[i + 1], ph[i >> 1], pl[i >> 1]);
       }
       *reinterpret_cast<uint4*>(p.dz_hi + q * p.dz_pitch + c) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
       if (p.dz_lo != nullptr) *reinterpret_cast<uint4*>(p.dz_lo + q * p.dz_pitch + c) = make_uint4(pl[0], pl[1], pl[2], pl[3]);

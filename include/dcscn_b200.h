@@ -179,6 +179,8 @@ int dcscn_get_activation(dcscn_handle* h, const char* tensor, float* host_data, 
  *          elsewhere like 0), one 32-byte store per lane and plane, or two 16-byte stores (the round-1/2 form, cross-check);
  *          "wide_tiles" 1 | 0 = column tiles of the streaming 3x3 kernel capped at 256 (default: layers wider than 160
  *          columns use two TMEM buffers and read each input box once per pixel tile) or at 160 (three buffers);
+ *          "ds_impl" 0 | 1 = depthwise-separable layers on the tile kernels (default) or the first-generation kernels (cross-check);
+ *          "act_grad_impl" 0 | 1 = activation gradients with 16-byte (default) or channel-pair accesses (cross-check);
  *          "ds_cache" 1 | 0 = depthwise-separable pixel-shuffler layers keep their depthwise values across column groups;
  *          "gather_impl" 0 | 1 = R-CNN1 gather with four pixels per thread (default where W % 4 == 0) or the generic kernel;
  *          "graph" 1 | 0 = replay the launches of a forward (all but the last kernel) as one CUDA graph per (n, h, w) once

@@ -51,3 +51,18 @@ def test_no_cpu_fallback():
 def test_missing_library_is_loud(tmp_path):
     with pytest.raises(E.EngineError):
         E.load_library(str(tmp_path / "nope.so"))
+
+
+def test_every_option_key_is_documented_in_the_header():
+    """dcscn_set_option's keys live in csrc/engine.cu; the header is the only documentation a binding author reads, so a
+    key the engine accepts but the header does not mention (or the other way round) is a documentation bug."""
+    src = open(os.path.join(ROOT, "dcscn-super-resolution_b200", "csrc", "engine.cu")).read()
+    body = src[src.index("int dcscn_set_option("):]
+    body = body[:body.index("\nint dcscn_get_timings")] if "\nint dcscn_get_timings" in body else body[:6000]
+    keys = set(re.findall(r'k == "([a-z_0-9]+)"', body))
+    assert {"graph", "store_mode", "wide_tiles", "seg_chunks", "conv_impl", "timing"} <= keys
+    header = open(os.path.join(ROOT, "include", "dcscn_b200.h")).read()
+    doc = header[header.index("int dcscn_set_option") - 6000:header.index("int dcscn_set_option")]
+    documented = set(re.findall(r'"([a-z_0-9]+)"', doc))
+    internal = {"halo_base", "wgrad_halo", "wmap_wide"}        # experiment switches of the A/B scripts, not part of the contract
+    assert keys - internal <= documented, sorted(keys - internal - documented)

@@ -113,3 +113,39 @@ def test_training_step_closed_form():
     lr_t = 0.002 * np.sqrt(1 - 0.999) / (1 - 0.9)
     expect = before[name] - lr_t * (0.1 * gg) / (np.sqrt(0.001 * gg * gg) + 1e-8)
     np.testing.assert_allclose(w[name], expect, rtol=1e-10, atol=1e-12)
+
+
+def test_depthwise_separable_training_step():
+    """The oracle side of the depthwise-separable train-step parity (tests/test_gpu_train.py::test_depthwise_separable_*):
+    tf.nn.separable_conv2d layers (tf_graph.py:155-177) under the loss of DCSCN.py:340-357.  fp64 autograd against finite
+    differences for a depthwise tap, a pointwise weight, a bias and a PReLU slope (with a dropout mask in place); the dead
+    `conv_W` of such layers (created by tf_graph.py:183, appended to self.Weights at :212, never read by the forward)
+    enters only through the L2 term, so its gradient is exactly l2_decay * conv_W and the forward does not depend on it."""
+    cfg = O.OracleConfig(scale=4, layers=3, filters=6, min_filters=3, nin_filters=5, nin_filters2=3, pixel_shuffler_filters=1,
+                         depthwise_separable=True)
+    w = {k: v.astype(np.float64) for k, v in O.he_init_weights(cfg, seed=7).items()}
+    orc = O.Oracle(cfg, w, torch.float64)
+    g = np.random.RandomState(1)
+    n, h, wd = 2, 5, 4
+    x = g.rand(n, h, wd, 1) * 255
+    x2 = g.rand(n, 4 * h, 4 * wd, 1) * 255
+    y = g.rand(n, 4 * h, 4 * wd, 1) * 255
+    masks = {scope: (g.rand(n, cout, h, wd) < 0.8).astype(np.float64)
+             for scope, k, cin, cout, bias, prelu in O.layer_table(cfg) if prelu}
+    mse, loss, grads = orc.loss_and_grads(x, x2, y, keep_prob=0.8, masks=masks)
+    l2 = sum(np.sum(w[nm] ** 2) / 2 for nm in orc.l2_weight_names())
+    assert loss == pytest.approx(mse + cfg.l2_decay * l2, rel=1e-12)
+    for name, idx in (("CNN2/depthwise_W", (0, 2, 1, 0)), ("A1/pointwise_W", (0, 0, 4, 2)), ("Up-PS/Up-PS_CNN/conv_B", (3,)),
+                      ("B1/prelu/B1_prelu", (1,)), ("R-CNN1/depthwise_W", (1, 1, 0, 0)), ("Up-PS2/Up-PS2_CNN/pointwise_W", (0, 0, 2, 1))):
+        eps = 1e-5 * max(1.0, abs(w[name][idx]))
+        w[name][idx] += eps
+        lp = orc.loss_and_grads(x, x2, y, keep_prob=0.8, masks=masks)[1]
+        w[name][idx] -= 2 * eps
+        lm = orc.loss_and_grads(x, x2, y, keep_prob=0.8, masks=masks)[1]
+        w[name][idx] += eps
+        assert grads[name][idx] == pytest.approx((lp - lm) / (2 * eps), rel=5e-4, abs=1e-6), name
+    for scope, *_ in O.layer_table(cfg):
+        np.testing.assert_allclose(grads[scope + "/conv_W"], cfg.l2_decay * w[scope + "/conv_W"], rtol=1e-12, atol=0)
+    y_before = orc.forward(x, x2)
+    w["CNN1/conv_W"] = w["CNN1/conv_W"] + 1.0
+    assert np.array_equal(O.Oracle(cfg, w, torch.float64).forward(x, x2), y_before)
